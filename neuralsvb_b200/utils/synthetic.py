@@ -1,0 +1,185 @@
+"""Deterministic synthetic weights and inputs for the mel-to-waveform path.
+
+There is no network on the build or GPU boxes, so no pretrained vocoder
+checkpoint and no dataset.  Everything here is generated from
+``numpy.random.RandomState`` (bit-stable across numpy versions and machines),
+so the oracle, the golden fixtures, the CUDA parity tests and ``bench.py`` all
+see identical tensors.
+
+Shapes and key names follow the reference checkpoint layout
+(``vocoders/hifigan.py:17-33`` loads ``ckpt['state_dict']['model_gen']`` into
+``HifiGanGenerator`` with weight-norm key names; layer shapes from
+``modules/hifigan/hifigan.py:105-142``).
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+
+def hifigan_config(nsf=True, hop=256):
+    """The hop-256 HiFi-GAN(-NSF) architecture of
+    ``egs/egs_bases/tts/vocoder/hifigan.yaml:3-10`` (+ ``use_pitch_embed``,
+    SURVEY D7) or the hop-128 variant used by the singing configs."""
+    if hop == 256:
+        rates, ksz = [8, 8, 2, 2], [16, 16, 4, 4]
+    elif hop == 128:
+        rates, ksz = [8, 4, 2, 2], [16, 8, 4, 4]
+    else:
+        raise ValueError(f'no stock architecture for hop {hop}')
+    return {
+        'resblock': '1',
+        'upsample_rates': rates,
+        'upsample_kernel_sizes': ksz,
+        'upsample_initial_channel': 512,
+        'resblock_kernel_sizes': [3, 7, 11],
+        'resblock_dilation_sizes': [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+        'use_pitch_embed': bool(nsf),
+        'audio_sample_rate': 22050,
+        'audio_num_mel_bins': 80,
+        'hop_size': hop,
+        'fft_size': 1024,
+        'win_size': 512,
+        'fmin': 80,
+        'fmax': 7600,
+    }
+
+
+def small_config(nsf=True):
+    """A narrow generator (64 initial channels, hop 16) for quick CPU-side
+    parity cases; same topology, every code path exercised."""
+    return {
+        'resblock': '1',
+        'upsample_rates': [4, 2, 2],
+        'upsample_kernel_sizes': [8, 4, 4],
+        'upsample_initial_channel': 64,
+        'resblock_kernel_sizes': [3, 7, 11],
+        'resblock_dilation_sizes': [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+        'use_pitch_embed': bool(nsf),
+        'audio_sample_rate': 22050,
+        'audio_num_mel_bins': 80,
+        'hop_size': 16,
+    }
+
+
+def _normal(rs, shape, std):
+    return (rs.standard_normal(size=shape) * std).astype(np.float32)
+
+
+def _uniform(rs, shape, bound):
+    return rs.uniform(-bound, bound, size=shape).astype(np.float32)
+
+
+def _wn_pair(rs, shape, std, norm_dims):
+    """weight_v ~ N(0, std) and a weight_g that is NOT equal to ||v|| so that
+    weight-norm folding is actually exercised (g = ||v|| * U(0.7, 1.4))."""
+    v = _normal(rs, shape, std)
+    nrm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=norm_dims, keepdims=True))
+    g = (nrm * rs.uniform(0.7, 1.4, size=nrm.shape)).astype(np.float32)
+    return g, v
+
+
+def make_generator_state_dict(h, seed=1234, n_mel=80):
+    """state_dict with the reference's weight-norm key names
+    (``conv_pre.weight_g/weight_v``, ``ups.{i}.*``, ``noise_convs.{i}.*``,
+    ``resblocks.{n}.convs{1,2}.{j}.*``, ``conv_post.*``,
+    ``m_source.l_linear.*``).  Conv weights ~ N(0, 0.01..0.05) in the spirit of
+    ``init_weights`` (``hifigan.py:14-17``); ConvTranspose1d weight-norm is
+    over dim 0 = in-channels."""
+    rs = np.random.RandomState(seed)
+    sd = OrderedDict()
+    c0 = h['upsample_initial_channel']
+    rates = h['upsample_rates']
+    if h['use_pitch_embed']:
+        sd['m_source.l_linear.weight'] = _uniform(rs, (1, 9), 1.0)
+        sd['m_source.l_linear.bias'] = _uniform(rs, (1,), 1.0 / 3.0)
+        for i in range(len(rates)):
+            c_cur = c0 // (2 ** (i + 1))
+            if i + 1 < len(rates):
+                s = int(np.prod(rates[i + 1:]))
+                k = 2 * s
+            else:
+                k = 1
+            b = 4.0 / np.sqrt(k)
+            sd[f'noise_convs.{i}.weight'] = _uniform(rs, (c_cur, 1, k), b)
+            sd[f'noise_convs.{i}.bias'] = _uniform(rs, (c_cur,), b)
+    b = 1.0 / np.sqrt(n_mel * 7)
+    sd['conv_pre.bias'] = _uniform(rs, (c0,), b)
+    g, v = _wn_pair(rs, (c0, n_mel, 7), b, (1, 2))
+    sd['conv_pre.weight_g'], sd['conv_pre.weight_v'] = g, v
+    for i, (u, k) in enumerate(zip(rates, h['upsample_kernel_sizes'])):
+        cin = c0 // (2 ** i)
+        cout = cin // 2
+        sd[f'ups.{i}.bias'] = _uniform(rs, (cout,), 0.05)
+        g, v = _wn_pair(rs, (cin, cout, k), 1.0 / np.sqrt(cin * k / u), (1, 2))
+        sd[f'ups.{i}.weight_g'], sd[f'ups.{i}.weight_v'] = g, v
+    nk = len(h['resblock_kernel_sizes'])
+    for i in range(len(rates)):
+        ch = c0 // (2 ** (i + 1))
+        for j, (k, dil) in enumerate(zip(h['resblock_kernel_sizes'], h['resblock_dilation_sizes'])):
+            n = i * nk + j
+            groups = ['convs1', 'convs2'] if h['resblock'] == '1' else ['convs']
+            for grp in groups:
+                for m in range(len(dil)):
+                    sd[f'resblocks.{n}.{grp}.{m}.bias'] = _uniform(rs, (ch,), 0.05)
+                    g, v = _wn_pair(rs, (ch, ch, k), 1.0 / np.sqrt(ch * k), (1, 2))
+                    sd[f'resblocks.{n}.{grp}.{m}.weight_g'] = g
+                    sd[f'resblocks.{n}.{grp}.{m}.weight_v'] = v
+    ch = c0 // (2 ** len(rates))
+    sd['conv_post.bias'] = _uniform(rs, (1,), 0.05)
+    g, v = _wn_pair(rs, (1, ch, 7), 0.2 / np.sqrt(ch * 7), (1, 2))
+    sd['conv_post.weight_g'], sd['conv_post.weight_v'] = g, v
+    return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v))) for k, v in sd.items())
+
+
+def make_mel_f0(batch, frames, seed=1234, n_mel=80):
+    """SURVEY 8(d) cfg 2 inputs: log10-mel ~ clamp(N(-2.5, 1.2^2), -6, 1.5)
+    (range of ``tts/base.yaml:59-60``), f0 piecewise constant over 8..32-frame
+    segments, voiced w.p. 0.8 with Hz ~ U(100, 500), 0 = unvoiced."""
+    rs = np.random.RandomState(seed)
+    mel = np.clip(rs.standard_normal((batch, n_mel, frames)) * 1.2 - 2.5, -6.0, 1.5).astype(np.float32)
+    f0 = np.zeros((batch, frames), np.float32)
+    for b in range(batch):
+        t = 0
+        while t < frames:
+            seg = int(rs.randint(8, 33))
+            hz = float(rs.uniform(100.0, 500.0)) if rs.uniform() < 0.8 else 0.0
+            f0[b, t:t + seg] = hz
+            t += seg
+    return torch.from_numpy(mel), torch.from_numpy(f0)
+
+
+def make_nsf_noise(batch, samples, seed=1234, harmonics=9):
+    """The three RNG draws of the NSF source in reference order (SURVEY D8;
+    ``source.py:53-56,131-132,397``): rand_ini[B,9] with column 0 zeroed,
+    sine noise randn[B,T,9]; the third draw (noise branch, unused by the
+    generator) is skipped."""
+    rs = np.random.RandomState(seed + 7)
+    rand_ini = rs.uniform(0.0, 1.0, size=(batch, harmonics)).astype(np.float32)
+    rand_ini[:, 0] = 0.0
+    noise = rs.standard_normal(size=(batch, samples, harmonics)).astype(np.float32)
+    return torch.from_numpy(rand_ini), torch.from_numpy(noise)
+
+
+def make_clip(n=44100, sr=22050, seed=1234, f_base=220.0):
+    """SURVEY 8(d) cfg 1 clip: tone + chirp + noise, float32 in [-1, 1]."""
+    rs = np.random.RandomState(seed)
+    t = np.arange(n, dtype=np.float64) / sr
+    wav = 0.3 * np.sin(2 * np.pi * f_base * t) + 0.1 * np.sin(2 * np.pi * (f_base + 330.0 * t) * t) \
+        + 0.01 * rs.standard_normal(n)
+    return np.clip(wav, -1.0, 1.0).astype(np.float32)
+
+
+def make_wave_batch(batch, samples, sr=22050, seed=1234):
+    """Harmonic + noise clips [B, samples] for the STFT-loss / discriminator cases."""
+    rs = np.random.RandomState(seed + 11)
+    out = np.zeros((batch, samples), np.float32)
+    t = np.arange(samples, dtype=np.float64) / sr
+    for b in range(batch):
+        f = rs.uniform(100.0, 400.0)
+        sig = np.zeros(samples)
+        for hnum in range(1, 6):
+            sig += (0.25 / hnum) * np.sin(2 * np.pi * f * hnum * t + rs.uniform(0, 2 * np.pi))
+        sig += 0.02 * rs.standard_normal(samples)
+        out[b] = np.clip(sig, -1.0, 1.0)
+    return torch.from_numpy(out)

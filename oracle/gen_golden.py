@@ -1,0 +1,124 @@
+"""ORACLE tooling (test infrastructure only; see oracle/__init__.py).
+
+Writes tests/golden/*.npz from the UNMODIFIED reference modules under
+/root/reference (via oracle/ref_harness.py).  Build container only; the
+fixtures are committed so the GPU box (no /root/reference) can still check the
+oracle and the CUDA path against reference outputs.
+
+    python -m oracle.gen_golden            # regenerate everything
+
+Inputs and weights are never stored: they are regenerated bit-identically by
+neuralsvb_b200/utils/synthetic.py from the seeds recorded in each fixture.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+from neuralsvb_b200.utils import synthetic as S
+from oracle import ref_harness as R
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+SEED = 1234
+
+FRONTEND_CASES = {
+    # name: (n_samples, fft, hop, win, fmin, fmax)      SURVEY 8(d) cfg 1 + D6 variants
+    'cfg1_win512': (44100, 1024, 256, 512, 80, 7600),
+    'cfg1_win1024': (22050, 1024, 256, 1024, 80, 7600),
+    'svb_hop128': (22050, 512, 128, 512, 50, 11025),
+    'ragged_short': (1000, 1024, 256, 512, 80, 7600),
+}
+
+
+def gen_frontend():
+    R.install()
+    from data_gen.tts.data_gen_utils import process_utterance        # the real reference function
+    out = {}
+    for name, (n, fft, hop, win, fmin, fmax) in FRONTEND_CASES.items():
+        wav = S.make_clip(n, seed=SEED)
+        w2, mel, lin = process_utterance(wav, fft_size=fft, hop_size=hop, win_length=win, num_mels=80,
+                                         fmin=fmin, fmax=fmax, sample_rate=22050, eps=1e-10,
+                                         return_linear=True, min_level_db=-100)
+        out[f'{name}/mel'] = mel.T.astype(np.float32)                # [T, 80] as PWG.wav2spec returns it
+        out[f'{name}/wav_len'] = np.int64(len(w2))
+        out[f'{name}/lin_sub'] = lin.T[::7, ::5].astype(np.float32)
+        out[f'{name}/params'] = np.array([n, fft, hop, win, fmin, fmax], np.int64)
+    np.savez_compressed(os.path.join(OUT, 'frontend.npz'), **out)
+    print('frontend.npz', {k: v.shape for k, v in out.items() if k.endswith('/mel')})
+
+
+GEN_CASES = {
+    # name: (config, B, T_frames, nsf, subsample stride)
+    'small_nsf': ('small', 2, 24, True, 1),
+    'small_plain': ('small', 2, 24, False, 1),
+    'small_ragged': ('small', 1, 37, True, 1),
+    'hop256_t16': ('hop256', 1, 16, True, 1),
+    'hop256_t21_plain': ('hop256', 1, 21, False, 1),
+    'cfg2_b16_t128': ('hop256', 16, 128, True, 61),
+}
+
+
+def _cfg(name, nsf):
+    return S.small_config(nsf) if name == 'small' else S.hifigan_config(nsf)
+
+
+def gen_generator():
+    out = {}
+    for name, (cfg, B, T, nsf, stride) in GEN_CASES.items():
+        h = _cfg(cfg, nsf)
+        hop = int(np.prod(h['upsample_rates']))
+        sd = S.make_generator_state_dict(h, SEED)
+        mel, f0 = S.make_mel_f0(B, T, SEED)
+        model = R.build_generator(h, sd)
+        if nsf:
+            ri, nz = S.make_nsf_noise(B, T * hop, SEED)
+            y = R.run_generator(model, mel, f0, ri, nz)
+            with R.injected_noise(ri, nz), torch.no_grad():
+                f0_up = model.f0_upsamp(f0[:, None]).transpose(1, 2)
+                har, _, _ = model.m_source(f0_up)
+            out[f'{name}/har_sub'] = har[:, :, 0].numpy()[:, ::stride].astype(np.float32)
+        else:
+            y = R.run_generator(model, mel, None)
+        y = y.numpy()[:, 0]
+        out[f'{name}/y_sub'] = y[:, ::stride].astype(np.float32)
+        out[f'{name}/rms'] = np.sqrt((y.astype(np.float64) ** 2).mean(axis=1))
+        out[f'{name}/meta'] = np.array([B, T, int(nsf), stride, hop], np.int64)
+        print(name, y.shape, 'rms', out[f'{name}/rms'].mean())
+    np.savez_compressed(os.path.join(OUT, 'generator.npz'), **out)
+
+
+def gen_losses():
+    R.install()
+    from modules.hifigan.mel_utils import mel_spectrogram
+    from modules.parallel_wavegan.losses.stft_loss import MultiResolutionSTFTLoss, stft
+    out = {}
+    h = S.hifigan_config()
+    y = S.make_wave_batch(2, 8192, seed=SEED)
+    x = (y + 0.05 * S.make_wave_batch(2, 8192, seed=SEED + 1)).clamp(-1, 1)
+    with R.legacy_stft(), torch.no_grad():
+        out['mel_spectrogram/y'] = mel_spectrogram(y, h).numpy().astype(np.float32)          # [2, 80, 32]
+        sc, mag = MultiResolutionSTFTLoss()(x, y)
+        out['mr_stft/sc_mag'] = np.array([float(sc), float(mag)], np.float64)
+        for fs, ss, wl in ((1024, 120, 600), (2048, 240, 1200), (512, 50, 240)):
+            m = stft(x, fs, ss, wl, torch.hann_window(wl))
+            out[f'stft_mag/{fs}'] = m.numpy()[:, ::3, ::7].astype(np.float32)
+            out[f'stft_mag/{fs}_shape'] = np.array(m.shape, np.int64)
+    np.savez_compressed(os.path.join(OUT, 'losses.npz'), **out)
+    print('losses.npz', out['mr_stft/sc_mag'])
+
+
+def main():
+    if not R.available():
+        sys.exit('gen_golden needs /root/reference (build container only)')
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    warnings.simplefilter('ignore')
+    which = sys.argv[1:] or ['frontend', 'generator', 'losses']
+    for w in which:
+        globals()[f'gen_{w}']()
+
+
+if __name__ == '__main__':
+    main()
