@@ -1,0 +1,175 @@
+/*
+ * svb_vocoder.h -- C ABI of libsvb_vocoder.so, the B200 (sm_100a) implementation of the
+ * NeuralSVB mel-to-waveform hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types, no C++ in the
+ * signatures.  Every entry point names the reference interface it replaces.  The reference
+ * is pure Python/PyTorch, so its "FFI" is ctypes: INTEGRATION.md shows the stub a
+ * maintainer adds to vocoders/hifigan.py to bind these.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative svb_status otherwise; nothing
+ *     throws across the ABI; svb_last_error() gives the message for the calling thread.
+ *   - "dev" pointers are device pointers on the handle's device, "host" pointers are host
+ *     memory; all buffers are caller-owned; scratch space is owned by the handle.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     stream-ordered and do not synchronise unless documented (the *_host entry points
+ *     synchronise before returning, like the reference's `.cpu()`).
+ *   - one handle per (process, device); a handle is not thread-safe.
+ *   - all floating-point tensors are fp32, dense, row-major in the stated shape.
+ */
+#ifndef SVB_VOCODER_H_
+#define SVB_VOCODER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB_ABI_VERSION 1
+
+typedef enum svb_status {
+    SVB_OK = 0,
+    SVB_ERR_INVALID = -1,      /* bad argument / shape / config */
+    SVB_ERR_CUDA = -2,         /* a CUDA runtime call or kernel failed */
+    SVB_ERR_STATE = -3,        /* call order violated (e.g. forward before finalize) */
+    SVB_ERR_MISSING = -4,      /* a required weight tensor was never set */
+    SVB_ERR_NOMEM = -5
+} svb_status;
+
+/* arithmetic used for the dense ResBlock / upsampler contractions */
+typedef enum svb_precision {
+    SVB_PREC_FP32 = 0,         /* CUDA-core FFMA, fp32 everywhere                              */
+    SVB_PREC_TF32 = 1,         /* tcgen05 kind::tf32, operands rounded to nearest, fp32 accum   */
+    SVB_PREC_TF32X3 = 2        /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi), ~fp32 accuracy */
+} svb_precision;
+
+#define SVB_MAX_UPS 8
+#define SVB_MAX_RBK 4
+#define SVB_MAX_DIL 4
+
+/* Mirrors the `h` dict given to HifiGanGenerator(h) -- modules/hifigan/hifigan.py:105-142;
+ * values for the shipped model: egs/egs_bases/tts/vocoder/hifigan.yaml:3-12. */
+typedef struct svb_gen_config {
+    int32_t n_mel;                                 /* input channels of conv_pre (80, hifigan.py:118)   */
+    int32_t upsample_initial_channel;              /* 512                                                */
+    int32_t n_ups;                                 /* len(upsample_rates)                                */
+    int32_t upsample_rates[SVB_MAX_UPS];           /* [8,8,2,2]                                          */
+    int32_t upsample_kernel_sizes[SVB_MAX_UPS];    /* [16,16,4,4]                                        */
+    int32_t resblock;                              /* 1 = ResBlock1 (:30-67), 2 = ResBlock2 (:70-91)     */
+    int32_t n_resblock_kernels;                    /* len(resblock_kernel_sizes)                         */
+    int32_t resblock_kernel_sizes[SVB_MAX_RBK];    /* [3,7,11]                                           */
+    int32_t n_dilations;                           /* dilations per ResBlock (3 for '1', 2 for '2')      */
+    int32_t resblock_dilation_sizes[SVB_MAX_RBK][SVB_MAX_DIL];
+    int32_t use_pitch_embed;                       /* NSF source + noise_convs (:111-117,126-132)        */
+    int32_t audio_sample_rate;                     /* 22050                                              */
+    int32_t precision;                             /* svb_precision                                      */
+} svb_gen_config;
+
+typedef struct svb_gen svb_gen_t;                  /* opaque generator handle */
+
+/* Message describing the last failure on the calling thread (never NULL). */
+const char *svb_last_error(void);
+int svb_abi_version(void);
+
+/* ---- HiFi-GAN(-NSF) generator: replaces HifiGanGenerator (modules/hifigan/hifigan.py:104-178)
+ *      as it is built and driven by vocoders/hifigan.py:17-33 (load_model) and :55-69 (spec2wav). */
+
+/* HifiGanGenerator.__init__ (hifigan.py:105-142).  `device` is a CUDA ordinal. */
+int svb_gen_create(const svb_gen_config *cfg, int device, svb_gen_t **out);
+void svb_gen_destroy(svb_gen_t *g);
+
+/* load_state_dict + remove_weight_norm (vocoders/hifigan.py:27-28, hifigan.py:171-178).
+ * `name` is the reference state_dict key with weight norm already folded
+ * ("conv_pre.weight", "ups.0.bias", "resblocks.4.convs2.1.weight", "noise_convs.2.weight",
+ * "m_source.l_linear.weight", ...); `data` is a HOST fp32 tensor in the PyTorch layout
+ * (Conv1d [Cout,Cin,K]; ConvTranspose1d [Cin,Cout,K]; Linear [out,in]; bias [C]). */
+int svb_gen_set_weight(svb_gen_t *g, const char *name, const float *data, const int64_t *shape, int32_t ndim);
+/* weight-norm folding on the device: w = g * v / ||v|| over all dims but 0
+ * (torch.nn.utils.weight_norm dim=0; hifigan.py:35-50,118,124,140).  v_host [d0, inner], g_host [d0]. */
+int svb_fold_weight_norm_host(const float *v_host, const float *g_host, int64_t d0, int64_t inner,
+                              float *w_host, int device);
+/* Packs the weights into kernel layouts and uploads them; checks every tensor is present. */
+int svb_gen_finalize(svb_gen_t *g);
+/* change svb_precision after finalize (repacks nothing; all layouts are kept resident) */
+int svb_gen_set_precision(svb_gen_t *g, int32_t precision);
+
+/* HifiGanGenerator.forward(x, f0) (hifigan.py:144-169), batched, device buffers.
+ *   mel_dev      [B, n_mel, T]   log10-mel
+ *   f0_dev       [B, T] Hz, 0 = unvoiced, or NULL for the non-NSF call model(c)
+ *   rand_ini_dev [B, 9]   initial phases of SineGen (source.py:53-55; column 0 is forced to 0)
+ *   noise_dev    [B, T*hop, 9] standard-normal draw of SineGen (source.py:132)
+ *                both NULL -> drawn in-kernel from a Philox4x32-10 stream keyed by `seed`
+ *   wav_dev      [B, T*hop]      output in (-1, 1)
+ * Stream-ordered, no host synchronisation. */
+int svb_gen_forward(svb_gen_t *g, const float *mel_dev, const float *f0_dev, const float *rand_ini_dev,
+                    const float *noise_dev, uint64_t seed, int32_t B, int32_t T, float *wav_dev, void *stream);
+
+/* HifiGAN.spec2wav(mel, f0=...) (vocoders/hifigan.py:55-69) end to end from HOST memory:
+ *   mel_host [B, T, n_mel] (the reference's [T, 80] frame-major layout, B clips of equal T),
+ *   f0_host [B, T] or NULL, wav_host [B, T*hop].  Copies in (pinned staging, H2D), runs the
+ *   generator, copies out (D2H) and synchronises `stream` before returning. */
+int svb_gen_spec2wav_host(svb_gen_t *g, const float *mel_host, const float *f0_host, uint64_t seed,
+                          int32_t B, int32_t T, float *wav_host, void *stream);
+
+/* Intermediate tap for layer-level parity tests: copies a named activation of the LAST forward
+ * ("har_source" [B,T*hop]; "conv_pre", "ups{i}", "stage{i}" as [B,C,T_i]) to out_dev. */
+int svb_gen_get_tap(svb_gen_t *g, const char *name, float *out_dev, int64_t capacity_floats,
+                    int64_t *shape3, void *stream);
+int64_t svb_gen_hop(const svb_gen_t *g);
+/* number of kernels launched by the last forward / their algorithmic FLOPs (for bench.py) */
+int64_t svb_gen_last_launches(const svb_gen_t *g);
+double svb_gen_last_flops(const svb_gen_t *g);
+/* CUDA-event time (ms) of the last forward on its stream when timing was enabled, else -1 */
+int svb_gen_enable_timing(svb_gen_t *g, int32_t on);
+float svb_gen_last_ms(svb_gen_t *g);
+
+/* ---- STFT / mel front end ------------------------------------------------------------------ */
+
+typedef enum svb_pad_mode {
+    SVB_PAD_CENTER_ZERO = 0,    /* librosa.stft(center=True, pad_mode='constant'): data_gen_utils.py:123-124 */
+    SVB_PAD_CENTER_REFLECT = 1, /* torch.stft(center=True) default: losses/stft_loss.py:26                   */
+    SVB_PAD_HALF_REFLECT = 2    /* reflect-pad (n_fft-hop)/2 then center=False: mel_utils.py:66-71           */
+} svb_pad_mode;
+
+typedef enum svb_spec_out {
+    SVB_OUT_LOG10_MEL = 0,      /* log10(max(eps, mel_basis @ |X|))              data_gen_utils.py:125-134   */
+    SVB_OUT_LN_MEL = 1,         /* ln(max(eps, mel_basis @ sqrt(|X|^2 + 1e-9)))  mel_utils.py:74-76,23-24     */
+    SVB_OUT_MAG = 2,            /* sqrt(max(|X|^2, floor))                       losses/stft_loss.py:31       */
+    SVB_OUT_MAG_RAW = 3         /* |X|                                           data_gen_utils.py:125        */
+} svb_spec_out;
+
+typedef struct svb_stft_config {
+    int32_t n_fft;              /* power of two, 64..4096                         */
+    int32_t hop;
+    int32_t win;                /* periodic hann(win) centred in n_fft            */
+    int32_t pad_mode;           /* svb_pad_mode                                   */
+    int32_t out_kind;           /* svb_spec_out                                   */
+    int32_t clamp_input;        /* clamp(y, -1, 1) first (mel_utils.py:59)        */
+    int32_t n_mels;             /* rows of mel_basis (mel outputs only)           */
+    int32_t frames_major;       /* 1: out [B, frames, n_out]; 0: out [B, n_out, frames] */
+    float eps;                  /* log floor (1e-10 / 1e-5) or magnitude floor (1e-7) */
+} svb_stft_config;
+
+/* number of frames the reference produces for `n` samples under cfg (bit-exact frame indexing):
+ *   CENTER_*: 1 + n / hop ; HALF_REFLECT: 1 + (n + 2*((n_fft-hop)/2) - n_fft) / hop */
+int64_t svb_stft_num_frames(const svb_stft_config *cfg, int64_t n);
+
+/* wav_dev [B, n]; mel_basis_dev [n_mels, n_fft/2+1] (NULL for magnitude outputs);
+ * out_dev [B, frames, n_out] or [B, n_out, frames]  (n_out = n_mels or n_fft/2+1). */
+int svb_stft_forward(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n,
+                     const float *mel_basis_dev, float *out_dev, void *stream);
+
+/* PWG.wav2spec / process_utterance (vocoders/pwg.py:105-122, data_gen_utils.py:93-147) from HOST
+ * memory: wav_host [n] -> mel_host [frames, n_mels] (log10), wav_out_host [frames*hop] (zero padded
+ * on the right, audio.librosa_pad_lr, utils/audio.py:67-76).  mel_basis_host [n_mels, n_fft/2+1].
+ * Returns the frame count (>= 0) or a negative status. */
+int64_t svb_wav2spec_host(const svb_stft_config *cfg, const float *wav_host, int64_t n,
+                          const float *mel_basis_host, float *mel_host, float *wav_out_host, int device,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVB_VOCODER_H_ */

@@ -1,0 +1,22 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution on the C4T layout.  See conv_tc.cu.
+#pragma once
+#include <vector>
+
+#include "conv_ffma.cuh"
+
+namespace svb {
+
+struct TcWeights {
+    float *hi = nullptr;    // tf32-rounded weights in UMMA K-major core-matrix order
+    float *lo = nullptr;    // residual (w - hi) rounded to tf32, for the 3xTF32 mode
+    int KS = 0, Cin = 0, CoutP = 0;
+    int n_tile = 0;         // GEMM columns per CTA (UMMA N)
+    bool ok = false;
+};
+
+// packed_ffma: [KS][Cin][CoutP] fp32 (the FFMA packing).  Allocations are appended to `allocs`.
+int tc_pack_weights(const float *packed_ffma, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs);
+bool tc_supported(const TcWeights &w, const ConvArgs &a);
+int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st);
+
+}  // namespace svb

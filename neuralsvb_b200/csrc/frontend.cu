@@ -1,0 +1,229 @@
+// Fused STFT front end: framing + padding + hann window + real FFT + magnitude + mel matmul + log,
+// one CTA per frame, no cuFFT, no intermediate spectrogram in HBM.
+//
+// Replaces (see include/svb_vocoder.h for the per-mode citations):
+//   process_utterance            data_gen/tts/data_gen_utils.py:123-134   (librosa.stft, |.|, mel @, log10)
+//   mel_spectrogram              modules/hifigan/mel_utils.py:59-76       (reflect pad, torch.stft, sqrt(.+1e-9), ln)
+//   stft() of the STFT losses    modules/parallel_wavegan/losses/stft_loss.py:26-31
+//
+// The frame is loaded bit-reversed into shared memory, transformed by an in-place radix-2 DIT FFT
+// with twiddles from sincospif (accurate to 1 ulp), and the n_fft/2+1 magnitudes stay in shared
+// memory for the mel projection: each warp owns mel bins and walks only the non-zero span of the
+// triangular filter.  HBM traffic = the waveform once (L2 absorbs the n_fft/hop overlap) + the
+// output; the kernel is bandwidth/latency bound (about 18.6 MFLOP per 2 s clip).
+#include "common.cuh"
+
+namespace svb {
+
+struct StftArgs {
+    const float *wav;        // [B, n]
+    const float *mel_basis;  // [n_mels, n_bins] or nullptr
+    float *out;
+    long long n;
+    int n_fft, log2n, hop, win, n_bins, n_mels;
+    int frames;
+    int pad_mode, out_kind, clamp_input, frames_major;
+    float eps;
+};
+
+__device__ __forceinline__ long long reflect_index(long long i, long long n) {
+    // numpy / torch 'reflect' (no edge repeat); valid for |overshoot| < n
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) stft_mel_kernel(StftArgs a) {
+    extern __shared__ float smem[];
+    float *re = smem;                 // [n_fft]
+    float *im = re + a.n_fft;         // [n_fft]
+    float *twc = im + a.n_fft;        // [n_fft/2] cos
+    float *tws = twc + a.n_fft / 2;   // [n_fft/2] -sin
+    float *mag = tws + a.n_fft / 2;   // [n_bins]
+    const int tid = threadIdx.x, N = a.n_fft;
+    const int frame = blockIdx.x, b = blockIdx.y;
+    const float *w = a.wav + (size_t)b * a.n;
+
+    // start of the frame in waveform coordinates
+    long long start;
+    if (a.pad_mode == SVB_PAD_HALF_REFLECT) start = (long long)frame * a.hop - (N - a.hop) / 2;
+    else start = (long long)frame * a.hop - N / 2;
+    const int wl = (N - a.win) / 2;   // window is centred in the n_fft frame (librosa pad_center / torch.stft)
+
+    for (int i = tid; i < N; i += 256) {
+        float v = 0.f;
+        const int wi = i - wl;
+        if (wi >= 0 && wi < a.win) {
+            long long s = start + i;
+            bool ok = true;
+            if (s < 0 || s >= a.n) {
+                if (a.pad_mode == SVB_PAD_CENTER_ZERO) ok = false;
+                else s = reflect_index(s, a.n);
+            }
+            if (ok) {
+                float x = __ldg(w + s);
+                if (a.clamp_input) x = fminf(fmaxf(x, -1.f), 1.f);
+                const float hann = 0.5f - 0.5f * cospif(2.0f * (float)wi / (float)a.win);   // periodic hann
+                v = x * hann;
+            }
+        }
+        const int j = __brev((unsigned)i) >> (32 - a.log2n);
+        re[j] = v;
+        im[j] = 0.f;
+    }
+    for (int i = tid; i < N / 2; i += 256) {
+        float s, c;
+        sincospif(2.0f * (float)i / (float)N, &s, &c);
+        twc[i] = c;
+        tws[i] = -s;
+    }
+    __syncthreads();
+
+    // radix-2 decimation-in-time, natural-order output
+    for (int s = 1; s <= a.log2n; ++s) {
+        const int half = 1 << (s - 1);
+        const int tw_stride = N >> s;
+        for (int i = tid; i < N / 2; i += 256) {
+            const int grp = i / half, k = i - grp * half;
+            const int i0 = grp * 2 * half + k, i1 = i0 + half;
+            const float c = twc[k * tw_stride], sn = tws[k * tw_stride];
+            const float xr = re[i1], xi = im[i1];
+            const float tr = xr * c - xi * sn, ti = xr * sn + xi * c;
+            const float ur = re[i0], ui = im[i0];
+            re[i0] = ur + tr, im[i0] = ui + ti;
+            re[i1] = ur - tr, im[i1] = ui - ti;
+        }
+        __syncthreads();
+    }
+
+    const bool want_mel = a.out_kind == SVB_OUT_LOG10_MEL || a.out_kind == SVB_OUT_LN_MEL;
+    for (int i = tid; i < a.n_bins; i += 256) {
+        const float p = re[i] * re[i] + im[i] * im[i];
+        float m;
+        if (a.out_kind == SVB_OUT_LN_MEL) m = sqrtf(p + 1e-9f);           // mel_utils.py:74
+        else if (a.out_kind == SVB_OUT_MAG) m = sqrtf(fmaxf(p, a.eps));   // stft_loss.py:31
+        else m = sqrtf(p);                                                // np.abs, data_gen_utils.py:125
+        if (want_mel) mag[i] = m;
+        else {
+            const size_t o = a.frames_major ? ((size_t)b * a.frames + frame) * a.n_bins + i
+                                            : ((size_t)b * a.n_bins + i) * a.frames + frame;
+            a.out[o] = m;
+        }
+    }
+    if (!want_mel) return;
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int m = warp; m < a.n_mels; m += 8) {
+        const float *row = a.mel_basis + (size_t)m * a.n_bins;
+        float acc = 0.f;
+        for (int i = lane; i < a.n_bins; i += 32) acc = fmaf(__ldg(row + i), mag[i], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            float v;
+            if (a.out_kind == SVB_OUT_LOG10_MEL) v = log10f(fmaxf(a.eps, acc));   // data_gen_utils.py:134
+            else v = logf(fmaxf(acc, a.eps));                                     // mel_utils.py:23-24
+            const size_t o = a.frames_major ? ((size_t)b * a.frames + frame) * a.n_mels + m
+                                            : ((size_t)b * a.n_mels + m) * a.frames + frame;
+            a.out[o] = v;
+        }
+    }
+}
+
+static int ilog2(int n) {
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return l;
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+extern "C" int64_t svb_stft_num_frames(const svb_stft_config *cfg, int64_t n) {
+    if (!cfg || cfg->hop <= 0) return SVB_ERR_INVALID;
+    if (cfg->pad_mode == SVB_PAD_HALF_REFLECT) {
+        const int64_t padded = n + 2 * (int64_t)((cfg->n_fft - cfg->hop) / 2);
+        return padded < cfg->n_fft ? 0 : 1 + (padded - cfg->n_fft) / cfg->hop;
+    }
+    return 1 + n / cfg->hop;
+}
+
+static int validate_stft(const svb_stft_config *cfg, int64_t n, bool need_mel) {
+    SVB_CHECK(cfg != nullptr, SVB_ERR_INVALID, "stft: null config");
+    SVB_CHECK(cfg->n_fft >= 64 && cfg->n_fft <= 4096 && (cfg->n_fft & (cfg->n_fft - 1)) == 0, SVB_ERR_INVALID,
+              "stft: n_fft %d must be a power of two in [64, 4096]", cfg->n_fft);
+    SVB_CHECK(cfg->hop > 0 && cfg->win > 0 && cfg->win <= cfg->n_fft, SVB_ERR_INVALID,
+              "stft: bad hop %d / win %d", cfg->hop, cfg->win);
+    SVB_CHECK(cfg->pad_mode >= 0 && cfg->pad_mode <= 2 && cfg->out_kind >= 0 && cfg->out_kind <= 3, SVB_ERR_INVALID,
+              "stft: bad pad_mode / out_kind");
+    SVB_CHECK(n >= 1, SVB_ERR_INVALID, "stft: empty waveform");
+    if (cfg->pad_mode != SVB_PAD_CENTER_ZERO) {
+        const int64_t reach = cfg->pad_mode == SVB_PAD_HALF_REFLECT ? (cfg->n_fft - cfg->hop) / 2 : cfg->n_fft / 2;
+        SVB_CHECK(reach < n, SVB_ERR_INVALID, "stft: reflect padding %lld needs a longer signal than %lld",
+                  (long long)reach, (long long)n);   // same condition torch's reflect pad enforces
+    }
+    if (need_mel) SVB_CHECK(cfg->n_mels > 0, SVB_ERR_INVALID, "stft: n_mels must be positive for mel outputs");
+    return SVB_OK;
+}
+
+extern "C" int svb_stft_forward(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n,
+                                const float *mel_basis_dev, float *out_dev, void *stream) {
+    const bool want_mel = cfg && (cfg->out_kind == SVB_OUT_LOG10_MEL || cfg->out_kind == SVB_OUT_LN_MEL);
+    SVB_TRY(validate_stft(cfg, n, want_mel));
+    SVB_CHECK(wav_dev && out_dev && B > 0, SVB_ERR_INVALID, "stft: null buffer or empty batch");
+    SVB_CHECK(!want_mel || mel_basis_dev, SVB_ERR_INVALID, "stft: mel output needs mel_basis_dev");
+    StftArgs a;
+    a.wav = wav_dev, a.mel_basis = mel_basis_dev, a.out = out_dev, a.n = n;
+    a.n_fft = cfg->n_fft, a.log2n = ilog2(cfg->n_fft), a.hop = cfg->hop, a.win = cfg->win;
+    a.n_bins = cfg->n_fft / 2 + 1, a.n_mels = cfg->n_mels;
+    a.frames = (int)svb_stft_num_frames(cfg, n);
+    a.pad_mode = cfg->pad_mode, a.out_kind = cfg->out_kind, a.clamp_input = cfg->clamp_input;
+    a.frames_major = cfg->frames_major, a.eps = cfg->eps;
+    if (a.frames <= 0) return SVB_OK;
+    const size_t smem = (size_t)(3 * a.n_fft + a.n_bins) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        SVB_CUDA(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(a.frames, B);
+    stft_mel_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int64_t svb_wav2spec_host(const svb_stft_config *cfg, const float *wav_host, int64_t n,
+                                     const float *mel_basis_host, float *mel_host, float *wav_out_host, int device,
+                                     void *stream) {
+    SVB_TRY(validate_stft(cfg, n, true));
+    SVB_CHECK(wav_host && mel_basis_host && mel_host, SVB_ERR_INVALID, "wav2spec: null buffer");
+    SVB_CUDA(cudaSetDevice(device));
+    cudaStream_t st = as_stream(stream);
+    const int64_t frames = svb_stft_num_frames(cfg, n);
+    const int n_bins = cfg->n_fft / 2 + 1;
+    float *d_wav = nullptr, *d_basis = nullptr, *d_mel = nullptr;
+    SVB_CUDA(cudaMallocAsync((void **)&d_wav, n * sizeof(float), st));
+    SVB_CUDA(cudaMallocAsync((void **)&d_basis, (size_t)cfg->n_mels * n_bins * sizeof(float), st));
+    SVB_CUDA(cudaMallocAsync((void **)&d_mel, (size_t)frames * cfg->n_mels * sizeof(float), st));
+    SVB_CUDA(cudaMemcpyAsync(d_wav, wav_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    SVB_CUDA(cudaMemcpyAsync(d_basis, mel_basis_host, (size_t)cfg->n_mels * n_bins * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+    svb_stft_config c = *cfg;
+    c.frames_major = 1;
+    int rc = svb_stft_forward(&c, d_wav, 1, n, d_basis, d_mel, stream);
+    if (rc == SVB_OK) {
+        SVB_CUDA(cudaMemcpyAsync(mel_host, d_mel, (size_t)frames * cfg->n_mels * sizeof(float), cudaMemcpyDeviceToHost,
+                                 st));
+    }
+    cudaFreeAsync(d_wav, st), cudaFreeAsync(d_basis, st), cudaFreeAsync(d_mel, st);
+    SVB_CUDA(cudaStreamSynchronize(st));
+    if (rc != SVB_OK) return rc;
+    if (wav_out_host) {
+        // audio.librosa_pad_lr(wav, fft, hop, 1): right-pad to (n // hop + 1) * hop, then wav[:frames * hop]
+        const int64_t out_len = frames * cfg->hop;
+        for (int64_t i = 0; i < out_len; ++i) wav_out_host[i] = i < n ? wav_host[i] : 0.f;
+    }
+    return frames;
+}

@@ -1,0 +1,504 @@
+// HiFi-GAN(-NSF) generator handle: weight packing, workspace planning and the forward schedule.
+// Reference: HifiGanGenerator (modules/hifigan/hifigan.py:104-178) as driven by
+// vocoders/hifigan.py:17-33 (load_model) and :55-69 (spec2wav).
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_ffma.cuh"
+#include "conv_tc.cuh"
+#include "nsf_source.cuh"
+
+using namespace svb;
+
+namespace {
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+};
+
+struct ConvLayer {          // one GEMM-shaped layer on the C4T layout
+    float *w = nullptr;     // FFMA packing [KS][Cin][CoutP]
+    float *b = nullptr;     // [Cout]
+    TcWeights tc;           // tensor-core packing (optional)
+    int Cin = 0, Cout = 0, CoutP = 0, KS = 1, dil = 1, ups_u = 0;
+    double macs_per_row = 0;   // algorithmic MACs per GEMM row (true taps only)
+};
+
+struct NoiseConv {
+    float *w = nullptr, *b = nullptr;
+    int C = 0, K = 1, stride = 1, pad = 0;
+};
+
+struct Stage {
+    int C = 0;              // channels after the upsampler
+    int u = 1;
+    ConvLayer up;
+    NoiseConv noise;
+    // resblocks[j].c1[m], c2[m]  (ResBlock2: only c1 used)
+    std::vector<std::vector<ConvLayer>> c1, c2;
+};
+
+struct Tap {
+    const float *p = nullptr;
+    int C = 0, T = 0, Tp = 0;
+    bool plain = false;     // [B][T] instead of C4T
+};
+
+}  // namespace
+
+struct svb_gen {
+    svb_gen_config cfg{};
+    int device = 0;
+    bool finalized = false;
+    std::map<std::string, HostTensor> host_w;
+    std::vector<void *> dev_allocs;
+
+    ConvLayer conv_pre;
+    std::vector<Stage> stages;
+    float *post_wq = nullptr;
+    float post_bias = 0.f;
+    int post_K = 7, post_C = 0;
+    float *lin_w = nullptr;
+    float lin_b = 0.f;
+    int hop = 1;
+
+    // workspace
+    char *ws = nullptr;
+    size_t ws_cap = 0;
+    int ws_B = 0, ws_T = 0;
+    std::map<std::string, Tap> taps;
+    int last_B = 0;
+
+    // host staging (spec2wav_host)
+    float *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
+    size_t pin_in_cap = 0, pin_out_cap = 0;
+
+    int64_t last_launches = 0;
+    double last_flops = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int upload(svb_gen *g, const std::vector<float> &h, float **out) {
+    float *d = nullptr;
+    SVB_CUDA(cudaMalloc((void **)&d, std::max<size_t>(h.size(), 4) * sizeof(float)));
+    SVB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    g->dev_allocs.push_back(d);
+    *out = d;
+    return SVB_OK;
+}
+
+int get_w(svb_gen *g, const std::string &name, std::vector<int64_t> want, const HostTensor **out) {
+    auto it = g->host_w.find(name);
+    SVB_CHECK(it != g->host_w.end(), SVB_ERR_MISSING, "weight '%s' was never set", name.c_str());
+    if (!want.empty()) {
+        bool ok = it->second.shape.size() == want.size();
+        for (size_t i = 0; ok && i < want.size(); ++i) ok = it->second.shape[i] == want[i];
+        if (!ok) {
+            std::string s;
+            for (auto v : it->second.shape) s += std::to_string(v) + ",";
+            std::string w;
+            for (auto v : want) w += std::to_string(v) + ",";
+            set_error("weight '%s' has shape [%s] but the config needs [%s]", name.c_str(), s.c_str(), w.c_str());
+            return SVB_ERR_INVALID;
+        }
+    }
+    *out = &it->second;
+    return SVB_OK;
+}
+
+// Conv1d weight [Cout][Cin][K] -> [K][Cin][Cout]
+int pack_conv(svb_gen *g, const std::string &prefix, int Cin, int Cout, int K, int dil, ConvLayer *L) {
+    const HostTensor *w, *b;
+    SVB_TRY(get_w(g, prefix + ".weight", {Cout, Cin, K}, &w));
+    SVB_TRY(get_w(g, prefix + ".bias", {Cout}, &b));
+    std::vector<float> p((size_t)K * Cin * Cout);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int k = 0; k < K; ++k) p[((size_t)k * Cin + ci) * Cout + co] = w->data[((size_t)co * Cin + ci) * K + k];
+    L->Cin = Cin, L->Cout = Cout, L->CoutP = Cout, L->KS = K, L->dil = dil, L->ups_u = 0;
+    L->macs_per_row = (double)Cin * Cout * K;
+    SVB_TRY(upload(g, p, &L->w));
+    SVB_TRY(upload(g, b->data, &L->b));
+    SVB_TRY(tc_pack_weights(p.data(), K, Cin, Cout, &L->tc, &g->dev_allocs));
+    return SVB_OK;
+}
+
+// ConvTranspose1d weight [Cin][Cout][K], stride u, padding pad -> polyphase taps:
+// out[q*u + phi][co] = sum_j sum_ci x[q + j][ci] * w[ci][co][phi + pad - j*u]
+int pack_convT(svb_gen *g, const std::string &prefix, int Cin, int Cout, int K, int u, int pad, ConvLayer *L) {
+    const HostTensor *w, *b;
+    SVB_TRY(get_w(g, prefix + ".weight", {Cin, Cout, K}, &w));
+    SVB_TRY(get_w(g, prefix + ".bias", {Cout}, &b));
+    int J = 0;
+    for (int phi = 0; phi < u; ++phi)
+        for (int j = -8; j <= 8; ++j) {
+            const int kk = phi + pad - j * u;
+            if (kk >= 0 && kk < K) J = std::max(J, std::abs(j));
+        }
+    const int KS = 2 * J + 1, CoutP = u * Cout;
+    SVB_CHECK(KS <= 11, SVB_ERR_INVALID, "upsampler %s: kernel %d / stride %d needs %d taps", prefix.c_str(), K, u, KS);
+    std::vector<float> p((size_t)KS * Cin * CoutP, 0.f);
+    for (int kidx = 0; kidx < KS; ++kidx)
+        for (int phi = 0; phi < u; ++phi) {
+            const int kk = phi + pad - (kidx - J) * u;
+            if (kk < 0 || kk >= K) continue;
+            for (int ci = 0; ci < Cin; ++ci)
+                for (int co = 0; co < Cout; ++co)
+                    p[((size_t)kidx * Cin + ci) * CoutP + phi * Cout + co] = w->data[((size_t)ci * Cout + co) * K + kk];
+        }
+    L->Cin = Cin, L->Cout = Cout, L->CoutP = CoutP, L->KS = KS, L->dil = 1, L->ups_u = u;
+    L->macs_per_row = (double)Cin * Cout * K;    // per input row: u outputs x K/u taps
+    SVB_TRY(upload(g, p, &L->w));
+    SVB_TRY(upload(g, b->data, &L->b));
+    SVB_TRY(tc_pack_weights(p.data(), KS, Cin, CoutP, &L->tc, &g->dev_allocs));
+    return SVB_OK;
+}
+
+struct Plan {
+    size_t total = 0;
+    size_t take(size_t bytes) {
+        const size_t off = total;
+        total += (bytes + 255) / 256 * 256;
+        return off;
+    }
+};
+
+struct Buffers {
+    size_t mel, pre, har, nsf;
+    std::vector<size_t> X, A, R, S;
+};
+
+Buffers plan_workspace(const svb_gen *g, int B, int T, size_t *total) {
+    Plan p;
+    Buffers b;
+    b.mel = p.take(c4t_floats(B, g->cfg.n_mel, T) * 4);
+    b.pre = p.take(c4t_floats(B, g->cfg.upsample_initial_channel, T) * 4);
+    b.har = p.take((size_t)B * T * g->hop * 4);
+    b.nsf = p.take(nsf_workspace_bytes(B, T, g->hop));
+    int Ti = T;
+    for (auto &s : g->stages) {
+        Ti *= s.u;
+        const size_t n = c4t_floats(B, s.C, Ti) * 4;
+        b.X.push_back(p.take(n)), b.A.push_back(p.take(n)), b.R.push_back(p.take(n)), b.S.push_back(p.take(n));
+    }
+    *total = p.total;
+    return b;
+}
+
+int run_conv(svb_gen *g, const ConvLayer &L, const float *in, int in_Tp, float *out, int out_Tp, const float *res,
+             int B, int Tq, float in_slope, float scale, int accumulate, cudaStream_t st) {
+    g->last_launches += 1;
+    g->last_flops += 2.0 * L.macs_per_row * (double)B * Tq;
+    ConvArgs a;
+    a.in = in, a.w = L.w, a.bias = L.b, a.res = res, a.out = out;
+    a.B = B, a.Cin = L.Cin, a.in_Tp = in_Tp, a.Cout = L.Cout, a.out_Tp = out_Tp, a.CoutP = L.CoutP, a.Tq = Tq;
+    a.KS = L.KS, a.dil = L.dil, a.ups_u = L.ups_u, a.in_slope = in_slope, a.out_scale = scale, a.accumulate = accumulate;
+    if (g->cfg.precision != SVB_PREC_FP32 && tc_supported(L.tc, a)) return launch_conv_tc(L.tc, a, g->cfg.precision, st);
+    return launch_conv_ffma(a, st);
+}
+
+int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float *f0, const float *rand_ini,
+                 const float *noise, uint64_t seed, int B, int T, float *wav, cudaStream_t st) {
+    SVB_CHECK(g && g->finalized, SVB_ERR_STATE, "generator: forward before finalize");
+    SVB_CHECK(mel && wav && B > 0 && T > 0, SVB_ERR_INVALID, "generator: null buffer or empty batch (B %d T %d)", B, T);
+    SVB_CHECK(!f0 || g->cfg.use_pitch_embed, SVB_ERR_INVALID, "generator: f0 given but use_pitch_embed is off");
+    SVB_CHECK((rand_ini == nullptr) == (noise == nullptr), SVB_ERR_INVALID,
+              "generator: rand_ini and noise must be given together");
+    SVB_CUDA(cudaSetDevice(g->device));
+    size_t need = 0;
+    Buffers bf = plan_workspace(g, B, T, &need);
+    if (need > g->ws_cap) {
+        if (g->ws) SVB_CUDA(cudaFree(g->ws));
+        g->ws = nullptr, g->ws_cap = 0;
+        SVB_CUDA(cudaMalloc((void **)&g->ws, need));
+        g->ws_cap = need, g->ws_B = 0;
+    }
+    if (g->ws_B != B || g->ws_T != T) {   // new shape: the zero padding of every C4T buffer must be rebuilt
+        SVB_CUDA(cudaMemsetAsync(g->ws, 0, need, st));
+        g->ws_B = B, g->ws_T = T;
+    }
+    g->last_launches = 0, g->last_flops = 0, g->last_B = B;
+    g->taps.clear();
+    if (g->timing) SVB_CUDA(cudaEventRecord(g->ev0, st));
+
+    auto F = [&](size_t off) { return reinterpret_cast<float *>(g->ws + off); };
+    const int n_mel = g->cfg.n_mel, C0 = g->cfg.upsample_initial_channel;
+    const int Tp0 = c4t_rows(T);
+    if (mel_frame_major) SVB_TRY(launch_btc_to_c4t(mel, F(bf.mel), B, n_mel, T, Tp0, st));
+    else SVB_TRY(launch_nct_to_c4t(mel, F(bf.mel), B, n_mel, T, Tp0, st));
+    g->last_launches += 1;
+
+    const int Tw = T * g->hop;
+    float *har = nullptr;
+    if (f0) {
+        har = F(bf.har);
+        int l = 0;
+        SVB_TRY(launch_nsf_source(f0, rand_ini, noise, seed, B, T, g->hop, (float)g->cfg.audio_sample_rate, g->lin_w,
+                                  g->lin_b, g->ws + bf.nsf, har, st, &l));
+        g->last_launches += l;
+        g->taps["har_source"] = Tap{har, 1, Tw, 0, true};
+    }
+
+    SVB_TRY(run_conv(g, g->conv_pre, F(bf.mel), Tp0, F(bf.pre), Tp0, nullptr, B, T, 1.f, 1.f, 0, st));
+    g->taps["conv_pre"] = Tap{F(bf.pre), C0, T, Tp0, false};
+
+    const float *x_in = F(bf.pre);
+    int Tin = T, Tin_p = Tp0;
+    const int nk = g->cfg.n_resblock_kernels, nd = g->cfg.n_dilations;
+    for (size_t i = 0; i < g->stages.size(); ++i) {
+        Stage &s = g->stages[i];
+        const int Ti = Tin * s.u, Tip = c4t_rows(Ti);
+        float *X = F(bf.X[i]), *A = F(bf.A[i]), *R = F(bf.R[i]), *S = F(bf.S[i]);
+        // x = ups[i](leaky_relu(x, 0.1))            hifigan.py:153-154
+        SVB_TRY(run_conv(g, s.up, x_in, Tin_p, X, Tip, nullptr, B, Tin, 0.1f, 1.f, 0, st));
+        if (f0) {                                   // x = x + noise_convs[i](har_source)   :155-157
+            SVB_TRY(launch_noise_conv_add(X, B, s.C, Ti, Tip, har, Tw, s.noise.w, s.noise.b, s.noise.K, s.noise.stride,
+                                          s.noise.pad, st));
+            g->last_launches += 1;
+            g->last_flops += 2.0 * B * (double)Ti * s.C * s.noise.K;
+        }
+        g->taps["ups" + std::to_string(i)] = Tap{X, s.C, Ti, Tip, false};
+        // xs = sum_j resblocks[i*nk + j](x) ; x = xs / nk      :158-164
+        for (int j = 0; j < nk; ++j) {
+            for (int m = 0; m < nd; ++m) {
+                const float *xin = m == 0 ? X : R;
+                const bool last = m == nd - 1;
+                float *dst = last ? S : R;
+                const float scale = last ? 1.f / nk : 1.f;
+                const int accum = (last && j > 0) ? 1 : 0;
+                if (g->cfg.resblock == 1) {         // ResBlock1.forward :54-61
+                    SVB_TRY(run_conv(g, s.c1[j][m], xin, Tip, A, Tip, nullptr, B, Ti, 0.1f, 1.f, 0, st));
+                    SVB_TRY(run_conv(g, s.c2[j][m], A, Tip, dst, Tip, xin, B, Ti, 0.1f, scale, accum, st));
+                } else {                            // ResBlock2.forward :81-86
+                    SVB_TRY(run_conv(g, s.c1[j][m], xin, Tip, dst, Tip, xin, B, Ti, 0.1f, scale, accum, st));
+                }
+            }
+        }
+        g->taps["stage" + std::to_string(i)] = Tap{S, s.C, Ti, Tip, false};
+        x_in = S, Tin = Ti, Tin_p = Tip;
+    }
+    // x = tanh(conv_post(leaky_relu(x)))   default slope 0.01   :165-167
+    SVB_TRY(launch_conv_post_tanh(x_in, B, g->post_C, Tin, Tin_p, g->post_wq, g->post_bias, g->post_K, 0.01f, wav, st));
+    g->last_launches += 1;
+    g->last_flops += 2.0 * B * (double)Tin * g->post_C * g->post_K;
+    if (g->timing) SVB_CUDA(cudaEventRecord(g->ev1, st));
+    return SVB_OK;
+}
+
+}  // namespace
+
+extern "C" int svb_gen_create(const svb_gen_config *cfg, int device, svb_gen_t **out) {
+    SVB_CHECK(cfg && out, SVB_ERR_INVALID, "gen_create: null argument");
+    SVB_CHECK(cfg->n_ups >= 1 && cfg->n_ups <= SVB_MAX_UPS, SVB_ERR_INVALID, "gen_create: n_ups %d out of range", cfg->n_ups);
+    SVB_CHECK(cfg->n_resblock_kernels >= 1 && cfg->n_resblock_kernels <= SVB_MAX_RBK, SVB_ERR_INVALID,
+              "gen_create: n_resblock_kernels %d out of range", cfg->n_resblock_kernels);
+    SVB_CHECK(cfg->n_dilations >= 1 && cfg->n_dilations <= SVB_MAX_DIL, SVB_ERR_INVALID, "gen_create: n_dilations %d",
+              cfg->n_dilations);
+    SVB_CHECK(cfg->resblock == 1 || cfg->resblock == 2, SVB_ERR_INVALID, "gen_create: resblock must be 1 or 2");
+    SVB_CHECK(cfg->n_mel > 0 && cfg->n_mel % 4 == 0, SVB_ERR_INVALID, "gen_create: n_mel %d must be a multiple of 4",
+              cfg->n_mel);
+    SVB_CHECK(cfg->precision >= 0 && cfg->precision <= 2, SVB_ERR_INVALID, "gen_create: bad precision %d", cfg->precision);
+    const int cfin = cfg->upsample_initial_channel >> cfg->n_ups;
+    SVB_CHECK(cfin >= 4 && (cfin << cfg->n_ups) == cfg->upsample_initial_channel && cfin % 4 == 0, SVB_ERR_INVALID,
+              "gen_create: upsample_initial_channel %d must stay a multiple of 4 after %d halvings",
+              cfg->upsample_initial_channel, cfg->n_ups);
+    for (int j = 0; j < cfg->n_resblock_kernels; ++j) {
+        const int k = cfg->resblock_kernel_sizes[j];
+        SVB_CHECK(k % 2 == 1 && k >= 1 && k <= 11, SVB_ERR_INVALID, "gen_create: resblock kernel %d unsupported", k);
+        for (int m = 0; m < cfg->n_dilations; ++m)
+            SVB_CHECK((k - 1) / 2 * cfg->resblock_dilation_sizes[j][m] <= kPad && cfg->resblock_dilation_sizes[j][m] >= 1,
+                      SVB_ERR_INVALID, "gen_create: kernel %d dilation %d exceeds the %d-row halo", k,
+                      cfg->resblock_dilation_sizes[j][m], kPad);
+    }
+    int count = 0;
+    SVB_CUDA(cudaGetDeviceCount(&count));
+    SVB_CHECK(device >= 0 && device < count, SVB_ERR_INVALID, "gen_create: device %d of %d", device, count);
+    SVB_CUDA(cudaSetDevice(device));
+    svb_gen *g = new (std::nothrow) svb_gen();
+    SVB_CHECK(g, SVB_ERR_NOMEM, "gen_create: out of host memory");
+    g->cfg = *cfg, g->device = device;
+    g->hop = 1;
+    for (int i = 0; i < cfg->n_ups; ++i) g->hop *= cfg->upsample_rates[i];
+    SVB_CUDA(cudaEventCreate(&g->ev0));
+    SVB_CUDA(cudaEventCreate(&g->ev1));
+    *out = g;
+    return SVB_OK;
+}
+
+extern "C" void svb_gen_destroy(svb_gen_t *g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    for (void *p : g->dev_allocs) cudaFree(p);
+    if (g->ws) cudaFree(g->ws);
+    if (g->pin_in) cudaFreeHost(g->pin_in);
+    if (g->pin_out) cudaFreeHost(g->pin_out);
+    if (g->dev_in) cudaFree(g->dev_in);
+    if (g->dev_out) cudaFree(g->dev_out);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    delete g;
+}
+
+extern "C" int svb_gen_set_weight(svb_gen_t *g, const char *name, const float *data, const int64_t *shape, int32_t ndim) {
+    SVB_CHECK(g && name && data && shape && ndim >= 1 && ndim <= 4, SVB_ERR_INVALID, "set_weight: bad argument");
+    SVB_CHECK(!g->finalized, SVB_ERR_STATE, "set_weight('%s') after finalize", name);
+    HostTensor t;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        SVB_CHECK(shape[i] > 0, SVB_ERR_INVALID, "set_weight('%s'): non-positive dim", name);
+        t.shape.push_back(shape[i]);
+        n *= (size_t)shape[i];
+    }
+    t.data.assign(data, data + n);
+    g->host_w[name] = std::move(t);
+    return SVB_OK;
+}
+
+extern "C" int svb_gen_finalize(svb_gen_t *g) {
+    SVB_CHECK(g, SVB_ERR_INVALID, "finalize: null handle");
+    SVB_CHECK(!g->finalized, SVB_ERR_STATE, "finalize called twice");
+    SVB_CUDA(cudaSetDevice(g->device));
+    const svb_gen_config &c = g->cfg;
+    const int C0 = c.upsample_initial_channel;
+    SVB_TRY(pack_conv(g, "conv_pre", c.n_mel, C0, 7, 1, &g->conv_pre));          // hifigan.py:118
+    int cin = C0;
+    g->stages.resize(c.n_ups);
+    for (int i = 0; i < c.n_ups; ++i) {
+        Stage &s = g->stages[i];
+        const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+        s.C = cin / 2, s.u = u;
+        SVB_CHECK(k >= u && (k - u) % 2 == 0, SVB_ERR_INVALID, "upsampler %d: kernel %d / rate %d unsupported", i, k, u);
+        SVB_TRY(pack_convT(g, "ups." + std::to_string(i), cin, s.C, k, u, (k - u) / 2, &s.up));   // :122-125
+        if (c.use_pitch_embed) {                                                                   // :126-132
+            int stride = 1;
+            for (int r = i + 1; r < c.n_ups; ++r) stride *= c.upsample_rates[r];
+            const bool last = i + 1 == c.n_ups;
+            s.noise.C = s.C, s.noise.K = last ? 1 : 2 * stride, s.noise.stride = last ? 1 : stride;
+            s.noise.pad = last ? 0 : stride / 2;
+            const HostTensor *w, *b;
+            SVB_TRY(get_w(g, "noise_convs." + std::to_string(i) + ".weight", {s.C, 1, s.noise.K}, &w));
+            SVB_TRY(get_w(g, "noise_convs." + std::to_string(i) + ".bias", {s.C}, &b));
+            SVB_TRY(upload(g, w->data, &s.noise.w));
+            SVB_TRY(upload(g, b->data, &s.noise.b));
+        }
+        s.c1.resize(c.n_resblock_kernels), s.c2.resize(c.n_resblock_kernels);
+        for (int j = 0; j < c.n_resblock_kernels; ++j) {
+            const int n = i * c.n_resblock_kernels + j, rk = c.resblock_kernel_sizes[j];
+            s.c1[j].resize(c.n_dilations), s.c2[j].resize(c.n_dilations);
+            for (int m = 0; m < c.n_dilations; ++m) {
+                const int d = c.resblock_dilation_sizes[j][m];
+                const std::string base = "resblocks." + std::to_string(n);
+                if (c.resblock == 1) {
+                    SVB_TRY(pack_conv(g, base + ".convs1." + std::to_string(m), s.C, s.C, rk, d, &s.c1[j][m]));
+                    SVB_TRY(pack_conv(g, base + ".convs2." + std::to_string(m), s.C, s.C, rk, 1, &s.c2[j][m]));
+                } else {
+                    SVB_TRY(pack_conv(g, base + ".convs." + std::to_string(m), s.C, s.C, rk, d, &s.c1[j][m]));
+                }
+            }
+        }
+        cin = s.C;
+    }
+    {   // conv_post: Conv1d(ch, 1, 7, padding 3)   :140
+        const HostTensor *w, *b;
+        SVB_TRY(get_w(g, "conv_post.weight", {1, cin, 7}, &w));
+        SVB_TRY(get_w(g, "conv_post.bias", {1}, &b));
+        std::vector<float> p((size_t)cin * 7);
+        for (int cq = 0; cq < cin / 4; ++cq)
+            for (int k = 0; k < 7; ++k)
+                for (int e = 0; e < 4; ++e) p[((size_t)cq * 7 + k) * 4 + e] = w->data[(size_t)(cq * 4 + e) * 7 + k];
+        SVB_TRY(upload(g, p, &g->post_wq));
+        g->post_bias = b->data[0], g->post_K = 7, g->post_C = cin;
+    }
+    if (c.use_pitch_embed) {   // m_source.l_linear: Linear(9, 1)   source.py:378
+        const HostTensor *w, *b;
+        SVB_TRY(get_w(g, "m_source.l_linear.weight", {1, 9}, &w));
+        SVB_TRY(get_w(g, "m_source.l_linear.bias", {1}, &b));
+        SVB_TRY(upload(g, w->data, &g->lin_w));
+        g->lin_b = b->data[0];
+    }
+    g->host_w.clear();
+    g->finalized = true;
+    return SVB_OK;
+}
+
+extern "C" int svb_gen_set_precision(svb_gen_t *g, int32_t precision) {
+    SVB_CHECK(g && precision >= 0 && precision <= 2, SVB_ERR_INVALID, "set_precision: bad argument");
+    g->cfg.precision = precision;
+    return SVB_OK;
+}
+
+extern "C" int svb_gen_forward(svb_gen_t *g, const float *mel_dev, const float *f0_dev, const float *rand_ini_dev,
+                               const float *noise_dev, uint64_t seed, int32_t B, int32_t T, float *wav_dev, void *stream) {
+    return forward_impl(g, mel_dev, false, f0_dev, rand_ini_dev, noise_dev, seed, B, T, wav_dev, as_stream(stream));
+}
+
+extern "C" int svb_gen_spec2wav_host(svb_gen_t *g, const float *mel_host, const float *f0_host, uint64_t seed, int32_t B,
+                                     int32_t T, float *wav_host, void *stream) {
+    SVB_CHECK(g && g->finalized, SVB_ERR_STATE, "spec2wav: generator not finalized");
+    SVB_CHECK(mel_host && wav_host && B > 0 && T > 0, SVB_ERR_INVALID, "spec2wav: null buffer or empty input");
+    SVB_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = as_stream(stream);
+    const size_t n_mel = (size_t)B * T * g->cfg.n_mel, n_f0 = f0_host ? (size_t)B * T : 0;
+    const size_t n_in = n_mel + n_f0, n_out = (size_t)B * T * g->hop;
+    if (n_in > g->pin_in_cap) {
+        if (g->pin_in) cudaFreeHost(g->pin_in);
+        if (g->dev_in) cudaFree(g->dev_in);
+        g->pin_in = nullptr, g->dev_in = nullptr, g->pin_in_cap = 0;
+        SVB_CUDA(cudaMallocHost((void **)&g->pin_in, n_in * 4));
+        SVB_CUDA(cudaMalloc((void **)&g->dev_in, n_in * 4));
+        g->pin_in_cap = n_in;
+    }
+    if (n_out > g->pin_out_cap) {
+        if (g->pin_out) cudaFreeHost(g->pin_out);
+        if (g->dev_out) cudaFree(g->dev_out);
+        g->pin_out = nullptr, g->dev_out = nullptr, g->pin_out_cap = 0;
+        SVB_CUDA(cudaMallocHost((void **)&g->pin_out, n_out * 4));
+        SVB_CUDA(cudaMalloc((void **)&g->dev_out, n_out * 4));
+        g->pin_out_cap = n_out;
+    }
+    memcpy(g->pin_in, mel_host, n_mel * 4);
+    if (f0_host) memcpy(g->pin_in + n_mel, f0_host, n_f0 * 4);
+    SVB_CUDA(cudaMemcpyAsync(g->dev_in, g->pin_in, n_in * 4, cudaMemcpyHostToDevice, st));
+    SVB_TRY(forward_impl(g, g->dev_in, true, f0_host ? g->dev_in + n_mel : nullptr, nullptr, nullptr, seed, B, T,
+                         g->dev_out, st));
+    SVB_CUDA(cudaMemcpyAsync(g->pin_out, g->dev_out, n_out * 4, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    memcpy(wav_host, g->pin_out, n_out * 4);
+    return SVB_OK;
+}
+
+extern "C" int svb_gen_get_tap(svb_gen_t *g, const char *name, float *out_dev, int64_t capacity_floats, int64_t *shape3,
+                               void *stream) {
+    SVB_CHECK(g && name && out_dev && shape3, SVB_ERR_INVALID, "get_tap: null argument");
+    auto it = g->taps.find(name);
+    SVB_CHECK(it != g->taps.end(), SVB_ERR_INVALID, "get_tap: no activation named '%s' in the last forward", name);
+    const Tap &t = it->second;
+    const int B = g->last_B;
+    shape3[0] = B, shape3[1] = t.C, shape3[2] = t.T;
+    SVB_CHECK((int64_t)B * t.C * t.T <= capacity_floats, SVB_ERR_INVALID, "get_tap: buffer too small");
+    cudaStream_t st = as_stream(stream);
+    if (t.plain) SVB_CUDA(cudaMemcpyAsync(out_dev, t.p, (size_t)B * t.T * 4, cudaMemcpyDeviceToDevice, st));
+    else SVB_TRY(launch_c4t_to_nct(t.p, out_dev, B, t.C, t.T, t.Tp, st));
+    return SVB_OK;
+}
+
+extern "C" int64_t svb_gen_hop(const svb_gen_t *g) { return g ? g->hop : 0; }
+extern "C" int64_t svb_gen_last_launches(const svb_gen_t *g) { return g ? g->last_launches : 0; }
+extern "C" double svb_gen_last_flops(const svb_gen_t *g) { return g ? g->last_flops : 0.0; }
+extern "C" int svb_gen_enable_timing(svb_gen_t *g, int32_t on) {
+    SVB_CHECK(g, SVB_ERR_INVALID, "enable_timing: null handle");
+    g->timing = on != 0;
+    return SVB_OK;
+}
+extern "C" float svb_gen_last_ms(svb_gen_t *g) {
+    if (!g || !g->timing) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(g->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}

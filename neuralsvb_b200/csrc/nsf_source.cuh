@@ -1,0 +1,15 @@
+// NSF harmonic source (SineGen + SourceModuleHnNSF) on the device.  See nsf_source.cu.
+#pragma once
+#include "common.cuh"
+
+namespace svb {
+
+size_t nsf_workspace_bytes(int B, int F, int U);
+
+// f0 [B,F] Hz (0 = unvoiced); rand_ini [B,9] / noise [B,F*U,9] or both nullptr (Philox from `seed`);
+// lin_w_dev [9] device, lin_b host scalar (m_source.l_linear); har [B, F*U] output.
+int launch_nsf_source(const float *f0, const float *rand_ini, const float *noise, uint64_t seed, int B, int F, int U,
+                      float sr, const float *lin_w_dev, float lin_b, void *workspace, float *har, cudaStream_t st,
+                      int *launches);
+
+}  // namespace svb

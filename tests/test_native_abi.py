@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
+exports every symbol include/svb_vocoder.h declares.  No compute calls (no GPU here)."""
+import ctypes
+import os
+
+import pytest
+
+from neuralsvb_b200 import _native
+
+
+@pytest.fixture(scope='module')
+def built():
+    try:
+        return _native.build()
+    except RuntimeError as e:          # no nvcc on this box: the prebuilt library must already be there
+        if os.path.exists(_native.LIB_PATH):
+            return _native.LIB_PATH
+        pytest.fail(str(e))
+
+
+def test_library_exports_every_declared_symbol(built):
+    l = ctypes.CDLL(built)
+    declared = _native.declared_symbols()
+    assert len(declared) >= 15
+    missing = [s for s in declared if not hasattr(l, s)]
+    assert not missing, f'declared in include/svb_vocoder.h but not exported: {missing}'
+
+
+def test_binding_covers_every_declared_symbol():
+    declared = set(_native.declared_symbols())
+    bound = set(_native._PROTOS)
+    assert declared <= bound, f'no ctypes prototype for {sorted(declared - bound)}'
+
+
+def test_abi_version_and_error_string(built):
+    l = _native.lib()
+    assert l.svb_abi_version() == 1
+    assert isinstance(l.svb_last_error(), bytes)
+
+
+def test_struct_layout_matches_header():
+    # 3 + 8 + 8 + 2 + 4 + 1 + 16 + 3 int32 fields
+    assert ctypes.sizeof(_native.GenConfig) == 4 * (3 + 8 + 8 + 2 + 4 + 1 + 16 + 3)
+    assert ctypes.sizeof(_native.StftConfig) == 4 * 9
+
+
+def test_argument_validation_without_gpu(built):
+    l = _native.lib()
+    # null config -> SVB_ERR_INVALID before any CUDA call
+    assert l.svb_stft_num_frames(None, 100) < 0
+    c = _native.StftConfig(1024, 256, 512, _native.PAD_CENTER_ZERO, _native.OUT_LOG10_MEL, 0, 80, 1, 1e-10)
+    assert l.svb_stft_num_frames(ctypes.byref(c), 44100) == 173          # 1 + n // hop
+    assert l.svb_stft_num_frames(ctypes.byref(c), 1000) == 4
+    c.pad_mode = _native.PAD_HALF_REFLECT
+    assert l.svb_stft_num_frames(ctypes.byref(c), 32768) == 128          # T_wav / hop exactly
+    c.n_fft = 1000                                                      # not a power of two
+    rc = l.svb_stft_forward(ctypes.byref(c), None, 1, 100, None, None, None)
+    assert rc == -1 and b'power of two' in l.svb_last_error()
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from neuralsvb_b200.modules.hifigan.hifigan import HifiGanGenerator
+    from neuralsvb_b200.utils import synthetic as S
+    h = S.small_config()
+    m = HifiGanGenerator(h)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.zeros(1, 80, 8))
+    from neuralsvb_b200.vocoders.hifigan import HifiGAN
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        HifiGAN.wav2spec(S.make_clip(2048), hp=S.hifigan_config())
