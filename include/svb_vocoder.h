@@ -125,6 +125,20 @@ double svb_gen_last_flops(const svb_gen_t *g);
 int svb_gen_enable_timing(svb_gen_t *g, int32_t on);
 float svb_gen_last_ms(svb_gen_t *g);
 
+/* One convolution layer of the generator on PyTorch-layout device tensors, through the CUDA-core
+ * (precision 0) or tcgen05 (1, 2) kernel -- for kernel-level parity tests and per-layer timing.
+ *   y = out_scale * (conv(leaky_relu(x, in_slope)) + bias [+ res])
+ *   transposed_stride = 0: Conv1d(Cin, Cout, K, dilation=dil, padding=dil*(K-1)/2), w_host [Cout,Cin,K]
+ *                          (F.conv1d; hifigan.py:30-61)
+ *   transposed_stride = u: ConvTranspose1d(Cin, Cout, K, stride=u, padding=(K-u)/2), w_host [Cin,Cout,K]
+ *                          (F.conv_transpose1d; hifigan.py:122-125)
+ * x [B,Cin,T], res / y [B,Cout,T or T*u].  Runs 1 warm-up + `iters` timed launches; *avg_ms = mean
+ * CUDA-event time per launch.  Synchronises `stream`. */
+int svb_conv1d_run(const float *x_nct_dev, const float *w_host, const float *bias_host, const float *res_nct_dev,
+                   int32_t B, int32_t Cin, int32_t Cout, int32_t T, int32_t K, int32_t dil,
+                   int32_t transposed_stride, float in_slope, float out_scale, int32_t precision, int32_t iters,
+                   float *y_nct_dev, float *avg_ms, void *stream);
+
 /* ---- STFT / mel front end ------------------------------------------------------------------ */
 
 typedef enum svb_pad_mode {

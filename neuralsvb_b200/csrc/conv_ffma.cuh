@@ -1,6 +1,8 @@
 // fp32 CUDA-core kernels of the generator (conv_pre, upsamplers, NSF injection, conv_post and the
 // SVB_PREC_FP32 ResBlock path).  Declarations; definitions in conv_ffma.cu.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace svb {
@@ -43,5 +45,9 @@ int launch_noise_conv_add(float *x, int B, int C, int T, int Tp, const float *ha
 // wav[b][t] = tanh(bias + sum_{ci,k} w[ci][k] * lrelu(x[b][t+k-3][ci], slope))   (hifigan.py:165-167)
 int launch_conv_post_tanh(const float *x, int B, int C, int T, int Tp, const float *wq, float bias, int K,
                           float slope, float *wav, cudaStream_t st);
+
+// host-side weight packing (layer_api.cu)
+std::vector<float> pack_conv_weights(const float *w, int Cout, int Cin, int K);
+std::vector<float> pack_convT_weights(const float *w, int Cin, int Cout, int K, int u, int pad, int *KS_out);
 
 }  // namespace svb

@@ -111,15 +111,11 @@ int get_w(svb_gen *g, const std::string &name, std::vector<int64_t> want, const 
     return SVB_OK;
 }
 
-// Conv1d weight [Cout][Cin][K] -> [K][Cin][Cout]
 int pack_conv(svb_gen *g, const std::string &prefix, int Cin, int Cout, int K, int dil, ConvLayer *L) {
     const HostTensor *w, *b;
     SVB_TRY(get_w(g, prefix + ".weight", {Cout, Cin, K}, &w));
     SVB_TRY(get_w(g, prefix + ".bias", {Cout}, &b));
-    std::vector<float> p((size_t)K * Cin * Cout);
-    for (int co = 0; co < Cout; ++co)
-        for (int ci = 0; ci < Cin; ++ci)
-            for (int k = 0; k < K; ++k) p[((size_t)k * Cin + ci) * Cout + co] = w->data[((size_t)co * Cin + ci) * K + k];
+    const std::vector<float> p = pack_conv_weights(w->data.data(), Cout, Cin, K);
     L->Cin = Cin, L->Cout = Cout, L->CoutP = Cout, L->KS = K, L->dil = dil, L->ups_u = 0;
     L->macs_per_row = (double)Cin * Cout * K;
     SVB_TRY(upload(g, p, &L->w));
@@ -128,34 +124,18 @@ int pack_conv(svb_gen *g, const std::string &prefix, int Cin, int Cout, int K, i
     return SVB_OK;
 }
 
-// ConvTranspose1d weight [Cin][Cout][K], stride u, padding pad -> polyphase taps:
-// out[q*u + phi][co] = sum_j sum_ci x[q + j][ci] * w[ci][co][phi + pad - j*u]
 int pack_convT(svb_gen *g, const std::string &prefix, int Cin, int Cout, int K, int u, int pad, ConvLayer *L) {
     const HostTensor *w, *b;
     SVB_TRY(get_w(g, prefix + ".weight", {Cin, Cout, K}, &w));
     SVB_TRY(get_w(g, prefix + ".bias", {Cout}, &b));
-    int J = 0;
-    for (int phi = 0; phi < u; ++phi)
-        for (int j = -8; j <= 8; ++j) {
-            const int kk = phi + pad - j * u;
-            if (kk >= 0 && kk < K) J = std::max(J, std::abs(j));
-        }
-    const int KS = 2 * J + 1, CoutP = u * Cout;
+    int KS = 0;
+    const std::vector<float> p = pack_convT_weights(w->data.data(), Cin, Cout, K, u, pad, &KS);
     SVB_CHECK(KS <= 11, SVB_ERR_INVALID, "upsampler %s: kernel %d / stride %d needs %d taps", prefix.c_str(), K, u, KS);
-    std::vector<float> p((size_t)KS * Cin * CoutP, 0.f);
-    for (int kidx = 0; kidx < KS; ++kidx)
-        for (int phi = 0; phi < u; ++phi) {
-            const int kk = phi + pad - (kidx - J) * u;
-            if (kk < 0 || kk >= K) continue;
-            for (int ci = 0; ci < Cin; ++ci)
-                for (int co = 0; co < Cout; ++co)
-                    p[((size_t)kidx * Cin + ci) * CoutP + phi * Cout + co] = w->data[((size_t)ci * Cout + co) * K + kk];
-        }
-    L->Cin = Cin, L->Cout = Cout, L->CoutP = CoutP, L->KS = KS, L->dil = 1, L->ups_u = u;
+    L->Cin = Cin, L->Cout = Cout, L->CoutP = u * Cout, L->KS = KS, L->dil = 1, L->ups_u = u;
     L->macs_per_row = (double)Cin * Cout * K;    // per input row: u outputs x K/u taps
     SVB_TRY(upload(g, p, &L->w));
     SVB_TRY(upload(g, b->data, &L->b));
-    SVB_TRY(tc_pack_weights(p.data(), KS, Cin, CoutP, &L->tc, &g->dev_allocs));
+    SVB_TRY(tc_pack_weights(p.data(), KS, Cin, u * Cout, &L->tc, &g->dev_allocs));
     return SVB_OK;
 }
 
