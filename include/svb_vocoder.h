@@ -42,7 +42,9 @@ typedef enum svb_status {
 typedef enum svb_precision {
     SVB_PREC_FP32 = 0,         /* CUDA-core FFMA, fp32 everywhere                              */
     SVB_PREC_TF32 = 1,         /* tcgen05 kind::tf32, operands rounded to nearest, fp32 accum   */
-    SVB_PREC_TF32X3 = 2        /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi), ~fp32 accuracy */
+    SVB_PREC_TF32X3 = 2,       /* tcgen05 3xTF32 split (hi*hi + hi*lo + lo*hi), ~fp32 accuracy */
+    SVB_PREC_BF16X3 = 3        /* tcgen05 kind::f16, operands split into bf16 hi + lo (16-bit mantissa),
+                                  3 MMAs at twice the TF32 rate, fp32 accumulate -- the default      */
 } svb_precision;
 
 #define SVB_MAX_UPS 8

@@ -19,6 +19,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+
+#include <cuda_bf16.h>
 
 #include "conv_tc.cuh"
 
@@ -135,11 +138,43 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// cute::UMMA::InstrDescriptor for kind::f16 with bf16 operands, fp32 accumulate, K-major
+__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                   // c_format = F32
+    d |= 1u << 7;                   // a_format = BF16
+    d |= 1u << 10;                  // b_format = BF16
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+// split x into bf16 hi + bf16 lo (x ~= hi + lo to 2^-17 relative); returns packed pairs
+__device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+// Operand modes (svb_precision): 1 = 1xTF32, 2 = 3xTF32, 3 = 3xBF16 (hi/lo split, 16-bit mantissa)
 struct TcArgs {
     ConvArgs a;
-    const float *w_hi, *w_lo;
-    int n_tile, n_chunks, R, x3, nW, nA, tmem_cols;
-    uint32_t slab_bytes, wtile_bytes;
+    const unsigned char *w;     // packed weight tiles of this mode
+    int mode;
+    int n_tile, n_chunks, MT, R, nW, nA, tmem_cols;
+    uint32_t raw_bytes;         // fp32 slab as TMA delivers it: 8 quads x R rows x 16 B
+    uint32_t slot_bytes;        // slab slot (raw_bytes, or 2x for the 3xTF32 lo plane)
+    uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile incl. hi + lo planes
 };
 
 __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
@@ -151,13 +186,11 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
     uint64_t *w_full = bars + 6, *w_empty = bars + 6 + 8;
     uint64_t *acc_full = bars + 6 + 16;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 6 + 16 + 1);
-    unsigned char *slab0 = smem + 256;                               // [nA][(1 + x3)][slab_bytes]
-    const uint32_t slab_slot = p.slab_bytes * (1 + p.x3);
-    unsigned char *wring = slab0 + p.nA * slab_slot;                 // [nW][(1 + x3)][wtile_bytes]
-    const uint32_t w_slot = p.wtile_bytes * (1 + p.x3);
+    unsigned char *slab0 = smem + 256;                               // [nA][slot_bytes]
+    unsigned char *wring = slab0 + p.nA * p.slot_bytes;              // [nW][wtile_bytes]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.z, nblk = blockIdx.y, t0 = blockIdx.x * kTcM;
+    const int b = blockIdx.z, nblk = blockIdx.y, t0 = blockIdx.x * (kTcM * p.MT);
     const int halo = (a.KS - 1) / 2 * a.dil;
 
     if (threadIdx.x == 0) {
@@ -177,54 +210,70 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
         if (lane == 0) {
             const int cin_q = a.Cin >> 2;
             const float *in_b = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4;
-            const size_t wtile_floats = (size_t)p.wtile_bytes / 4;
             for (int c = 0; c < p.n_chunks; ++c) {
                 const int sA = c & (p.nA - 1);
                 mbar_wait(a_empty + sA, ((c / p.nA) & 1) ^ 1);
-                mbar_expect_tx(a_full + sA, p.slab_bytes);
-                unsigned char *dst = slab0 + sA * slab_slot;
+                mbar_expect_tx(a_full + sA, p.raw_bytes);
+                unsigned char *dst = slab0 + sA * p.slot_bytes;
                 const uint32_t qbytes = (uint32_t)p.R * 16;
                 for (int q = 0; q < 8; ++q)
                     bulk_g2s(dst + q * qbytes, in_b + (size_t)(c * 8 + q) * a.in_Tp * 4, qbytes, a_full + sA);
                 for (int k = 0; k < a.KS; ++k) {
                     const int it = c * a.KS + k, sW = it % p.nW;
                     mbar_wait(w_empty + sW, ((it / p.nW) & 1) ^ 1);
-                    mbar_expect_tx(w_full + sW, w_slot);
-                    const size_t off = (((size_t)nblk * p.n_chunks + c) * a.KS + k) * wtile_floats;
-                    bulk_g2s(wring + sW * w_slot, p.w_hi + off, p.wtile_bytes, w_full + sW);
-                    if (p.x3) bulk_g2s(wring + sW * w_slot + p.wtile_bytes, p.w_lo + off, p.wtile_bytes, w_full + sW);
+                    mbar_expect_tx(w_full + sW, p.wtile_bytes);
+                    const size_t off = (((size_t)nblk * p.n_chunks + c) * a.KS + k) * (size_t)p.wtile_bytes;
+                    bulk_g2s(wring + sW * p.wtile_bytes, p.w + off, p.wtile_bytes, w_full + sW);
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(kTcM, p.n_tile);
+            const bool bf = p.mode == SVB_PREC_BF16X3;
+            const uint32_t idesc = bf ? umma_idesc_bf16(kTcM, p.n_tile) : umma_idesc_tf32(kTcM, p.n_tile);
             const uint32_t a_lbo = (uint32_t)p.R * 16, b_lbo = (uint32_t)p.n_tile * 16;
-            uint32_t acc = 0;
+            // lo planes: bf16 -> second half of the (in-place) slab / tile; 3xTF32 -> separate plane
+            const uint32_t a_lo_off = bf ? 4 * a_lbo : p.raw_bytes;
+            const uint32_t b_lo_off = bf ? 4 * b_lbo : p.wtile_bytes / 2;
+            const int nkk = bf ? 2 : 4;
+            uint32_t first = 1;
             for (int c = 0; c < p.n_chunks; ++c) {
                 const int sA = c & (p.nA - 1);
                 mbar_wait(a_ready + sA, (c / p.nA) & 1);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(slab0 + sA * slab_slot), a_lo = a_hi + p.slab_bytes;
+                const uint32_t a_base = smem_u32(slab0 + sA * p.slot_bytes);
                 for (int k = 0; k < a.KS; ++k) {
                     const int it = c * a.KS + k, sW = it % p.nW;
                     mbar_wait(w_full + sW, (it / p.nW) & 1);
                     tc_fence_after();
-                    const uint32_t b_hi = smem_u32(wring + sW * w_slot), b_lo = b_hi + p.wtile_bytes;
-                    const uint32_t row_off = (uint32_t)(k * a.dil) * 16;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t ao = row_off + kk * 2 * a_lbo, bo = kk * 2 * b_lbo;
-                        const uint64_t adh = umma_desc(a_hi + ao, a_lbo, 128), bdh = umma_desc(b_hi + bo, b_lbo, 128);
-                        if (p.x3) {     // small terms first
-                            umma_tf32(tmem_base, umma_desc(a_lo + ao, a_lbo, 128), bdh, idesc, acc);
-                            acc = 1;
-                            umma_tf32(tmem_base, adh, umma_desc(b_lo + bo, b_lbo, 128), idesc, acc);
+                    const uint32_t b_base = smem_u32(wring + sW * p.wtile_bytes);
+                    for (int m = 0; m < p.MT; ++m) {
+                        const uint32_t d = tmem_base + (uint32_t)(m * p.n_tile);
+                        const uint32_t a_row = a_base + (uint32_t)(k * a.dil + m * kTcM) * 16;
+                        uint32_t acc = first ? 0u : 1u;
+                        for (int kk = 0; kk < nkk; ++kk) {
+                            const uint32_t ao = a_row + kk * 2 * a_lbo, bo = b_base + kk * 2 * b_lbo;
+                            const uint64_t adh = umma_desc(ao, a_lbo, 128), bdh = umma_desc(bo, b_lbo, 128);
+                            if (p.mode == SVB_PREC_TF32) {
+                                umma_tf32(d, adh, bdh, idesc, acc);
+                            } else {                    // split modes: small cross terms first
+                                const uint64_t adl = umma_desc(ao + a_lo_off, a_lbo, 128);
+                                const uint64_t bdl = umma_desc(bo + b_lo_off, b_lbo, 128);
+                                if (bf) {
+                                    umma_bf16(d, adl, bdh, idesc, acc);
+                                    umma_bf16(d, adh, bdl, idesc, 1u);
+                                    umma_bf16(d, adh, bdh, idesc, 1u);
+                                } else {
+                                    umma_tf32(d, adl, bdh, idesc, acc);
+                                    umma_tf32(d, adh, bdl, idesc, 1u);
+                                    umma_tf32(d, adh, bdh, idesc, 1u);
+                                }
+                            }
+                            acc = 1u;
                         }
-                        umma_tf32(tmem_base, adh, bdh, idesc, acc);
-                        acc = 1;
                     }
+                    first = 0;
                     umma_commit(w_empty + sW);      // frees the weight slot when these MMAs retire
                 }
                 umma_commit(a_empty + sA);
@@ -234,44 +283,86 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
     } else {
         // ====================== transform (main loop) + epilogue warps ================
         const int tid = threadIdx.x - 64;                       // 0..127
-        const int n4 = 8 * p.R;                                 // float4 rows in a slab
         for (int c = 0; c < p.n_chunks; ++c) {
             const int sA = c & (p.nA - 1);
             mbar_wait(a_full + sA, (c / p.nA) & 1);
-            float4 *hi = reinterpret_cast<float4 *>(slab0 + sA * slab_slot);
-            float4 *lo = reinterpret_cast<float4 *>(slab0 + sA * slab_slot + p.slab_bytes);
-            for (int i = tid; i < n4; i += 128) {
-                float4 v = lrelu4(hi[i], a.in_slope);
-                const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-                hi[i] = h;
-                if (p.x3) lo[i] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+            float4 *raw = reinterpret_cast<float4 *>(slab0 + sA * p.slot_bytes);
+            if (p.mode == SVB_PREC_BF16X3) {
+                // one thread per slab row: read its 8 quads, then overwrite them with 4 hi + 4 lo
+                // bf16 rows (8 channels x 2 B = 16 B): rows are independent, so this is race free
+                uint4 *o = reinterpret_cast<uint4 *>(raw);
+                for (int r = tid; r < p.R; r += 128) {
+                    float4 v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = lrelu4(raw[q * p.R + r], a.in_slope);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 h, l;
+                        bf16_split2(v[2 * j].x, v[2 * j].y, h.x, l.x);
+                        bf16_split2(v[2 * j].z, v[2 * j].w, h.y, l.y);
+                        bf16_split2(v[2 * j + 1].x, v[2 * j + 1].y, h.z, l.z);
+                        bf16_split2(v[2 * j + 1].z, v[2 * j + 1].w, h.w, l.w);
+                        o[j * p.R + r] = h;
+                        o[(4 + j) * p.R + r] = l;
+                    }
+                }
+            } else {
+                float4 *lo = reinterpret_cast<float4 *>(slab0 + sA * p.slot_bytes + p.raw_bytes);
+                const int n4 = 8 * p.R;
+                for (int i = tid; i < n4; i += 128) {
+                    const float4 v = lrelu4(raw[i], a.in_slope);
+                    const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+                    raw[i] = h;
+                    if (p.mode == SVB_PREC_TF32X3)
+                        lo[i] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+                }
             }
             fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
             mbar_arrive(a_ready + sA);
         }
-        // ---- epilogue: TMEM lane = time row, column = output channel
+        // ---- epilogue: TMEM lane = time row, column = output channel.  Residual rows for block
+        // i+1 are requested before block i is drained from TMEM, so their latency overlaps.
+        const int lane_base = 32 * (warp & 3);                  // a warp may only touch its own TMEM lane quarter
+        const int out_q = a.Cout >> 2;
+        const int jb = p.n_tile / 32, nblocks = p.MT * jb;
+        const float4 *res4 = reinterpret_cast<const float4 *>(a.res);
+        auto row_of = [&](int blk, int g, int &co) -> size_t {
+            const int m = blk / jb, j = blk - m * jb;
+            const int q = t0 + m * kTcM + lane_base + lane;
+            const int cop = nblk * p.n_tile + j * 32 + 4 * g;
+            int phi = 0;
+            co = cop;
+            if (a.ups_u > 0) { phi = cop / a.Cout; co = cop - phi * a.Cout; }
+            return ((size_t)b * out_q + (co >> 2)) * a.out_Tp + kPad + (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q);
+        };
+        float4 rcur[8], rnxt[8];
+        auto fetch_res = [&](int blk, float4 *dst) {
+            const int m = blk / jb;
+            const bool ok = (t0 + m * kTcM + lane_base + lane) < a.Tq;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                int co;
+                const size_t row = row_of(blk, g, co);
+                dst[g] = (res4 && ok) ? __ldg(res4 + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        fetch_res(0, rcur);
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int lane_base = 32 * (warp & 3);                  // a warp may only touch its own TMEM lane quarter
-        const int q = t0 + lane_base + lane;                    // GEMM row of this thread
-        const int out_q = a.Cout >> 2;
-        for (int j = 0; j < p.n_tile / 32; ++j) {
+        for (int blk = 0; blk < nblocks; ++blk) {
+            if (blk + 1 < nblocks) fetch_res(blk + 1, rnxt);
+            const int m = blk / jb, j = blk - m * jb;
+            const int q = t0 + m * kTcM + lane_base + lane;
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(j * 32), v);
+            tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(m * p.n_tile + j * 32), v);
             if (q < a.Tq) {
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    const int cop = nblk * p.n_tile + j * 32 + 4 * g;
-                    int phi = 0, co = cop;
-                    if (a.ups_u > 0) { phi = cop / a.Cout; co = cop - phi * a.Cout; }
+                    int co;
+                    const size_t row = row_of(blk, g, co);
                     const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co));
-                    const size_t row = ((size_t)b * out_q + (co >> 2)) * a.out_Tp + kPad +
-                                       (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q);
-                    float4 o = make_float4(v[4 * g] + bv.x, v[4 * g + 1] + bv.y, v[4 * g + 2] + bv.z, v[4 * g + 3] + bv.w);
-                    if (a.res) {
-                        const float4 rv = __ldg(reinterpret_cast<const float4 *>(a.res) + row);
-                        o.x += rv.x, o.y += rv.y, o.z += rv.z, o.w += rv.w;
-                    }
+                    float4 o = make_float4(v[4 * g] + bv.x + rcur[g].x, v[4 * g + 1] + bv.y + rcur[g].y,
+                                           v[4 * g + 2] + bv.z + rcur[g].z, v[4 * g + 3] + bv.w + rcur[g].w);
                     o.x *= a.out_scale, o.y *= a.out_scale, o.z *= a.out_scale, o.w *= a.out_scale;
                     float4 *op = reinterpret_cast<float4 *>(a.out) + row;
                     if (a.accumulate) {
@@ -281,6 +372,8 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
                     *op = o;
                 }
             }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) rcur[g] = rnxt[g];
         }
     }
     tc_fence_before();
@@ -302,6 +395,19 @@ static float host_tf32(float x) {   // round to nearest, ties away (cvt.rna.tf32
     std::memcpy(&r, &u, 4);
     return r;
 }
+static uint16_t host_bf16(float x) {   // round to nearest even (__float2bfloat16_rn)
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float bf16_to_float(uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
 
 static int pick_n_tile(int CoutP) {
     if (CoutP % 16 != 0) return 0;
@@ -314,32 +420,40 @@ static int pick_n_tile(int CoutP) {
 int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs) {
     out->KS = KS, out->Cin = Cin, out->CoutP = CoutP, out->ok = false;
     const int n_tile = pick_n_tile(CoutP);
-    if (n_tile == 0 || Cin % kTcCK != 0) return SVB_OK;           // FFMA handles it
+    if (n_tile == 0 || Cin % kTcCK != 0) return SVB_OK;           // CUDA cores handle it
     out->n_tile = n_tile;
     const int n_chunks = Cin / kTcCK, n_blk = CoutP / n_tile;
-    const size_t tile = (size_t)n_tile * kTcCK;                    // floats per (nblk, chunk, tap)
-    std::vector<float> hi((size_t)n_blk * n_chunks * KS * tile), lo(hi.size());
+    const size_t tile = (size_t)n_tile * kTcCK;                    // elements per (nblk, chunk, tap)
+    const size_t n_tiles = (size_t)n_blk * n_chunks * KS;
+    std::vector<float> tf(n_tiles * tile), tf3(n_tiles * tile * 2);
+    std::vector<uint16_t> bf(n_tiles * tile * 2);
     for (int nb = 0; nb < n_blk; ++nb)
         for (int c = 0; c < n_chunks; ++c)
             for (int k = 0; k < KS; ++k) {
-                float *th = hi.data() + (((size_t)nb * n_chunks + c) * KS + k) * tile;
-                float *tl = lo.data() + (((size_t)nb * n_chunks + c) * KS + k) * tile;
-                for (int q = 0; q < 8; ++q)                        // K quads of the chunk
-                    for (int n = 0; n < n_tile; ++n)
-                        for (int e = 0; e < 4; ++e) {
-                            const int ci = c * kTcCK + q * 4 + e, co = nb * n_tile + n;
-                            const float w = packed[((size_t)k * Cin + ci) * CoutP + co];
-                            const float h = host_tf32(w);
-                            th[((size_t)q * n_tile + n) * 4 + e] = h;
-                            tl[((size_t)q * n_tile + n) * 4 + e] = host_tf32(w - h);
-                        }
+                const size_t t = ((size_t)nb * n_chunks + c) * KS + k;
+                float *t1 = tf.data() + t * tile;
+                float *t3 = tf3.data() + t * tile * 2;              // [hi tile][lo tile]
+                uint16_t *tb = bf.data() + t * tile * 2;            // [hi: 4 octs][lo: 4 octs], oct = [n_tile][8]
+                for (int ci = 0; ci < kTcCK; ++ci)
+                    for (int n = 0; n < n_tile; ++n) {
+                        const float w = packed[((size_t)k * Cin + c * kTcCK + ci) * CoutP + nb * n_tile + n];
+                        const size_t i4 = ((size_t)(ci >> 2) * n_tile + n) * 4 + (ci & 3);     // quad-major
+                        const float h = host_tf32(w);
+                        t1[i4] = h, t3[i4] = h, t3[tile + i4] = host_tf32(w - h);
+                        const size_t i8 = ((size_t)(ci >> 3) * n_tile + n) * 8 + (ci & 7);     // oct-major
+                        const uint16_t bh = host_bf16(w);
+                        tb[i8] = bh, tb[tile + i8] = host_bf16(w - bf16_to_float(bh));
+                    }
             }
-    SVB_CUDA(cudaMalloc((void **)&out->hi, hi.size() * 4));
-    allocs->push_back(out->hi);
-    SVB_CUDA(cudaMalloc((void **)&out->lo, lo.size() * 4));
-    allocs->push_back(out->lo);
-    SVB_CUDA(cudaMemcpy(out->hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
-    SVB_CUDA(cudaMemcpy(out->lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+    auto up = [&](const void *src, size_t bytes, void **dst) -> int {
+        SVB_CUDA(cudaMalloc(dst, bytes));
+        allocs->push_back(*dst);
+        SVB_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return SVB_OK;
+    };
+    SVB_TRY(up(tf.data(), tf.size() * 4, &out->blob[SVB_PREC_TF32]));
+    SVB_TRY(up(tf3.data(), tf3.size() * 4, &out->blob[SVB_PREC_TF32X3]));
+    SVB_TRY(up(bf.data(), bf.size() * 2, &out->blob[SVB_PREC_BF16X3]));
     out->ok = true;
     return SVB_OK;
 }
@@ -350,33 +464,58 @@ bool tc_supported(const TcWeights &w, const ConvArgs &a) {
 }
 
 int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st) {
+    SVB_CHECK(precision >= SVB_PREC_TF32 && precision <= SVB_PREC_BF16X3, SVB_ERR_INVALID, "tc conv: bad precision %d",
+              precision);
     TcArgs p;
-    p.a = a, p.w_hi = w.hi, p.w_lo = w.lo;
+    p.a = a, p.mode = precision, p.w = reinterpret_cast<const unsigned char *>(w.blob[precision]);
     p.n_tile = w.n_tile, p.n_chunks = a.Cin / kTcCK;
     const int halo = (a.KS - 1) / 2 * a.dil;
-    p.R = kTcM + 2 * halo;
-    p.x3 = precision == SVB_PREC_TF32X3 ? 1 : 0;
-    p.slab_bytes = (uint32_t)8 * p.R * 16;
-    p.wtile_bytes = (uint32_t)p.n_tile * kTcCK * 4;
-    int cols = 32;
-    while (cols < p.n_tile) cols <<= 1;
-    p.tmem_cols = cols;
+    const int tiles = (a.Tq + kTcM - 1) / kTcM;              // 128-row tiles per batch item
+    const int col_blocks = a.CoutP / p.n_tile;
+    const int elem_w = precision == SVB_PREC_TF32 ? 4 : precision == SVB_PREC_TF32X3 ? 8 : 4;   // bytes per weight incl. lo
+    p.wtile_bytes = (uint32_t)p.n_tile * kTcCK * elem_w;
     p.nA = std::min(2, p.n_chunks);
-    const size_t fixed = 256 + (size_t)p.nA * p.slab_bytes * (1 + p.x3);
-    const size_t wslot = (size_t)p.wtile_bytes * (1 + p.x3);
-    // wide tiles take the whole SM; narrow (bandwidth-bound) layers keep 2-3 CTAs per SM resident
-    const size_t budget = p.n_tile > 128 ? 224 * 1024 : p.n_tile > 64 ? 110 * 1024 : 74 * 1024;
-    int nW = fixed + 2 * wslot <= budget ? (int)((budget - fixed) / wslot) : 2;
+    // ---- M tiles per CTA: every weight tile fetched from L2 is reused by MT accumulators.  Bounded
+    // by TMEM (MT * N <= 512 columns), shared memory, and by keeping the grid at least ~2 waves.
+    int MT = 1;
+    for (int cand : {4, 2}) {
+        if (cand * p.n_tile > 512) continue;
+        if ((tiles + cand - 1) / cand * cand * kTcM > round_up(a.Tq, kTileT)) continue;   // stay inside the allocation
+        if ((long long)((tiles + cand - 1) / cand) * col_blocks * a.B < 222) continue;          // >= 1.5 waves
+        const size_t slab = (size_t)8 * (cand * kTcM + 2 * halo) * 16 * (precision == SVB_PREC_TF32X3 ? 2 : 1);
+        if (256 + p.nA * slab + 2 * (size_t)p.wtile_bytes > 200 * 1024) continue;
+        MT = cand;
+        break;
+    }
+    if (const char *e = getenv("SVB_TC_MT")) {      // tuning override (must respect the same bounds)
+        const int f = atoi(e);
+        if ((f == 1 || f == 2 || f == 4) && f * p.n_tile <= 512 && (tiles + f - 1) / f * f * kTcM <= round_up(a.Tq, kTileT)) MT = f;
+    }
+    p.MT = MT;
+    p.R = MT * kTcM + 2 * halo;
+    p.raw_bytes = (uint32_t)8 * p.R * 16;
+    p.slot_bytes = p.raw_bytes * (precision == SVB_PREC_TF32X3 ? 2 : 1);
+    int cols = 32;
+    while (cols < MT * p.n_tile) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t fixed = 256 + (size_t)p.nA * p.slot_bytes;
+    // TMEM allows 512 / cols CTAs per SM; give each as much of the weight ring as still lets them co-reside
+    int want_ctas = std::max(1, std::min(3, 512 / cols));
+    if (const char *e = getenv("SVB_TC_CTAS")) want_ctas = std::max(1, std::min(want_ctas, atoi(e)));
+    size_t budget = (size_t)(227 * 1024) / want_ctas - 1024;
+    if (fixed + 2 * (size_t)p.wtile_bytes > budget) budget = 224 * 1024;
+    int nW = (int)((budget - fixed) / p.wtile_bytes);
     nW = std::max(1, std::min(std::min(nW, 8), p.n_chunks * a.KS));
     p.nW = nW;
-    const size_t smem = fixed + (size_t)nW * wslot;
-    SVB_CHECK(smem <= 227 * 1024, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d, %zu B)", p.n_tile, smem);
+    const size_t smem = fixed + (size_t)nW * p.wtile_bytes;
+    SVB_CHECK(smem <= 227 * 1024, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d MT %d, %zu B)", p.n_tile,
+              MT, smem);
     static size_t configured = 0;
     if (smem > configured) {
         SVB_CUDA(cudaFuncSetAttribute(conv1d_c4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid((a.Tq + kTcM - 1) / kTcM, a.CoutP / p.n_tile, a.B);
+    dim3 grid((tiles + MT - 1) / MT, col_blocks, a.B);
     conv1d_c4_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
     SVB_CUDA(cudaGetLastError());
     return SVB_OK;

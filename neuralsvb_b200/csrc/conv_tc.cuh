@@ -7,8 +7,7 @@
 namespace svb {
 
 struct TcWeights {
-    float *hi = nullptr;    // tf32-rounded weights in UMMA K-major core-matrix order
-    float *lo = nullptr;    // residual (w - hi) rounded to tf32, for the 3xTF32 mode
+    void *blob[4] = {nullptr, nullptr, nullptr, nullptr};   // per svb_precision: weight tiles in UMMA core-matrix order
     int KS = 0, Cin = 0, CoutP = 0;
     int n_tile = 0;         // GEMM columns per CTA (UMMA N)
     bool ok = false;

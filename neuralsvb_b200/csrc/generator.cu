@@ -282,7 +282,7 @@ extern "C" int svb_gen_create(const svb_gen_config *cfg, int device, svb_gen_t *
     SVB_CHECK(cfg->resblock == 1 || cfg->resblock == 2, SVB_ERR_INVALID, "gen_create: resblock must be 1 or 2");
     SVB_CHECK(cfg->n_mel > 0 && cfg->n_mel % 4 == 0, SVB_ERR_INVALID, "gen_create: n_mel %d must be a multiple of 4",
               cfg->n_mel);
-    SVB_CHECK(cfg->precision >= 0 && cfg->precision <= 2, SVB_ERR_INVALID, "gen_create: bad precision %d", cfg->precision);
+    SVB_CHECK(cfg->precision >= 0 && cfg->precision <= 3, SVB_ERR_INVALID, "gen_create: bad precision %d", cfg->precision);
     const int cfin = cfg->upsample_initial_channel >> cfg->n_ups;
     SVB_CHECK(cfin >= 4 && (cfin << cfg->n_ups) == cfg->upsample_initial_channel && cfin % 4 == 0, SVB_ERR_INVALID,
               "gen_create: upsample_initial_channel %d must stay a multiple of 4 after %d halvings",
@@ -407,7 +407,7 @@ extern "C" int svb_gen_finalize(svb_gen_t *g) {
 }
 
 extern "C" int svb_gen_set_precision(svb_gen_t *g, int32_t precision) {
-    SVB_CHECK(g && precision >= 0 && precision <= 2, SVB_ERR_INVALID, "set_precision: bad argument");
+    SVB_CHECK(g && precision >= 0 && precision <= 3, SVB_ERR_INVALID, "set_precision: bad argument");
     g->cfg.precision = precision;
     return SVB_OK;
 }

@@ -111,7 +111,7 @@ class HifiGanGenerator(nn.Module):
         self.h = h
         self.num_kernels = len(h['resblock_kernel_sizes'])
         self.num_upsamples = len(h['upsample_rates'])
-        self.precision = precision or h.get('svb_precision', 'tf32')
+        self.precision = precision or h.get('svb_precision', 'bf16x3')
         self.n_mel = int(h.get('audio_num_mel_bins', 80))
         c0 = h['upsample_initial_channel']
         if h['use_pitch_embed']:
