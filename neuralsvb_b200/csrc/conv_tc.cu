@@ -232,9 +232,11 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
         if (lane == 0) {
             const bool bf = p.mode == SVB_PREC_BF16X3;
             const uint32_t idesc = bf ? umma_idesc_bf16(kTcM, p.n_tile) : umma_idesc_tf32(kTcM, p.n_tile);
-            const uint32_t a_lbo = (uint32_t)p.R * 16, b_lbo = (uint32_t)p.n_tile * 16;
-            // lo planes: bf16 -> second half of the (in-place) slab / tile; 3xTF32 -> separate plane
-            const uint32_t a_lo_off = bf ? 4 * a_lbo : p.raw_bytes;
+            // A slab: fp32 quads at q*R*16.  bf16 mode rewrites quad pair (2j, 2j+1) in place as
+            // (hi oct j, lo oct j): consecutive hi octs are 2 quads apart and lo = hi + one quad.
+            const uint32_t qstride = (uint32_t)p.R * 16;
+            const uint32_t a_lbo = bf ? 2 * qstride : qstride, b_lbo = (uint32_t)p.n_tile * 16;
+            const uint32_t a_lo_off = bf ? qstride : p.raw_bytes;
             const uint32_t b_lo_off = bf ? 4 * b_lbo : p.wtile_bytes / 2;
             const int nkk = bf ? 2 : 4;
             uint32_t first = 1;
@@ -288,23 +290,21 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
             mbar_wait(a_full + sA, (c / p.nA) & 1);
             float4 *raw = reinterpret_cast<float4 *>(slab0 + sA * p.slot_bytes);
             if (p.mode == SVB_PREC_BF16X3) {
-                // one thread per slab row: read its 8 quads, then overwrite them with 4 hi + 4 lo
-                // bf16 rows (8 channels x 2 B = 16 B): rows are independent, so this is race free
+                // (oct j, row r): read quads 2j and 2j+1 of the row (8 channels), write the bf16 hi
+                // row over quad 2j and the bf16 lo row over quad 2j+1 -- purely element-local
                 uint4 *o = reinterpret_cast<uint4 *>(raw);
-                for (int r = tid; r < p.R; r += 128) {
-                    float4 v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = lrelu4(raw[q * p.R + r], a.in_slope);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 h, l;
-                        bf16_split2(v[2 * j].x, v[2 * j].y, h.x, l.x);
-                        bf16_split2(v[2 * j].z, v[2 * j].w, h.y, l.y);
-                        bf16_split2(v[2 * j + 1].x, v[2 * j + 1].y, h.z, l.z);
-                        bf16_split2(v[2 * j + 1].z, v[2 * j + 1].w, h.w, l.w);
-                        o[j * p.R + r] = h;
-                        o[(4 + j) * p.R + r] = l;
-                    }
+                const int n = 4 * p.R;
+                for (int i = tid; i < n; i += 128) {
+                    const int j = i / p.R, r = i - j * p.R;
+                    const int i0 = (2 * j) * p.R + r, i1 = i0 + p.R;
+                    const float4 v0 = lrelu4(raw[i0], a.in_slope), v1 = lrelu4(raw[i1], a.in_slope);
+                    uint4 h, l;
+                    bf16_split2(v0.x, v0.y, h.x, l.x);
+                    bf16_split2(v0.z, v0.w, h.y, l.y);
+                    bf16_split2(v1.x, v1.y, h.z, l.z);
+                    bf16_split2(v1.z, v1.w, h.w, l.w);
+                    o[i0] = h;
+                    o[i1] = l;
                 }
             } else {
                 float4 *lo = reinterpret_cast<float4 *>(slab0 + sA * p.slot_bytes + p.raw_bytes);
@@ -320,60 +320,42 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
             fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
             mbar_arrive(a_ready + sA);
         }
-        // ---- epilogue: TMEM lane = time row, column = output channel.  Residual rows for block
-        // i+1 are requested before block i is drained from TMEM, so their latency overlaps.
-        const int lane_base = 32 * (warp & 3);                  // a warp may only touch its own TMEM lane quarter
-        const int out_q = a.Cout >> 2;
-        const int jb = p.n_tile / 32, nblocks = p.MT * jb;
-        const float4 *res4 = reinterpret_cast<const float4 *>(a.res);
-        auto row_of = [&](int blk, int g, int &co) -> size_t {
-            const int m = blk / jb, j = blk - m * jb;
-            const int q = t0 + m * kTcM + lane_base + lane;
-            const int cop = nblk * p.n_tile + j * 32 + 4 * g;
-            int phi = 0;
-            co = cop;
-            if (a.ups_u > 0) { phi = cop / a.Cout; co = cop - phi * a.Cout; }
-            return ((size_t)b * out_q + (co >> 2)) * a.out_Tp + kPad + (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q);
-        };
-        float4 rcur[8], rnxt[8];
-        auto fetch_res = [&](int blk, float4 *dst) {
-            const int m = blk / jb;
-            const bool ok = (t0 + m * kTcM + lane_base + lane) < a.Tq;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                int co;
-                const size_t row = row_of(blk, g, co);
-                dst[g] = (res4 && ok) ? __ldg(res4 + row) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        fetch_res(0, rcur);
+        // ---- epilogue: TMEM lane = time row, column = output channel.  Kept register-light on
+        // purpose: residual latency is hidden by co-resident CTAs, not by per-thread prefetch.
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        for (int blk = 0; blk < nblocks; ++blk) {
-            if (blk + 1 < nblocks) fetch_res(blk + 1, rnxt);
-            const int m = blk / jb, j = blk - m * jb;
-            const int q = t0 + m * kTcM + lane_base + lane;
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(m * p.n_tile + j * 32), v);
-            if (q < a.Tq) {
+        const int lane_base = 32 * (warp & 3);                  // a warp may only touch its own TMEM lane quarter
+        const int out_q = a.Cout >> 2;
+        const float4 *res4 = reinterpret_cast<const float4 *>(a.res);
+        float4 *out4 = reinterpret_cast<float4 *>(a.out);
+        for (int m = 0; m < p.MT; ++m) {
+            const int q = t0 + m * kTcM + lane_base + lane;     // GEMM row of this thread
+            for (int j = 0; j < p.n_tile / 32; ++j) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(m * p.n_tile + j * 32), v);
+                if (q >= a.Tq) continue;
+                const int cop0 = nblk * p.n_tile + j * 32;      // 32 columns never straddle an upsampler phase
+                int phi = 0, co0 = cop0;
+                if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
+                const size_t row0 = ((size_t)b * out_q + (co0 >> 2)) * a.out_Tp + kPad +
+                                    (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q);
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    int co;
-                    const size_t row = row_of(blk, g, co);
-                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co));
-                    float4 o = make_float4(v[4 * g] + bv.x + rcur[g].x, v[4 * g + 1] + bv.y + rcur[g].y,
-                                           v[4 * g + 2] + bv.z + rcur[g].z, v[4 * g + 3] + bv.w + rcur[g].w);
+                    const size_t row = row0 + (size_t)g * a.out_Tp;
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co0 + 4 * g));
+                    float4 o = make_float4(v[4 * g] + bv.x, v[4 * g + 1] + bv.y, v[4 * g + 2] + bv.z, v[4 * g + 3] + bv.w);
+                    if (res4) {
+                        const float4 rv = __ldg(res4 + row);
+                        o.x += rv.x, o.y += rv.y, o.z += rv.z, o.w += rv.w;
+                    }
                     o.x *= a.out_scale, o.y *= a.out_scale, o.z *= a.out_scale, o.w *= a.out_scale;
-                    float4 *op = reinterpret_cast<float4 *>(a.out) + row;
                     if (a.accumulate) {
-                        const float4 old = *op;
+                        const float4 old = out4[row];
                         o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
                     }
-                    *op = o;
+                    out4[row] = o;
                 }
             }
-#pragma unroll
-            for (int g = 0; g < 8; ++g) rcur[g] = rnxt[g];
         }
     }
     tc_fence_before();
@@ -460,7 +442,7 @@ int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *
 
 bool tc_supported(const TcWeights &w, const ConvArgs &a) {
     return w.ok && a.Cin % kTcCK == 0 && a.bias != nullptr && (a.KS - 1) / 2 * a.dil <= kPad &&
-           (a.ups_u == 0 || a.Cout % 4 == 0);
+           (a.ups_u == 0 || a.Cout % 32 == 0);
 }
 
 int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st) {
@@ -499,12 +481,14 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     while (cols < MT * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
     const size_t fixed = 256 + (size_t)p.nA * p.slot_bytes;
-    // TMEM allows 512 / cols CTAs per SM; give each as much of the weight ring as still lets them co-reside
-    int want_ctas = std::max(1, std::min(3, 512 / cols));
+    // The kernel hides load / epilogue latency with co-resident CTAs (64 registers, 192 threads):
+    // TMEM allows 512 / cols of them, registers 5; size the weight ring so that many still fit.
+    int want_ctas = std::max(1, std::min(5, 512 / cols));
     if (const char *e = getenv("SVB_TC_CTAS")) want_ctas = std::max(1, std::min(want_ctas, atoi(e)));
-    size_t budget = (size_t)(227 * 1024) / want_ctas - 1024;
-    if (fixed + 2 * (size_t)p.wtile_bytes > budget) budget = 224 * 1024;
-    int nW = (int)((budget - fixed) / p.wtile_bytes);
+    const int min_ring = std::min(2, p.n_chunks * a.KS);
+    while (want_ctas > 1 && fixed + (size_t)min_ring * p.wtile_bytes > (size_t)(227 * 1024) / want_ctas - 1024) --want_ctas;
+    const size_t budget = (size_t)(227 * 1024) / want_ctas - 1024;
+    int nW = budget > fixed ? (int)((budget - fixed) / p.wtile_bytes) : 1;
     nW = std::max(1, std::min(std::min(nW, 8), p.n_chunks * a.KS));
     p.nW = nW;
     const size_t smem = fixed + (size_t)nW * p.wtile_bytes;
