@@ -5,10 +5,11 @@
 // GEMM mapping: M = time (128 rows per CTA), N = output channels (<= 256 per CTA), K = taps x Cin.
 // * A operand = the activation slab.  C4T keeps, per channel quad, consecutive time steps as
 //   consecutive 16-byte rows, so a [rows x 4 ch] slab is one contiguous span: it is fetched with ONE
-//   cp.async.bulk (TMA, UBLKCP) per quad and it already IS the K-major no-swizzle UMMA core-matrix
-//   layout (8 rows x 16 B = 128 B, SBO = 128 B, LBO = quad stride).  A conv tap at dilation d is a
-//   row shift of the same slab = +16*k*d bytes on the descriptor start address, so one slab load
-//   (128 + halo rows) feeds all KS taps.
+//   cp.async.bulk (TMA, UBLKCP) per quad.  The transform warps turn the fp32 slab into the MMA
+//   operand: one 128-byte row per time step (K-major, SWIZZLE_128B -- the no-swizzle layout was
+//   measured at only ~40 B/clk of operand fetch).  A conv tap at dilation d is a ROW SHIFT of that
+//   operand = +128*k*d bytes on the descriptor start address, so one slab load (128 + halo rows)
+//   feeds all KS taps.
 // * B operand = weights, packed on the host per (column block, input-channel chunk, tap) in the
 //   same core-matrix order, streamed through a ring of bulk copies.
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
@@ -110,26 +111,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-// start address, leading byte offset (between the two 16-byte K halves of one MMA), stride byte
-// offset (between 8-row core matrices), all in 16-byte units.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
-    return d;                   // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
+// Rows are 128 bytes; 8-row groups (1024 B atoms) are SBO apart; within an atom the 16-byte chunk
+// index is XORed with (row & 7).  hi word is constant per operand; lo word carries the address.
+__device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t base_offset) {
+    // bits [32,46) SBO>>4 = 64 ; [46,48) version = 1 ; [49,52) base offset ; [61,64) layout = 2 (SWIZZLE_128B)
+    return 64u | (1u << 14) | ((base_offset & 7u) << 17) | (2u << 29);
 }
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
-__host__ __device__ inline uint32_t umma_idesc_tf32(int M, int N) {
-    uint32_t d = 0;
-    d |= 1u << 4;                   // c_format = F32
-    d |= 2u << 7;                   // a_format = TF32
-    d |= 2u << 10;                  // b_format = TF32
-    d |= (uint32_t)(N >> 3) << 17;  // n_dim
-    d |= (uint32_t)(M >> 4) << 24;  // m_dim
-    return d;
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+
+// cute::UMMA::InstrDescriptor: fp32 accumulate, both operands K-major; fmt 1 = BF16 (kind::f16), 2 = TF32
+__host__ __device__ inline uint32_t umma_idesc(int fmt, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <bool BF>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                     uint32_t idesc, uint32_t acc) {
+    if (BF)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+            : "memory");
 }
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -137,26 +151,6 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-
-// cute::UMMA::InstrDescriptor for kind::f16 with bf16 operands, fp32 accumulate, K-major
-__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
-    uint32_t d = 0;
-    d |= 1u << 4;                   // c_format = F32
-    d |= 1u << 7;                   // a_format = BF16
-    d |= 1u << 10;                  // b_format = BF16
-    d |= (uint32_t)(N >> 3) << 17;
-    d |= (uint32_t)(M >> 4) << 24;
-    return d;
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
 // split x into bf16 hi + bf16 lo (x ~= hi + lo to 2^-17 relative); returns packed pairs
 __device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
     const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
@@ -166,36 +160,44 @@ __device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t &hi, ui
     lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
 }
 
-// Operand modes (svb_precision): 1 = 1xTF32, 2 = 3xTF32, 3 = 3xBF16 (hi/lo split, 16-bit mantissa)
+// Operand modes (svb_precision): 1 = 1xTF32, 2 = 3xTF32, 3 = 3xBF16 (hi/lo split, 16-bit mantissa).
+// One operand row = 32 input channels = 128 bytes:  TF32: 32 x tf32 ; BF16x3: [32 x bf16 hi | 32 x bf16 lo].
 struct TcArgs {
     ConvArgs a;
-    const unsigned char *w;     // packed weight tiles of this mode
-    int mode;
-    int n_tile, n_chunks, MT, R, nW, nA, tmem_cols;
+    const unsigned char *w;     // packed, pre-swizzled weight tiles of this mode
+    int n_tile, n_chunks, MT, R, Rp, nW, nA, nR, tmem_cols, base_off_mode;
     uint32_t raw_bytes;         // fp32 slab as TMA delivers it: 8 quads x R rows x 16 B
-    uint32_t slot_bytes;        // slab slot (raw_bytes, or 2x for the 3xTF32 lo plane)
-    uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile incl. hi + lo planes
+    uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
+    uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile (x2 with the 3xTF32 lo plane)
+    uint32_t off_op, off_w;     // byte offsets of the operand slots / weight ring in dynamic smem
 };
 
+constexpr int kMaxW = 8;
+
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr bool BF = MODE == SVB_PREC_BF16X3;
+    constexpr bool X3 = MODE == SVB_PREC_TF32X3;
     const ConvArgs &a = p.a;
-    // ---- shared memory carve-up
+    // ---- shared memory carve-up (operand slots and weight ring are 1024-byte aligned: swizzle atoms)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    uint64_t *a_full = bars, *a_ready = bars + 2, *a_empty = bars + 4;
-    uint64_t *w_full = bars + 6, *w_empty = bars + 6 + 8;
-    uint64_t *acc_full = bars + 6 + 16;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 6 + 16 + 1);
-    unsigned char *slab0 = smem + 256;                               // [nA][slot_bytes]
-    unsigned char *wring = slab0 + p.nA * p.slot_bytes;              // [nW][wtile_bytes]
+    uint64_t *raw_full = bars, *raw_empty = bars + 2, *a_ready = bars + 4, *a_empty = bars + 6;
+    uint64_t *w_full = bars + 8, *w_empty = bars + 8 + kMaxW;
+    uint64_t *acc_full = bars + 8 + 2 * kMaxW;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 8 + 2 * kMaxW + 1);
+    unsigned char *raw0 = smem + 256;                                // [nR][raw_bytes]
+    unsigned char *op0 = smem + p.off_op;                            // [nA][op_bytes]
+    unsigned char *wring = smem + p.off_w;                           // [nW][wtile_bytes]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z, nblk = blockIdx.y, t0 = blockIdx.x * (kTcM * p.MT);
     const int halo = (a.KS - 1) / 2 * a.dil;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) mbar_init(a_full + i, 1), mbar_init(a_ready + i, 128), mbar_init(a_empty + i, 1);
-        for (int i = 0; i < 8; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, 1);
+        for (int i = 0; i < 2; ++i)
+            mbar_init(raw_full + i, 1), mbar_init(raw_empty + i, 128), mbar_init(a_ready + i, 128), mbar_init(a_empty + i, 1);
+        for (int i = 0; i < kMaxW; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, 1);
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -210,14 +212,14 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
         if (lane == 0) {
             const int cin_q = a.Cin >> 2;
             const float *in_b = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4;
+            const uint32_t qbytes = (uint32_t)p.R * 16;
             for (int c = 0; c < p.n_chunks; ++c) {
-                const int sA = c & (p.nA - 1);
-                mbar_wait(a_empty + sA, ((c / p.nA) & 1) ^ 1);
-                mbar_expect_tx(a_full + sA, p.raw_bytes);
-                unsigned char *dst = slab0 + sA * p.slot_bytes;
-                const uint32_t qbytes = (uint32_t)p.R * 16;
+                const int sR = c % p.nR;
+                mbar_wait(raw_empty + sR, ((c / p.nR) & 1) ^ 1);
+                mbar_expect_tx(raw_full + sR, p.raw_bytes);
+                unsigned char *dst = raw0 + sR * p.raw_bytes;
                 for (int q = 0; q < 8; ++q)
-                    bulk_g2s(dst + q * qbytes, in_b + (size_t)(c * 8 + q) * a.in_Tp * 4, qbytes, a_full + sA);
+                    bulk_g2s(dst + q * qbytes, in_b + (size_t)(c * 8 + q) * a.in_Tp * 4, qbytes, raw_full + sR);
                 for (int k = 0; k < a.KS; ++k) {
                     const int it = c * a.KS + k, sW = it % p.nW;
                     mbar_wait(w_empty + sW, ((it / p.nW) & 1) ^ 1);
@@ -230,21 +232,16 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
-            const bool bf = p.mode == SVB_PREC_BF16X3;
-            const uint32_t idesc = bf ? umma_idesc_bf16(kTcM, p.n_tile) : umma_idesc_tf32(kTcM, p.n_tile);
-            // A slab: fp32 quads at q*R*16.  bf16 mode rewrites quad pair (2j, 2j+1) in place as
-            // (hi oct j, lo oct j): consecutive hi octs are 2 quads apart and lo = hi + one quad.
-            const uint32_t qstride = (uint32_t)p.R * 16;
-            const uint32_t a_lbo = bf ? 2 * qstride : qstride, b_lbo = (uint32_t)p.n_tile * 16;
-            const uint32_t a_lo_off = bf ? qstride : p.raw_bytes;
-            const uint32_t b_lo_off = bf ? 4 * b_lbo : p.wtile_bytes / 2;
-            const int nkk = bf ? 2 : 4;
+            const uint32_t idesc = umma_idesc(BF ? 1 : 2, kTcM, p.n_tile);
+            const uint32_t w_hi_word = desc_hi_sw128(0);
+            const uint32_t a_lo_plane = X3 ? p.op_bytes / 2 : 64u;      // byte offset of the lo plane / half-row
+            const uint32_t b_lo_plane = X3 ? p.wtile_bytes / 2 : 64u;
             uint32_t first = 1;
             for (int c = 0; c < p.n_chunks; ++c) {
-                const int sA = c & (p.nA - 1);
+                const int sA = c % p.nA;
                 mbar_wait(a_ready + sA, (c / p.nA) & 1);
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(slab0 + sA * p.slot_bytes);
+                const uint32_t a_base = smem_u32(op0 + sA * p.op_bytes);
                 for (int k = 0; k < a.KS; ++k) {
                     const int it = c * a.KS + k, sW = it % p.nW;
                     mbar_wait(w_full + sW, (it / p.nW) & 1);
@@ -252,27 +249,33 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
                     const uint32_t b_base = smem_u32(wring + sW * p.wtile_bytes);
                     for (int m = 0; m < p.MT; ++m) {
                         const uint32_t d = tmem_base + (uint32_t)(m * p.n_tile);
-                        const uint32_t a_row = a_base + (uint32_t)(k * a.dil + m * kTcM) * 16;
+                        const uint32_t a_row = a_base + (uint32_t)(k * a.dil + m * kTcM) * 128;   // tap = row shift
+                        const uint32_t a_hi_word = desc_hi_sw128(p.base_off_mode ? (a_row >> 7) : 0u);
                         uint32_t acc = first ? 0u : 1u;
-                        for (int kk = 0; kk < nkk; ++kk) {
-                            const uint32_t ao = a_row + kk * 2 * a_lbo, bo = b_base + kk * 2 * b_lbo;
-                            const uint64_t adh = umma_desc(ao, a_lbo, 128), bdh = umma_desc(bo, b_lbo, 128);
-                            if (p.mode == SVB_PREC_TF32) {
-                                umma_tf32(d, adh, bdh, idesc, acc);
-                            } else {                    // split modes: small cross terms first
-                                const uint64_t adl = umma_desc(ao + a_lo_off, a_lbo, 128);
-                                const uint64_t bdl = umma_desc(bo + b_lo_off, b_lbo, 128);
-                                if (bf) {
-                                    umma_bf16(d, adl, bdh, idesc, acc);
-                                    umma_bf16(d, adh, bdl, idesc, 1u);
-                                    umma_bf16(d, adh, bdh, idesc, 1u);
-                                } else {
-                                    umma_tf32(d, adl, bdh, idesc, acc);
-                                    umma_tf32(d, adh, bdl, idesc, 1u);
-                                    umma_tf32(d, adh, bdh, idesc, 1u);
-                                }
+                        if (BF) {
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb) {      // 2 x 16 channels; small cross terms first
+                                const uint32_t ah = desc_lo(a_row + kb * 32), al = desc_lo(a_row + a_lo_plane + kb * 32);
+                                const uint32_t bh = desc_lo(b_base + kb * 32), bl = desc_lo(b_base + b_lo_plane + kb * 32);
+                                umma<true>(d, al, a_hi_word, bh, w_hi_word, idesc, acc);
+                                umma<true>(d, ah, a_hi_word, bl, w_hi_word, idesc, 1u);
+                                umma<true>(d, ah, a_hi_word, bh, w_hi_word, idesc, 1u);
+                                acc = 1u;
                             }
-                            acc = 1u;
+                        } else {
+#pragma unroll
+                            for (int kb = 0; kb < 4; ++kb) {      // 4 x 8 channels
+                                const uint32_t ah = desc_lo(a_row + kb * 32), bh = desc_lo(b_base + kb * 32);
+                                if (X3) {
+                                    const uint32_t al = desc_lo(a_row + a_lo_plane + kb * 32);
+                                    const uint32_t bl = desc_lo(b_base + b_lo_plane + kb * 32);
+                                    umma<false>(d, al, a_hi_word, bh, w_hi_word, idesc, acc);
+                                    umma<false>(d, ah, a_hi_word, bl, w_hi_word, idesc, 1u);
+                                    acc = 1u;
+                                }
+                                umma<false>(d, ah, a_hi_word, bh, w_hi_word, idesc, acc);
+                                acc = 1u;
+                            }
                         }
                     }
                     first = 0;
@@ -286,39 +289,44 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
         // ====================== transform (main loop) + epilogue warps ================
         const int tid = threadIdx.x - 64;                       // 0..127
         for (int c = 0; c < p.n_chunks; ++c) {
-            const int sA = c & (p.nA - 1);
-            mbar_wait(a_full + sA, (c / p.nA) & 1);
-            float4 *raw = reinterpret_cast<float4 *>(slab0 + sA * p.slot_bytes);
-            if (p.mode == SVB_PREC_BF16X3) {
-                // (oct j, row r): read quads 2j and 2j+1 of the row (8 channels), write the bf16 hi
-                // row over quad 2j and the bf16 lo row over quad 2j+1 -- purely element-local
-                uint4 *o = reinterpret_cast<uint4 *>(raw);
-                const int n = 4 * p.R;
-                for (int i = tid; i < n; i += 128) {
-                    const int j = i / p.R, r = i - j * p.R;
-                    const int i0 = (2 * j) * p.R + r, i1 = i0 + p.R;
-                    const float4 v0 = lrelu4(raw[i0], a.in_slope), v1 = lrelu4(raw[i1], a.in_slope);
-                    uint4 h, l;
-                    bf16_split2(v0.x, v0.y, h.x, l.x);
-                    bf16_split2(v0.z, v0.w, h.y, l.y);
-                    bf16_split2(v1.x, v1.y, h.z, l.z);
-                    bf16_split2(v1.z, v1.w, h.w, l.w);
-                    o[i0] = h;
-                    o[i1] = l;
-                }
-            } else {
-                float4 *lo = reinterpret_cast<float4 *>(slab0 + sA * p.slot_bytes + p.raw_bytes);
-                const int n4 = 8 * p.R;
-                for (int i = tid; i < n4; i += 128) {
-                    const float4 v = lrelu4(raw[i], a.in_slope);
-                    const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-                    raw[i] = h;
-                    if (p.mode == SVB_PREC_TF32X3)
-                        lo[i] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+            const int sR = c % p.nR, sA = c % p.nA;
+            mbar_wait(raw_full + sR, (c / p.nR) & 1);
+            mbar_wait(a_empty + sA, ((c / p.nA) & 1) ^ 1);
+            const float4 *raw = reinterpret_cast<const float4 *>(raw0 + sR * p.raw_bytes);
+            uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
+            for (int r = tid; r < p.R; r += 128) {
+                // row r: 8 quads (32 channels) -> one 128-byte operand row; chunk c16 lives at c16 ^ (r & 7)
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = lrelu4(raw[q * p.R + r], a.in_slope);
+                uint4 *row = op + (size_t)r * 8;
+                const int sw = r & 7;
+                if (BF) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {               // oct j = channels 8j .. 8j+7
+                        uint4 h, l;
+                        bf16_split2(v[2 * j].x, v[2 * j].y, h.x, l.x);
+                        bf16_split2(v[2 * j].z, v[2 * j].w, h.y, l.y);
+                        bf16_split2(v[2 * j + 1].x, v[2 * j + 1].y, h.z, l.z);
+                        bf16_split2(v[2 * j + 1].z, v[2 * j + 1].w, h.w, l.w);
+                        row[j ^ sw] = h;
+                        row[(4 + j) ^ sw] = l;
+                    }
+                } else {
+                    uint4 *row_lo = row + (p.op_bytes / 32);    // lo plane (3xTF32): op_bytes / 2 bytes further
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 h = make_float4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
+                        row[q ^ sw] = make_uint4(__float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w));
+                        if (X3)
+                            row_lo[q ^ sw] = make_uint4(__float_as_uint(to_tf32(v[q].x - h.x)), __float_as_uint(to_tf32(v[q].y - h.y)),
+                                                        __float_as_uint(to_tf32(v[q].z - h.z)), __float_as_uint(to_tf32(v[q].w - h.w)));
+                    }
                 }
             }
             fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
             mbar_arrive(a_ready + sA);
+            mbar_arrive(raw_empty + sR);
         }
         // ---- epilogue: TMEM lane = time row, column = output channel.  Kept register-light on
         // purpose: residual latency is hidden by co-resident CTAs, not by per-thread prefetch.
@@ -399,32 +407,36 @@ static int pick_n_tile(int CoutP) {
     return 0;
 }
 
+// Weight tiles in K-major SWIZZLE_128B order: row n (output column) = 128 bytes holding the 32 input
+// channels of the chunk; the 16-byte chunk c of row n is stored at chunk position c ^ (n & 7).
 int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs) {
     out->KS = KS, out->Cin = Cin, out->CoutP = CoutP, out->ok = false;
     const int n_tile = pick_n_tile(CoutP);
-    if (n_tile == 0 || Cin % kTcCK != 0) return SVB_OK;           // CUDA cores handle it
+    if (n_tile == 0 || n_tile % 8 != 0 || Cin % kTcCK != 0) return SVB_OK;    // CUDA cores handle it
     out->n_tile = n_tile;
     const int n_chunks = Cin / kTcCK, n_blk = CoutP / n_tile;
-    const size_t tile = (size_t)n_tile * kTcCK;                    // elements per (nblk, chunk, tap)
+    const size_t tile_b = (size_t)n_tile * 128;                    // bytes per tile plane
     const size_t n_tiles = (size_t)n_blk * n_chunks * KS;
-    std::vector<float> tf(n_tiles * tile), tf3(n_tiles * tile * 2);
-    std::vector<uint16_t> bf(n_tiles * tile * 2);
+    std::vector<unsigned char> tf(n_tiles * tile_b), tf3(n_tiles * tile_b * 2), bf(n_tiles * tile_b);
     for (int nb = 0; nb < n_blk; ++nb)
         for (int c = 0; c < n_chunks; ++c)
             for (int k = 0; k < KS; ++k) {
                 const size_t t = ((size_t)nb * n_chunks + c) * KS + k;
-                float *t1 = tf.data() + t * tile;
-                float *t3 = tf3.data() + t * tile * 2;              // [hi tile][lo tile]
-                uint16_t *tb = bf.data() + t * tile * 2;            // [hi: 4 octs][lo: 4 octs], oct = [n_tile][8]
-                for (int ci = 0; ci < kTcCK; ++ci)
-                    for (int n = 0; n < n_tile; ++n) {
+                float *t1 = reinterpret_cast<float *>(tf.data() + t * tile_b);
+                float *t3h = reinterpret_cast<float *>(tf3.data() + t * tile_b * 2);
+                float *t3l = reinterpret_cast<float *>(tf3.data() + t * tile_b * 2 + tile_b);
+                uint16_t *tb = reinterpret_cast<uint16_t *>(bf.data() + t * tile_b);
+                for (int n = 0; n < n_tile; ++n)
+                    for (int ci = 0; ci < kTcCK; ++ci) {
                         const float w = packed[((size_t)k * Cin + c * kTcCK + ci) * CoutP + nb * n_tile + n];
-                        const size_t i4 = ((size_t)(ci >> 2) * n_tile + n) * 4 + (ci & 3);     // quad-major
                         const float h = host_tf32(w);
-                        t1[i4] = h, t3[i4] = h, t3[tile + i4] = host_tf32(w - h);
-                        const size_t i8 = ((size_t)(ci >> 3) * n_tile + n) * 8 + (ci & 7);     // oct-major
-                        const uint16_t bh = host_bf16(w);
-                        tb[i8] = bh, tb[tile + i8] = host_bf16(w - bf16_to_float(bh));
+                        const int c16 = ci >> 2;                   // fp32: 4 channels per 16-byte chunk
+                        const size_t i4 = (size_t)n * 32 + ((c16 ^ (n & 7)) << 2) + (ci & 3);
+                        t1[i4] = h, t3h[i4] = h, t3l[i4] = host_tf32(w - h);
+                        const uint16_t bh = host_bf16(w), bl = host_bf16(w - bf16_to_float(bh));
+                        const int ch = ci >> 3, cl = 4 + (ci >> 3); // bf16: 8 channels per chunk; hi chunks 0-3, lo 4-7
+                        tb[(size_t)n * 64 + ((ch ^ (n & 7)) << 3) + (ci & 7)] = bh;
+                        tb[(size_t)n * 64 + ((cl ^ (n & 7)) << 3) + (ci & 7)] = bl;
                     }
             }
     auto up = [&](const void *src, size_t bytes, void **dst) -> int {
@@ -433,9 +445,9 @@ int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *
         SVB_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
         return SVB_OK;
     };
-    SVB_TRY(up(tf.data(), tf.size() * 4, &out->blob[SVB_PREC_TF32]));
-    SVB_TRY(up(tf3.data(), tf3.size() * 4, &out->blob[SVB_PREC_TF32X3]));
-    SVB_TRY(up(bf.data(), bf.size() * 2, &out->blob[SVB_PREC_BF16X3]));
+    SVB_TRY(up(tf.data(), tf.size(), &out->blob[SVB_PREC_TF32]));
+    SVB_TRY(up(tf3.data(), tf3.size(), &out->blob[SVB_PREC_TF32X3]));
+    SVB_TRY(up(bf.data(), bf.size(), &out->blob[SVB_PREC_BF16X3]));
     out->ok = true;
     return SVB_OK;
 }
@@ -445,64 +457,70 @@ bool tc_supported(const TcWeights &w, const ConvArgs &a) {
            (a.ups_u == 0 || a.Cout % 32 == 0);
 }
 
+template <int MODE>
+static int launch_mode(const TcArgs &p, dim3 grid, size_t smem, cudaStream_t st) {
+    auto kern = conv1d_c4_tc_kernel<MODE>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    kern<<<grid, kTcThreads, smem, st>>>(p);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
 int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st) {
     SVB_CHECK(precision >= SVB_PREC_TF32 && precision <= SVB_PREC_BF16X3, SVB_ERR_INVALID, "tc conv: bad precision %d",
               precision);
     TcArgs p;
-    p.a = a, p.mode = precision, p.w = reinterpret_cast<const unsigned char *>(w.blob[precision]);
+    p.a = a, p.w = reinterpret_cast<const unsigned char *>(w.blob[precision]);
     p.n_tile = w.n_tile, p.n_chunks = a.Cin / kTcCK;
     const int halo = (a.KS - 1) / 2 * a.dil;
     const int tiles = (a.Tq + kTcM - 1) / kTcM;              // 128-row tiles per batch item
     const int col_blocks = a.CoutP / p.n_tile;
-    const int elem_w = precision == SVB_PREC_TF32 ? 4 : precision == SVB_PREC_TF32X3 ? 8 : 4;   // bytes per weight incl. lo
-    p.wtile_bytes = (uint32_t)p.n_tile * kTcCK * elem_w;
-    p.nA = std::min(2, p.n_chunks);
-    // ---- M tiles per CTA: every weight tile fetched from L2 is reused by MT accumulators.  Bounded
-    // by TMEM (MT * N <= 512 columns), shared memory, and by keeping the grid at least ~2 waves.
+    const int planes = precision == SVB_PREC_TF32X3 ? 2 : 1;
+    p.wtile_bytes = (uint32_t)p.n_tile * 128 * planes;
+    // ---- M tiles per CTA (weight-tile reuse); measured: MT = 1 with many co-resident CTAs wins
     int MT = 1;
-    for (int cand : {4, 2}) {
-        if (cand * p.n_tile > 512) continue;
-        if ((tiles + cand - 1) / cand * cand * kTcM > round_up(a.Tq, kTileT)) continue;   // stay inside the allocation
-        if ((long long)((tiles + cand - 1) / cand) * col_blocks * a.B < 222) continue;          // >= 1.5 waves
-        const size_t slab = (size_t)8 * (cand * kTcM + 2 * halo) * 16 * (precision == SVB_PREC_TF32X3 ? 2 : 1);
-        if (256 + p.nA * slab + 2 * (size_t)p.wtile_bytes > 200 * 1024) continue;
-        MT = cand;
-        break;
-    }
-    if (const char *e = getenv("SVB_TC_MT")) {      // tuning override (must respect the same bounds)
+    if (const char *e = getenv("SVB_TC_MT")) {
         const int f = atoi(e);
         if ((f == 1 || f == 2 || f == 4) && f * p.n_tile <= 512 && (tiles + f - 1) / f * f * kTcM <= round_up(a.Tq, kTileT)) MT = f;
     }
     p.MT = MT;
     p.R = MT * kTcM + 2 * halo;
+    p.Rp = round_up(p.R, 8);
     p.raw_bytes = (uint32_t)8 * p.R * 16;
-    p.slot_bytes = p.raw_bytes * (precision == SVB_PREC_TF32X3 ? 2 : 1);
+    p.op_bytes = (uint32_t)p.Rp * 128 * planes;
+    p.nA = std::min(2, p.n_chunks);
+    p.nR = 1;
+    p.base_off_mode = 0;
+    if (const char *e = getenv("SVB_TC_BASEOFF")) p.base_off_mode = atoi(e) != 0;
     int cols = 32;
     while (cols < MT * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t fixed = 256 + (size_t)p.nA * p.slot_bytes;
+    p.off_op = (uint32_t)round_up(256 + p.nR * (int)p.raw_bytes, 1024);
+    p.off_w = p.off_op + (uint32_t)p.nA * p.op_bytes;          // op_bytes is a multiple of 1024
+    const size_t fixed = p.off_w;
     // The kernel hides load / epilogue latency with co-resident CTAs (64 registers, 192 threads):
     // TMEM allows 512 / cols of them, registers 5; size the weight ring so that many still fit.
     int want_ctas = std::max(1, std::min(5, 512 / cols));
     if (const char *e = getenv("SVB_TC_CTAS")) want_ctas = std::max(1, std::min(want_ctas, atoi(e)));
     const int min_ring = std::min(2, p.n_chunks * a.KS);
-    while (want_ctas > 1 && fixed + (size_t)min_ring * p.wtile_bytes > (size_t)(227 * 1024) / want_ctas - 1024) --want_ctas;
-    const size_t budget = (size_t)(227 * 1024) / want_ctas - 1024;
+    while (want_ctas > 1 && fixed + (size_t)min_ring * p.wtile_bytes > (size_t)(227 * 1024) / want_ctas - 2048) --want_ctas;
+    const size_t budget = (size_t)(227 * 1024) / want_ctas - 2048;
     int nW = budget > fixed ? (int)((budget - fixed) / p.wtile_bytes) : 1;
-    nW = std::max(1, std::min(std::min(nW, 8), p.n_chunks * a.KS));
+    nW = std::max(1, std::min(std::min(nW, kMaxW), p.n_chunks * a.KS));
     p.nW = nW;
     const size_t smem = fixed + (size_t)nW * p.wtile_bytes;
     SVB_CHECK(smem <= 227 * 1024, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d MT %d, %zu B)", p.n_tile,
               MT, smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        SVB_CUDA(cudaFuncSetAttribute(conv1d_c4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     dim3 grid((tiles + MT - 1) / MT, col_blocks, a.B);
-    conv1d_c4_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
-    SVB_CUDA(cudaGetLastError());
-    return SVB_OK;
+    switch (precision) {
+        case SVB_PREC_TF32: return launch_mode<SVB_PREC_TF32>(p, grid, smem, st);
+        case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3>(p, grid, smem, st);
+        default: return launch_mode<SVB_PREC_BF16X3>(p, grid, smem, st);
+    }
 }
 
 }  // namespace svb
