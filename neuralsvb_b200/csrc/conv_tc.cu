@@ -70,6 +70,22 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mcast(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -93,6 +109,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
@@ -166,6 +188,7 @@ struct TcArgs {
     ConvArgs a;
     const unsigned char *w;     // packed, pre-swizzled weight tiles of this mode
     int n_tile, n_chunks, MT, R, Rp, nW, nA, nR, tmem_cols, base_off_mode;
+    int CL;                     // CTAs per cluster sharing (multicasting) the weight stream
     uint32_t raw_bytes;         // fp32 slab as TMA delivers it: 8 quads x R rows x 16 B
     uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
     uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile (x2 with the 3xTF32 lo plane)
@@ -197,7 +220,7 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i)
             mbar_init(raw_full + i, 1), mbar_init(raw_empty + i, 128), mbar_init(a_ready + i, 128), mbar_init(a_empty + i, 1);
-        for (int i = 0; i < kMaxW; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, 1);
+        for (int i = 0; i < kMaxW; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, (uint32_t)p.CL);
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -206,6 +229,12 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Weight tiles are shared by the CL CTAs of a cluster (same column block, neighbouring time
+    // tiles): each CTA fetches 1/CL of every tile and multicasts it to all of them, so L2 is read
+    // once per cluster.  Peers must not signal barriers that are not initialised yet.
+    const uint16_t cmask = (uint16_t)((1u << p.CL) - 1u);
+    const uint32_t crank = p.CL > 1 ? cluster_ctarank() : 0u;
+    if (p.CL > 1) cluster_sync_all();
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -225,7 +254,13 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
                     mbar_wait(w_empty + sW, ((it / p.nW) & 1) ^ 1);
                     mbar_expect_tx(w_full + sW, p.wtile_bytes);
                     const size_t off = (((size_t)nblk * p.n_chunks + c) * a.KS + k) * (size_t)p.wtile_bytes;
-                    bulk_g2s(wring + sW * p.wtile_bytes, p.w + off, p.wtile_bytes, w_full + sW);
+                    if (p.CL > 1) {
+                        const uint32_t slice = p.wtile_bytes / (uint32_t)p.CL;
+                        bulk_g2s_mcast(wring + sW * p.wtile_bytes + crank * slice, p.w + off + crank * slice, slice,
+                                       w_full + sW, cmask);
+                    } else {
+                        bulk_g2s(wring + sW * p.wtile_bytes, p.w + off, p.wtile_bytes, w_full + sW);
+                    }
                 }
             }
         }
@@ -279,7 +314,8 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
                         }
                     }
                     first = 0;
-                    umma_commit(w_empty + sW);      // frees the weight slot when these MMAs retire
+                    if (p.CL > 1) umma_commit_mcast(w_empty + sW, cmask);   // slot is free once EVERY peer is done with it
+                    else umma_commit(w_empty + sW);
                 }
                 umma_commit(a_empty + sA);
             }
@@ -372,6 +408,7 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
+    if (p.CL > 1) cluster_sync_all();       // peers may still multicast into / arrive on this CTA's smem
 }
 
 // ------------------------------------------------------------------ host side
@@ -458,15 +495,20 @@ bool tc_supported(const TcWeights &w, const ConvArgs &a) {
 }
 
 template <int MODE>
-static int launch_mode(const TcArgs &p, dim3 grid, size_t smem, cudaStream_t st) {
+static int launch_mode(const TcArgs &p, dim3 grid, dim3 cluster, size_t smem, cudaStream_t st) {
     auto kern = conv1d_c4_tc_kernel<MODE>;
     static size_t configured = 0;
     if (smem > configured) {
         SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<grid, kTcThreads, smem, st>>>(p);
-    SVB_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = dim3(kTcThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster.x, attr[0].val.clusterDim.y = cluster.y, attr[0].val.clusterDim.z = cluster.z;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    SVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     return SVB_OK;
 }
 
@@ -504,7 +546,9 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     const size_t fixed = p.off_w;
     // The kernel hides load / epilogue latency with co-resident CTAs (64 registers, 192 threads):
     // TMEM allows 512 / cols of them, registers 5; size the weight ring so that many still fit.
+    const long long total_ctas = (long long)((tiles + MT - 1) / MT) * col_blocks * a.B;
     int want_ctas = std::max(1, std::min(5, 512 / cols));
+    want_ctas = (int)std::max<long long>(1, std::min<long long>(want_ctas, (total_ctas + 147) / 148));
     if (const char *e = getenv("SVB_TC_CTAS")) want_ctas = std::max(1, std::min(want_ctas, atoi(e)));
     const int min_ring = std::min(2, p.n_chunks * a.KS);
     while (want_ctas > 1 && fixed + (size_t)min_ring * p.wtile_bytes > (size_t)(227 * 1024) / want_ctas - 2048) --want_ctas;
@@ -516,10 +560,21 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     SVB_CHECK(smem <= 227 * 1024, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d MT %d, %zu B)", p.n_tile,
               MT, smem);
     dim3 grid((tiles + MT - 1) / MT, col_blocks, a.B);
+    // cluster: CTAs with the same column block share the weight stream; along time, else along batch
+    int CL = p.n_tile >= 128 ? 4 : 2;
+    if (const char *e = getenv("SVB_TC_CL")) CL = std::max(1, std::min(8, atoi(e)));
+    dim3 cluster(1, 1, 1);
+    while (CL > 1 && (p.wtile_bytes / CL) % 16 != 0) CL >>= 1;
+    while (CL > 1 && grid.x % CL != 0 && grid.z % CL != 0) CL >>= 1;
+    if (CL > 1) {
+        if (grid.x % CL == 0) cluster.x = CL;
+        else cluster.z = CL;
+    }
+    p.CL = CL;
     switch (precision) {
-        case SVB_PREC_TF32: return launch_mode<SVB_PREC_TF32>(p, grid, smem, st);
-        case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3>(p, grid, smem, st);
-        default: return launch_mode<SVB_PREC_BF16X3>(p, grid, smem, st);
+        case SVB_PREC_TF32: return launch_mode<SVB_PREC_TF32>(p, grid, cluster, smem, st);
+        case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3>(p, grid, cluster, smem, st);
+        default: return launch_mode<SVB_PREC_BF16X3>(p, grid, cluster, smem, st);
     }
 }
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Tuning sweep for the tcgen05 conv kernel: M-tiles per CTA (SVB_TC_MT) x resident-CTA target
+"""Tuning sweep for the tcgen05 conv kernel: cluster size of the weight multicast (SVB_TC_CL) x resident-CTA target
 (SVB_TC_CTAS) per generator layer shape at BASELINE config 2.  Prints one row per layer (us)."""
 import os
 import sys
@@ -13,8 +13,8 @@ from tools.layer_bench import B, SHAPES  # noqa: E402
 
 def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else 'bf16x3'
-    combos = [(mt, c) for mt in (1, 2, 4) for c in (5, 2)]
-    print('layer'.ljust(24) + ''.join(f'MT{mt}/c{c}'.rjust(9) for mt, c in combos))
+    combos = [(cl, c) for cl in (1, 2, 4, 8) for c in (5, 2)]
+    print('layer'.ljust(24) + ''.join(f'CL{cl}/c{c}'.rjust(9) for cl, c in combos))
     for name, Cin, Cout, T, K, dil, u, with_res in SHAPES:
         g = torch.Generator().manual_seed(1)
         x = torch.randn(B, Cin, T, generator=g).cuda()
@@ -23,7 +23,7 @@ def main():
         res = torch.randn(B, Cout, T * u if u else T, generator=g).cuda() if with_res else None
         row = name.ljust(24)
         for mt, c in combos:
-            os.environ['SVB_TC_MT'], os.environ['SVB_TC_CTAS'] = str(mt), str(c)
+            os.environ['SVB_TC_CL'], os.environ['SVB_TC_CTAS'] = str(mt), str(c)
             _, ms = run_layer(x, w, b, res, K, max(dil, 1), u, 0.1, 1.0, prec, iters=10)
             row += f'{ms * 1e3:9.1f}'
         print(row, flush=True)
