@@ -30,7 +30,7 @@ namespace svb {
 
 constexpr int kTcM = 128;       // rows per CTA (UMMA M)
 constexpr int kTcCK = 32;       // input channels per chunk = 4 MMAs of K = 8
-constexpr int kTcThreads = 192;
+
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -187,8 +187,9 @@ __device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t &hi, ui
 struct TcArgs {
     ConvArgs a;
     const unsigned char *w;     // packed, pre-swizzled weight tiles of this mode
-    int n_tile, n_chunks, MT, R, Rp, nW, nA, nR, tmem_cols, base_off_mode;
-    int CL;                     // CTAs per cluster sharing (multicasting) the weight stream
+    int n_tile, n_chunks, MT, R, Rp, nW, nA, nR, tmem_cols;
+    int col_blocks, groups_per_b, total_groups;
+    int dbg;                    // SVB_TC_DBG experiments: 1 = no MMAs, 2 = hi*hi only
     uint32_t raw_bytes;         // fp32 slab as TMA delivers it: 8 quads x R rows x 16 B
     uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
     uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile (x2 with the 3xTF32 lo plane)
@@ -196,9 +197,15 @@ struct TcArgs {
 };
 
 constexpr int kMaxW = 8;
+constexpr int kTcThreadsP = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-9 epilogue
 
+// Persistent kernel: one CTA per SM walks "groups" (MT consecutive 128-row tiles of one clip for
+// one column block).  Every stage is decoupled by mbarriers, so the TMA producer runs ahead into
+// the next group, the transform warps prepare operands while the tensor core works on the
+// previous chunk, and the epilogue drains accumulator set (g & 1) from TMEM while the MMAs of
+// group g + 1 fill the other set.
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
+__global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr bool BF = MODE == SVB_PREC_BF16X3;
     constexpr bool X3 = MODE == SVB_PREC_TF32X3;
@@ -207,21 +214,22 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
     uint64_t *raw_full = bars, *raw_empty = bars + 2, *a_ready = bars + 4, *a_empty = bars + 6;
     uint64_t *w_full = bars + 8, *w_empty = bars + 8 + kMaxW;
-    uint64_t *acc_full = bars + 8 + 2 * kMaxW;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 8 + 2 * kMaxW + 1);
+    uint64_t *acc_full = bars + 8 + 2 * kMaxW, *acc_empty = acc_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
     unsigned char *raw0 = smem + 256;                                // [nR][raw_bytes]
     unsigned char *op0 = smem + p.off_op;                            // [nA][op_bytes]
     unsigned char *wring = smem + p.off_w;                           // [nW][wtile_bytes]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.z, nblk = blockIdx.y, t0 = blockIdx.x * (kTcM * p.MT);
     const int halo = (a.KS - 1) / 2 * a.dil;
+    const int acc_cols = p.MT * p.n_tile;                            // columns of one accumulator set
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i) {
             mbar_init(raw_full + i, 1), mbar_init(raw_empty + i, 128), mbar_init(a_ready + i, 128), mbar_init(a_empty + i, 1);
-        for (int i = 0; i < kMaxW; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, (uint32_t)p.CL);
-        mbar_init(acc_full, 1);
+            mbar_init(acc_full + i, 1), mbar_init(acc_empty + i, 128);
+        }
+        for (int i = 0; i < kMaxW; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, p.tmem_cols);
@@ -229,36 +237,36 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    // Weight tiles are shared by the CL CTAs of a cluster (same column block, neighbouring time
-    // tiles): each CTA fetches 1/CL of every tile and multicasts it to all of them, so L2 is read
-    // once per cluster.  Peers must not signal barriers that are not initialised yet.
-    const uint16_t cmask = (uint16_t)((1u << p.CL) - 1u);
-    const uint32_t crank = p.CL > 1 ? cluster_ctarank() : 0u;
-    if (p.CL > 1) cluster_sync_all();
+
+    // group id -> (column block, clip, first row); consecutive ids are neighbours in time
+    auto decode = [&](int g, int &nblk, int &b, int &t0) {
+        const int tg = g % p.groups_per_b;
+        const int r = g / p.groups_per_b;
+        b = r % a.B, nblk = r / a.B, t0 = tg * (kTcM * p.MT);
+    };
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             const int cin_q = a.Cin >> 2;
-            const float *in_b = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4;
             const uint32_t qbytes = (uint32_t)p.R * 16;
-            for (int c = 0; c < p.n_chunks; ++c) {
-                const int sR = c % p.nR;
-                mbar_wait(raw_empty + sR, ((c / p.nR) & 1) ^ 1);
-                mbar_expect_tx(raw_full + sR, p.raw_bytes);
-                unsigned char *dst = raw0 + sR * p.raw_bytes;
-                for (int q = 0; q < 8; ++q)
-                    bulk_g2s(dst + q * qbytes, in_b + (size_t)(c * 8 + q) * a.in_Tp * 4, qbytes, raw_full + sR);
-                for (int k = 0; k < a.KS; ++k) {
-                    const int it = c * a.KS + k, sW = it % p.nW;
-                    mbar_wait(w_empty + sW, ((it / p.nW) & 1) ^ 1);
-                    mbar_expect_tx(w_full + sW, p.wtile_bytes);
-                    const size_t off = (((size_t)nblk * p.n_chunks + c) * a.KS + k) * (size_t)p.wtile_bytes;
-                    if (p.CL > 1) {
-                        const uint32_t slice = p.wtile_bytes / (uint32_t)p.CL;
-                        bulk_g2s_mcast(wring + sW * p.wtile_bytes + crank * slice, p.w + off + crank * slice, slice,
-                                       w_full + sW, cmask);
-                    } else {
+            int gc = 0, it = 0;
+            for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
+                int nblk, b, t0;
+                decode(g, nblk, b, t0);
+                const float *in_b = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4;
+                for (int c = 0; c < p.n_chunks; ++c, ++gc) {
+                    const int sR = gc % p.nR;
+                    mbar_wait(raw_empty + sR, ((gc / p.nR) & 1) ^ 1);
+                    mbar_expect_tx(raw_full + sR, p.raw_bytes);
+                    unsigned char *dst = raw0 + sR * p.raw_bytes;
+                    for (int q = 0; q < 8; ++q)
+                        bulk_g2s(dst + q * qbytes, in_b + (size_t)(c * 8 + q) * a.in_Tp * 4, qbytes, raw_full + sR);
+                    for (int k = 0; k < a.KS; ++k, ++it) {
+                        const int sW = it % p.nW;
+                        mbar_wait(w_empty + sW, ((it / p.nW) & 1) ^ 1);
+                        mbar_expect_tx(w_full + sW, p.wtile_bytes);
+                        const size_t off = (((size_t)nblk * p.n_chunks + c) * a.KS + k) * (size_t)p.wtile_bytes;
                         bulk_g2s(wring + sW * p.wtile_bytes, p.w + off, p.wtile_bytes, w_full + sW);
                     }
                 }
@@ -268,138 +276,159 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(BF ? 1 : 2, kTcM, p.n_tile);
-            const uint32_t w_hi_word = desc_hi_sw128(0);
+            const uint32_t hi_word = desc_hi_sw128(0);
             const uint32_t a_lo_plane = X3 ? p.op_bytes / 2 : 64u;      // byte offset of the lo plane / half-row
             const uint32_t b_lo_plane = X3 ? p.wtile_bytes / 2 : 64u;
-            uint32_t first = 1;
-            for (int c = 0; c < p.n_chunks; ++c) {
-                const int sA = c % p.nA;
-                mbar_wait(a_ready + sA, (c / p.nA) & 1);
+            int gc = 0, it = 0, gi = 0;
+            for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x, ++gi) {
+                const int as = gi & 1;
+                mbar_wait(acc_empty + as, ((gi >> 1) & 1) ^ 1);        // epilogue has drained this accumulator set
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(op0 + sA * p.op_bytes);
-                for (int k = 0; k < a.KS; ++k) {
-                    const int it = c * a.KS + k, sW = it % p.nW;
-                    mbar_wait(w_full + sW, (it / p.nW) & 1);
+                const uint32_t d_set = tmem_base + (uint32_t)(as * acc_cols);
+                uint32_t first = 1;
+                for (int c = 0; c < p.n_chunks; ++c, ++gc) {
+                    const int sA = gc % p.nA;
+                    mbar_wait(a_ready + sA, (gc / p.nA) & 1);
                     tc_fence_after();
-                    const uint32_t b_base = smem_u32(wring + sW * p.wtile_bytes);
-                    for (int m = 0; m < p.MT; ++m) {
-                        const uint32_t d = tmem_base + (uint32_t)(m * p.n_tile);
-                        const uint32_t a_row = a_base + (uint32_t)(k * a.dil + m * kTcM) * 128;   // tap = row shift
-                        const uint32_t a_hi_word = desc_hi_sw128(p.base_off_mode ? (a_row >> 7) : 0u);
-                        uint32_t acc = first ? 0u : 1u;
-                        if (BF) {
+                    const uint32_t a_base = smem_u32(op0 + sA * p.op_bytes);
+                    for (int k = 0; k < a.KS; ++k, ++it) {
+                        const int sW = it % p.nW;
+                        mbar_wait(w_full + sW, (it / p.nW) & 1);
+                        tc_fence_after();
+                        const uint32_t b_base = smem_u32(wring + sW * p.wtile_bytes);
+                        for (int m = 0; m < p.MT; ++m) {
+                            const uint32_t d = d_set + (uint32_t)(m * p.n_tile);
+                            const uint32_t a_row = a_base + (uint32_t)(k * a.dil + m * kTcM) * 128;   // tap = row shift
+                            uint32_t acc = first ? 0u : 1u;
+                            if (p.dbg == 1) continue;
+                            if (BF) {
 #pragma unroll
-                            for (int kb = 0; kb < 2; ++kb) {      // 2 x 16 channels; small cross terms first
-                                const uint32_t ah = desc_lo(a_row + kb * 32), al = desc_lo(a_row + a_lo_plane + kb * 32);
-                                const uint32_t bh = desc_lo(b_base + kb * 32), bl = desc_lo(b_base + b_lo_plane + kb * 32);
-                                umma<true>(d, al, a_hi_word, bh, w_hi_word, idesc, acc);
-                                umma<true>(d, ah, a_hi_word, bl, w_hi_word, idesc, 1u);
-                                umma<true>(d, ah, a_hi_word, bh, w_hi_word, idesc, 1u);
-                                acc = 1u;
-                            }
-                        } else {
-#pragma unroll
-                            for (int kb = 0; kb < 4; ++kb) {      // 4 x 8 channels
-                                const uint32_t ah = desc_lo(a_row + kb * 32), bh = desc_lo(b_base + kb * 32);
-                                if (X3) {
-                                    const uint32_t al = desc_lo(a_row + a_lo_plane + kb * 32);
-                                    const uint32_t bl = desc_lo(b_base + b_lo_plane + kb * 32);
-                                    umma<false>(d, al, a_hi_word, bh, w_hi_word, idesc, acc);
-                                    umma<false>(d, ah, a_hi_word, bl, w_hi_word, idesc, 1u);
+                                for (int kb = 0; kb < 2; ++kb) {      // 2 x 16 channels; small cross terms first
+                                    const uint32_t ah = desc_lo(a_row + kb * 32), al = desc_lo(a_row + a_lo_plane + kb * 32);
+                                    const uint32_t bh = desc_lo(b_base + kb * 32), bl = desc_lo(b_base + b_lo_plane + kb * 32);
+                                    if (p.dbg != 2) {
+                                        umma<true>(d, al, hi_word, bh, hi_word, idesc, acc);
+                                        umma<true>(d, ah, hi_word, bl, hi_word, idesc, 1u);
+                                        acc = 1u;
+                                    }
+                                    umma<true>(d, ah, hi_word, bh, hi_word, idesc, acc);
                                     acc = 1u;
                                 }
-                                umma<false>(d, ah, a_hi_word, bh, w_hi_word, idesc, acc);
-                                acc = 1u;
+                            } else {
+#pragma unroll
+                                for (int kb = 0; kb < 4; ++kb) {      // 4 x 8 channels
+                                    const uint32_t ah = desc_lo(a_row + kb * 32), bh = desc_lo(b_base + kb * 32);
+                                    if (X3) {
+                                        const uint32_t al = desc_lo(a_row + a_lo_plane + kb * 32);
+                                        const uint32_t bl = desc_lo(b_base + b_lo_plane + kb * 32);
+                                        umma<false>(d, al, hi_word, bh, hi_word, idesc, acc);
+                                        umma<false>(d, ah, hi_word, bl, hi_word, idesc, 1u);
+                                        acc = 1u;
+                                    }
+                                    umma<false>(d, ah, hi_word, bh, hi_word, idesc, acc);
+                                    acc = 1u;
+                                }
                             }
                         }
+                        first = 0;
+                        umma_commit(w_empty + sW);      // frees the weight slot when these MMAs retire
                     }
-                    first = 0;
-                    if (p.CL > 1) umma_commit_mcast(w_empty + sW, cmask);   // slot is free once EVERY peer is done with it
-                    else umma_commit(w_empty + sW);
+                    umma_commit(a_empty + sA);
                 }
-                umma_commit(a_empty + sA);
+                umma_commit(acc_full + as);
             }
-            umma_commit(acc_full);
+        }
+    } else if (warp < 6) {
+        // ====================== operand transform warps (128 threads) =================
+        const int tid = threadIdx.x - 64;                       // 0..127
+        int gc = 0;
+        for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
+            for (int c = 0; c < p.n_chunks; ++c, ++gc) {
+                const int sR = gc % p.nR, sA = gc % p.nA;
+                mbar_wait(raw_full + sR, (gc / p.nR) & 1);
+                mbar_wait(a_empty + sA, ((gc / p.nA) & 1) ^ 1);
+                const float4 *raw = reinterpret_cast<const float4 *>(raw0 + sR * p.raw_bytes);
+                uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
+                for (int r = tid; r < p.R; r += 128) {
+                    // row r: 8 quads (32 channels) -> one 128-byte operand row; chunk c16 lives at c16 ^ (r & 7)
+                    float4 v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = lrelu4(raw[q * p.R + r], a.in_slope);
+                    uint4 *row = op + (size_t)r * 8;
+                    const int sw = r & 7;
+                    if (BF) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {               // oct j = channels 8j .. 8j+7
+                            uint4 h, l;
+                            bf16_split2(v[2 * j].x, v[2 * j].y, h.x, l.x);
+                            bf16_split2(v[2 * j].z, v[2 * j].w, h.y, l.y);
+                            bf16_split2(v[2 * j + 1].x, v[2 * j + 1].y, h.z, l.z);
+                            bf16_split2(v[2 * j + 1].z, v[2 * j + 1].w, h.w, l.w);
+                            row[j ^ sw] = h;
+                            row[(4 + j) ^ sw] = l;
+                        }
+                    } else {
+                        uint4 *row_lo = row + (p.op_bytes / 32);    // lo plane (3xTF32): op_bytes / 2 bytes further
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 h = make_float4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
+                            row[q ^ sw] = make_uint4(__float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w));
+                            if (X3)
+                                row_lo[q ^ sw] = make_uint4(__float_as_uint(to_tf32(v[q].x - h.x)), __float_as_uint(to_tf32(v[q].y - h.y)),
+                                                            __float_as_uint(to_tf32(v[q].z - h.z)), __float_as_uint(to_tf32(v[q].w - h.w)));
+                        }
+                    }
+                }
+                fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(a_ready + sA);
+                mbar_arrive(raw_empty + sR);
+            }
         }
     } else {
-        // ====================== transform (main loop) + epilogue warps ================
-        const int tid = threadIdx.x - 64;                       // 0..127
-        for (int c = 0; c < p.n_chunks; ++c) {
-            const int sR = c % p.nR, sA = c % p.nA;
-            mbar_wait(raw_full + sR, (c / p.nR) & 1);
-            mbar_wait(a_empty + sA, ((c / p.nA) & 1) ^ 1);
-            const float4 *raw = reinterpret_cast<const float4 *>(raw0 + sR * p.raw_bytes);
-            uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
-            for (int r = tid; r < p.R; r += 128) {
-                // row r: 8 quads (32 channels) -> one 128-byte operand row; chunk c16 lives at c16 ^ (r & 7)
-                float4 v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = lrelu4(raw[q * p.R + r], a.in_slope);
-                uint4 *row = op + (size_t)r * 8;
-                const int sw = r & 7;
-                if (BF) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {               // oct j = channels 8j .. 8j+7
-                        uint4 h, l;
-                        bf16_split2(v[2 * j].x, v[2 * j].y, h.x, l.x);
-                        bf16_split2(v[2 * j].z, v[2 * j].w, h.y, l.y);
-                        bf16_split2(v[2 * j + 1].x, v[2 * j + 1].y, h.z, l.z);
-                        bf16_split2(v[2 * j + 1].z, v[2 * j + 1].w, h.w, l.w);
-                        row[j ^ sw] = h;
-                        row[(4 + j) ^ sw] = l;
-                    }
-                } else {
-                    uint4 *row_lo = row + (p.op_bytes / 32);    // lo plane (3xTF32): op_bytes / 2 bytes further
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 h = make_float4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
-                        row[q ^ sw] = make_uint4(__float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w));
-                        if (X3)
-                            row_lo[q ^ sw] = make_uint4(__float_as_uint(to_tf32(v[q].x - h.x)), __float_as_uint(to_tf32(v[q].y - h.y)),
-                                                        __float_as_uint(to_tf32(v[q].z - h.z)), __float_as_uint(to_tf32(v[q].w - h.w)));
-                    }
-                }
-            }
-            fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
-            mbar_arrive(a_ready + sA);
-            mbar_arrive(raw_empty + sR);
-        }
-        // ---- epilogue: TMEM lane = time row, column = output channel.  Kept register-light on
-        // purpose: residual latency is hidden by co-resident CTAs, not by per-thread prefetch.
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int lane_base = 32 * (warp & 3);                  // a warp may only touch its own TMEM lane quarter
+        // ================================ epilogue warps (128 threads) ================
+        // TMEM lane = time row, column = output channel; a warp may only touch lanes 32*(warp%4)..+31
+        const int lane_base = 32 * (warp & 3);
         const int out_q = a.Cout >> 2;
         const float4 *res4 = reinterpret_cast<const float4 *>(a.res);
         float4 *out4 = reinterpret_cast<float4 *>(a.out);
-        for (int m = 0; m < p.MT; ++m) {
-            const int q = t0 + m * kTcM + lane_base + lane;     // GEMM row of this thread
-            for (int j = 0; j < p.n_tile / 32; ++j) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(m * p.n_tile + j * 32), v);
-                if (q >= a.Tq) continue;
-                const int cop0 = nblk * p.n_tile + j * 32;      // 32 columns never straddle an upsampler phase
-                int phi = 0, co0 = cop0;
-                if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
-                const size_t row0 = ((size_t)b * out_q + (co0 >> 2)) * a.out_Tp + kPad +
-                                    (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q);
+        int gi = 0;
+        for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x, ++gi) {
+            int nblk, b, t0;
+            decode(g, nblk, b, t0);
+            const int as = gi & 1;
+            mbar_wait(acc_full + as, (gi >> 1) & 1);
+            tc_fence_after();
+            for (int m = 0; m < p.MT; ++m) {
+                const int q = t0 + m * kTcM + lane_base + lane;     // GEMM row of this thread
+                for (int j = 0; j < p.n_tile / 32; ++j) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * acc_cols + m * p.n_tile + j * 32), v);
+                    if (q >= a.Tq) continue;
+                    const int cop0 = nblk * p.n_tile + j * 32;      // 32 columns never straddle an upsampler phase
+                    int phi = 0, co0 = cop0;
+                    if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
+                    const size_t row0 = ((size_t)b * out_q + (co0 >> 2)) * a.out_Tp + kPad +
+                                        (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q);
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const size_t row = row0 + (size_t)g * a.out_Tp;
-                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co0 + 4 * g));
-                    float4 o = make_float4(v[4 * g] + bv.x, v[4 * g + 1] + bv.y, v[4 * g + 2] + bv.z, v[4 * g + 3] + bv.w);
-                    if (res4) {
-                        const float4 rv = __ldg(res4 + row);
-                        o.x += rv.x, o.y += rv.y, o.z += rv.z, o.w += rv.w;
+                    for (int gq = 0; gq < 8; ++gq) {
+                        const size_t row = row0 + (size_t)gq * a.out_Tp;
+                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co0 + 4 * gq));
+                        float4 o = make_float4(v[4 * gq] + bv.x, v[4 * gq + 1] + bv.y, v[4 * gq + 2] + bv.z, v[4 * gq + 3] + bv.w);
+                        if (res4) {
+                            const float4 rv = __ldg(res4 + row);
+                            o.x += rv.x, o.y += rv.y, o.z += rv.z, o.w += rv.w;
+                        }
+                        o.x *= a.out_scale, o.y *= a.out_scale, o.z *= a.out_scale, o.w *= a.out_scale;
+                        if (a.accumulate) {
+                            const float4 old = out4[row];
+                            o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+                        }
+                        out4[row] = o;
                     }
-                    o.x *= a.out_scale, o.y *= a.out_scale, o.z *= a.out_scale, o.w *= a.out_scale;
-                    if (a.accumulate) {
-                        const float4 old = out4[row];
-                        o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
-                    }
-                    out4[row] = o;
                 }
             }
+            tc_fence_before();
+            mbar_arrive(acc_empty + as);                            // this accumulator set may be overwritten
         }
     }
     tc_fence_before();
@@ -408,7 +437,6 @@ __global__ void __launch_bounds__(kTcThreads) conv1d_c4_tc_kernel(TcArgs p) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
-    if (p.CL > 1) cluster_sync_all();       // peers may still multicast into / arrive on this CTA's smem
 }
 
 // ------------------------------------------------------------------ host side
@@ -438,8 +466,8 @@ static float bf16_to_float(uint16_t h) {
 
 static int pick_n_tile(int CoutP) {
     if (CoutP % 16 != 0) return 0;
-    if (CoutP <= 256) return CoutP;
-    for (int n = 256; n >= 16; n -= 16)
+    if (CoutP <= 128) return CoutP;
+    for (int n = 128; n >= 16; n -= 16)
         if (CoutP % n == 0) return n;
     return 0;
 }
@@ -495,21 +523,27 @@ bool tc_supported(const TcWeights &w, const ConvArgs &a) {
 }
 
 template <int MODE>
-static int launch_mode(const TcArgs &p, dim3 grid, dim3 cluster, size_t smem, cudaStream_t st) {
+static int launch_mode(const TcArgs &p, int grid, size_t smem, cudaStream_t st) {
     auto kern = conv1d_c4_tc_kernel<MODE>;
     static size_t configured = 0;
     if (smem > configured) {
         SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid, cfg.blockDim = dim3(kTcThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster.x, attr[0].val.clusterDim.y = cluster.y, attr[0].val.clusterDim.z = cluster.z;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    SVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    kern<<<grid, kTcThreadsP, smem, st>>>(p);
+    SVB_CUDA(cudaGetLastError());
     return SVB_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
 
 int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st) {
@@ -519,62 +553,49 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     p.a = a, p.w = reinterpret_cast<const unsigned char *>(w.blob[precision]);
     p.n_tile = w.n_tile, p.n_chunks = a.Cin / kTcCK;
     const int halo = (a.KS - 1) / 2 * a.dil;
-    const int tiles = (a.Tq + kTcM - 1) / kTcM;              // 128-row tiles per batch item
-    const int col_blocks = a.CoutP / p.n_tile;
+    const int tiles = (a.Tq + kTcM - 1) / kTcM;              // 128-row tiles per clip
+    p.col_blocks = a.CoutP / p.n_tile;
     const int planes = precision == SVB_PREC_TF32X3 ? 2 : 1;
     p.wtile_bytes = (uint32_t)p.n_tile * 128 * planes;
-    // ---- M tiles per CTA (weight-tile reuse); measured: MT = 1 with many co-resident CTAs wins
-    int MT = 1;
-    if (const char *e = getenv("SVB_TC_MT")) {
-        const int f = atoi(e);
-        if ((f == 1 || f == 2 || f == 4) && f * p.n_tile <= 512 && (tiles + f - 1) / f * f * kTcM <= round_up(a.Tq, kTileT)) MT = f;
+    p.nA = std::min(2, p.n_chunks * 2), p.nR = 2;
+    p.nA = 2;
+    p.dbg = 0;
+    if (const char *e = getenv("SVB_TC_DBG")) p.dbg = atoi(e);
+    int force_mt = 0;
+    if (const char *e = getenv("SVB_TC_MT")) force_mt = atoi(e);
+    // ---- M tiles per group: each weight tile fetched from L2 feeds MT accumulators.  Two accumulator
+    // sets live in TMEM (2 * MT * N <= 512 columns); slabs and the weight ring must fit shared memory.
+    size_t smem = 0;
+    for (int MT : {4, 2, 1}) {
+        if (force_mt && MT != force_mt && MT != 1) continue;
+        if (2 * MT * p.n_tile > 512) continue;
+        if ((tiles + MT - 1) / MT * MT * kTcM > round_up(a.Tq, kTileT) && MT != 1) continue;   // stay inside the allocation
+        p.MT = MT;
+        p.R = MT * kTcM + 2 * halo;
+        p.Rp = round_up(p.R, 8);
+        p.raw_bytes = (uint32_t)8 * p.R * 16;
+        p.op_bytes = (uint32_t)p.Rp * 128 * planes;
+        p.off_op = (uint32_t)round_up(256 + p.nR * (int)p.raw_bytes, 1024);
+        p.off_w = p.off_op + (uint32_t)p.nA * p.op_bytes;
+        const size_t budget = 226 * 1024;
+        if (p.off_w + 2 * (size_t)p.wtile_bytes > budget && MT != 1) continue;
+        int nW = p.off_w < budget ? (int)((budget - p.off_w) / p.wtile_bytes) : 0;
+        nW = std::min(std::min(nW, kMaxW), p.n_chunks * a.KS * 4);
+        SVB_CHECK(nW >= 1, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d)", p.n_tile);
+        p.nW = nW;
+        smem = p.off_w + (size_t)nW * p.wtile_bytes;
+        break;
     }
-    p.MT = MT;
-    p.R = MT * kTcM + 2 * halo;
-    p.Rp = round_up(p.R, 8);
-    p.raw_bytes = (uint32_t)8 * p.R * 16;
-    p.op_bytes = (uint32_t)p.Rp * 128 * planes;
-    p.nA = std::min(2, p.n_chunks);
-    p.nR = 1;
-    p.base_off_mode = 0;
-    if (const char *e = getenv("SVB_TC_BASEOFF")) p.base_off_mode = atoi(e) != 0;
     int cols = 32;
-    while (cols < MT * p.n_tile) cols <<= 1;
+    while (cols < 2 * p.MT * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
-    p.off_op = (uint32_t)round_up(256 + p.nR * (int)p.raw_bytes, 1024);
-    p.off_w = p.off_op + (uint32_t)p.nA * p.op_bytes;          // op_bytes is a multiple of 1024
-    const size_t fixed = p.off_w;
-    // The kernel hides load / epilogue latency with co-resident CTAs (64 registers, 192 threads):
-    // TMEM allows 512 / cols of them, registers 5; size the weight ring so that many still fit.
-    const long long total_ctas = (long long)((tiles + MT - 1) / MT) * col_blocks * a.B;
-    int want_ctas = std::max(1, std::min(5, 512 / cols));
-    want_ctas = (int)std::max<long long>(1, std::min<long long>(want_ctas, (total_ctas + 147) / 148));
-    if (const char *e = getenv("SVB_TC_CTAS")) want_ctas = std::max(1, std::min(want_ctas, atoi(e)));
-    const int min_ring = std::min(2, p.n_chunks * a.KS);
-    while (want_ctas > 1 && fixed + (size_t)min_ring * p.wtile_bytes > (size_t)(227 * 1024) / want_ctas - 2048) --want_ctas;
-    const size_t budget = (size_t)(227 * 1024) / want_ctas - 2048;
-    int nW = budget > fixed ? (int)((budget - fixed) / p.wtile_bytes) : 1;
-    nW = std::max(1, std::min(std::min(nW, kMaxW), p.n_chunks * a.KS));
-    p.nW = nW;
-    const size_t smem = fixed + (size_t)nW * p.wtile_bytes;
-    SVB_CHECK(smem <= 227 * 1024, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d MT %d, %zu B)", p.n_tile,
-              MT, smem);
-    dim3 grid((tiles + MT - 1) / MT, col_blocks, a.B);
-    // cluster: CTAs with the same column block share the weight stream; along time, else along batch
-    int CL = p.n_tile >= 128 ? 4 : 2;
-    if (const char *e = getenv("SVB_TC_CL")) CL = std::max(1, std::min(8, atoi(e)));
-    dim3 cluster(1, 1, 1);
-    while (CL > 1 && (p.wtile_bytes / CL) % 16 != 0) CL >>= 1;
-    while (CL > 1 && grid.x % CL != 0 && grid.z % CL != 0) CL >>= 1;
-    if (CL > 1) {
-        if (grid.x % CL == 0) cluster.x = CL;
-        else cluster.z = CL;
-    }
-    p.CL = CL;
+    p.groups_per_b = (tiles + p.MT - 1) / p.MT;
+    p.total_groups = p.groups_per_b * a.B * p.col_blocks;
+    const int grid = std::min(p.total_groups, sm_count());
     switch (precision) {
-        case SVB_PREC_TF32: return launch_mode<SVB_PREC_TF32>(p, grid, cluster, smem, st);
-        case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3>(p, grid, cluster, smem, st);
-        default: return launch_mode<SVB_PREC_BF16X3>(p, grid, cluster, smem, st);
+        case SVB_PREC_TF32: return launch_mode<SVB_PREC_TF32>(p, grid, smem, st);
+        case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3>(p, grid, smem, st);
+        default: return launch_mode<SVB_PREC_BF16X3>(p, grid, smem, st);
     }
 }
 
