@@ -197,7 +197,7 @@ struct TcArgs {
 };
 
 constexpr int kMaxW = 8;
-constexpr int kTcThreadsP = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-9 epilogue
+constexpr int kTcThreadsP = 448;   // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-13 epilogue
 
 // Persistent kernel: one CTA per SM walks "groups" (MT consecutive 128-row tiles of one clip for
 // one column block).  Every stage is decoupled by mbarriers, so the TMA producer runs ahead into
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(raw_full + i, 1), mbar_init(raw_empty + i, 128), mbar_init(a_ready + i, 128), mbar_init(a_empty + i, 1);
-            mbar_init(acc_full + i, 1), mbar_init(acc_empty + i, 128);
+            mbar_init(acc_full + i, 1), mbar_init(acc_empty + i, 256);
         }
         for (int i = 0; i < kMaxW; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, 1);
         fence_barrier_init();
@@ -385,39 +385,60 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
             }
         }
     } else {
-        // ================================ epilogue warps (128 threads) ================
-        // TMEM lane = time row, column = output channel; a warp may only touch lanes 32*(warp%4)..+31
+        // ================================ epilogue warps (256 threads) ================
+        // TMEM lane = time row, column = output channel; a warp may only touch lanes 32*(warp%4)..+31,
+        // so two warps share each lane quarter and alternate over the 32-column blocks.  The residual
+        // rows of the NEXT block are requested before the current block is drained from TMEM, and
+        // the first request is issued before the accumulator is even complete: residual latency
+        // overlaps the MMAs instead of serialising behind them.
         const int lane_base = 32 * (warp & 3);
+        const int half = (warp - 6) >> 2;                           // 0 / 1: which blocks this warp takes
         const int out_q = a.Cout >> 2;
         const float4 *res4 = reinterpret_cast<const float4 *>(a.res);
         float4 *out4 = reinterpret_cast<float4 *>(a.out);
+        const int jb = p.n_tile / 32, nblocks = p.MT * jb;
         int gi = 0;
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x, ++gi) {
             int nblk, b, t0;
             decode(g, nblk, b, t0);
             const int as = gi & 1;
+            // block -> first C4T row (float4 index) of this thread's 8 quads, or -1 if the row is padding
+            auto block_row0 = [&](int blk, int &co0) -> long long {
+                const int m = blk / jb, j = blk - m * jb;
+                const int q = t0 + m * kTcM + lane_base + lane;
+                const int cop0 = nblk * p.n_tile + j * 32;          // 32 columns never straddle an upsampler phase
+                int phi = 0;
+                co0 = cop0;
+                if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
+                if (q >= a.Tq) return -1;
+                return (long long)(((size_t)b * out_q + (co0 >> 2)) * a.out_Tp + kPad +
+                                   (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q));
+            };
+            float4 rcur[8], rnxt[8];
+            auto fetch_res = [&](int blk, float4 *dst) {
+                int co0;
+                const long long row0 = blk < nblocks ? block_row0(blk, co0) : -1;
+#pragma unroll
+                for (int gq = 0; gq < 8; ++gq)
+                    dst[gq] = (res4 && row0 >= 0) ? __ldg(res4 + row0 + (long long)gq * a.out_Tp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            fetch_res(half, rcur);
             mbar_wait(acc_full + as, (gi >> 1) & 1);
             tc_fence_after();
-            for (int m = 0; m < p.MT; ++m) {
-                const int q = t0 + m * kTcM + lane_base + lane;     // GEMM row of this thread
-                for (int j = 0; j < p.n_tile / 32; ++j) {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * acc_cols + m * p.n_tile + j * 32), v);
-                    if (q >= a.Tq) continue;
-                    const int cop0 = nblk * p.n_tile + j * 32;      // 32 columns never straddle an upsampler phase
-                    int phi = 0, co0 = cop0;
-                    if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
-                    const size_t row0 = ((size_t)b * out_q + (co0 >> 2)) * a.out_Tp + kPad +
-                                        (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q);
+            for (int blk = half; blk < nblocks; blk += 2) {
+                fetch_res(blk + 2, rnxt);
+                const int m = blk / jb, j = blk - m * jb;
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * acc_cols + m * p.n_tile + j * 32), v);
+                int co0;
+                const long long row0 = block_row0(blk, co0);
+                if (row0 >= 0) {
 #pragma unroll
                     for (int gq = 0; gq < 8; ++gq) {
-                        const size_t row = row0 + (size_t)gq * a.out_Tp;
+                        const size_t row = (size_t)row0 + (size_t)gq * a.out_Tp;
                         const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co0 + 4 * gq));
-                        float4 o = make_float4(v[4 * gq] + bv.x, v[4 * gq + 1] + bv.y, v[4 * gq + 2] + bv.z, v[4 * gq + 3] + bv.w);
-                        if (res4) {
-                            const float4 rv = __ldg(res4 + row);
-                            o.x += rv.x, o.y += rv.y, o.z += rv.z, o.w += rv.w;
-                        }
+                        float4 o = make_float4(v[4 * gq] + bv.x + rcur[gq].x, v[4 * gq + 1] + bv.y + rcur[gq].y,
+                                               v[4 * gq + 2] + bv.z + rcur[gq].z, v[4 * gq + 3] + bv.w + rcur[gq].w);
                         o.x *= a.out_scale, o.y *= a.out_scale, o.z *= a.out_scale, o.w *= a.out_scale;
                         if (a.accumulate) {
                             const float4 old = out4[row];
@@ -426,6 +447,8 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                         out4[row] = o;
                     }
                 }
+#pragma unroll
+                for (int gq = 0; gq < 8; ++gq) rcur[gq] = rnxt[gq];
             }
             tc_fence_before();
             mbar_arrive(acc_empty + as);                            // this accumulator set may be overwritten
