@@ -189,6 +189,8 @@ struct TcArgs {
     const unsigned char *w;     // packed, pre-swizzled weight tiles of this mode
     int n_tile, n_chunks, MT, R, Rp, nW, nA, nR, tmem_cols;
     int col_blocks, groups_per_b, total_groups;
+    int tps, n_st, w_resident;  // taps per weight stage, stages per chunk, whole layer resident in smem
+    uint32_t wstage_bytes;      // ring slot = tps weight tiles
     int dbg;                    // SVB_TC_DBG experiments: 1 = no MMAs, 2 = hi*hi only
     uint32_t raw_bytes;         // fp32 slab as TMA delivers it: 8 quads x R rows x 16 B
     uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
@@ -247,29 +249,37 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            const int cin_q = a.Cin >> 2;
-            const uint32_t qbytes = (uint32_t)p.R * 16;
-            int gc = 0, it = 0;
-            for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
-                int nblk, b, t0;
-                decode(g, nblk, b, t0);
-                const float *in_b = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4;
-                for (int c = 0; c < p.n_chunks; ++c, ++gc) {
-                    const int sR = gc % p.nR;
+        // lane 0 owns the barriers; lanes 0..7 each issue one quad of the slab so the eight copies
+        // leave in parallel.  A weight stage (tps taps of one chunk) is ONE bulk copy.
+        const int cin_q = a.Cin >> 2;
+        const uint32_t qbytes = (uint32_t)p.R * 16;
+        int gc = 0, it = 0;
+        for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
+            int nblk, b, t0;
+            decode(g, nblk, b, t0);
+            const float *in_b = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4;
+            for (int c = 0; c < p.n_chunks; ++c, ++gc) {
+                const int sR = gc % p.nR;
+                if (lane == 0) {
                     mbar_wait(raw_empty + sR, ((gc / p.nR) & 1) ^ 1);
                     mbar_expect_tx(raw_full + sR, p.raw_bytes);
-                    unsigned char *dst = raw0 + sR * p.raw_bytes;
-                    for (int q = 0; q < 8; ++q)
-                        bulk_g2s(dst + q * qbytes, in_b + (size_t)(c * 8 + q) * a.in_Tp * 4, qbytes, raw_full + sR);
-                    for (int k = 0; k < a.KS; ++k, ++it) {
+                }
+                __syncwarp();
+                if (lane < 8)
+                    bulk_g2s(raw0 + sR * p.raw_bytes + lane * qbytes, in_b + (size_t)(c * 8 + lane) * a.in_Tp * 4, qbytes,
+                             raw_full + sR);
+                if (lane == 0 && !(p.w_resident && g != (int)blockIdx.x)) {
+                    for (int st = 0; st < p.n_st; ++st, ++it) {
                         const int sW = it % p.nW;
+                        const int k0 = st * p.tps, nt = min(p.tps, a.KS - k0);
+                        const uint32_t bytes = (uint32_t)nt * p.wtile_bytes;
                         mbar_wait(w_empty + sW, ((it / p.nW) & 1) ^ 1);
-                        mbar_expect_tx(w_full + sW, p.wtile_bytes);
-                        const size_t off = (((size_t)nblk * p.n_chunks + c) * a.KS + k) * (size_t)p.wtile_bytes;
-                        bulk_g2s(wring + sW * p.wtile_bytes, p.w + off, p.wtile_bytes, w_full + sW);
+                        mbar_expect_tx(w_full + sW, bytes);
+                        const size_t off = (((size_t)nblk * p.n_chunks + c) * a.KS + k0) * (size_t)p.wtile_bytes;
+                        bulk_g2s(wring + sW * p.wstage_bytes, p.w + off, bytes, w_full + sW);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
@@ -291,11 +301,14 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                     mbar_wait(a_ready + sA, (gc / p.nA) & 1);
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(op0 + sA * p.op_bytes);
-                    for (int k = 0; k < a.KS; ++k, ++it) {
-                        const int sW = it % p.nW;
-                        mbar_wait(w_full + sW, (it / p.nW) & 1);
-                        tc_fence_after();
-                        const uint32_t b_base = smem_u32(wring + sW * p.wtile_bytes);
+                    for (int k = 0; k < a.KS; ++k) {
+                        const int st = k / p.tps;
+                        const int sW = p.w_resident ? 0 : (it + st) % p.nW;
+                        if (k == st * p.tps && !(p.w_resident && gi > 0)) {     // first tap of a stage: wait for its copy
+                            mbar_wait(w_full + sW, ((it + st) / p.nW) & 1);
+                            tc_fence_after();
+                        }
+                        const uint32_t b_base = smem_u32(wring + sW * p.wstage_bytes) + (uint32_t)(k - st * p.tps) * p.wtile_bytes;
                         for (int m = 0; m < p.MT; ++m) {
                             const uint32_t d = d_set + (uint32_t)(m * p.n_tile);
                             const uint32_t a_row = a_base + (uint32_t)(k * a.dil + m * kTcM) * 128;   // tap = row shift
@@ -331,8 +344,10 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                             }
                         }
                         first = 0;
-                        umma_commit(w_empty + sW);      // frees the weight slot when these MMAs retire
+                        if (!p.w_resident && (k + 1 == a.KS || (k + 1) % p.tps == 0))
+                            umma_commit(w_empty + sW);  // frees the weight stage when these MMAs retire
                     }
+                    if (!p.w_resident) it += p.n_st;
                     umma_commit(a_empty + sA);
                 }
                 umma_commit(acc_full + as);
@@ -589,6 +604,7 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     // ---- M tiles per group: each weight tile fetched from L2 feeds MT accumulators.  Two accumulator
     // sets live in TMEM (2 * MT * N <= 512 columns); slabs and the weight ring must fit shared memory.
     size_t smem = 0;
+    const size_t budget = 226 * 1024;
     for (int MT : {4, 2, 1}) {
         if (force_mt && MT != force_mt && MT != 1) continue;
         if (2 * MT * p.n_tile > 512) continue;
@@ -598,15 +614,25 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         p.Rp = round_up(p.R, 8);
         p.raw_bytes = (uint32_t)8 * p.R * 16;
         p.op_bytes = (uint32_t)p.Rp * 128 * planes;
+        // wide (tensor-bound) layers need weight bytes in flight more than slab bytes: one raw slot
+        p.nR = p.n_tile >= 128 ? 1 : 2;
         p.off_op = (uint32_t)round_up(256 + p.nR * (int)p.raw_bytes, 1024);
         p.off_w = p.off_op + (uint32_t)p.nA * p.op_bytes;
-        const size_t budget = 226 * 1024;
         if (p.off_w + 2 * (size_t)p.wtile_bytes > budget && MT != 1) continue;
-        int nW = p.off_w < budget ? (int)((budget - p.off_w) / p.wtile_bytes) : 0;
-        nW = std::min(std::min(nW, kMaxW), p.n_chunks * a.KS * 4);
-        SVB_CHECK(nW >= 1, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d)", p.n_tile);
+        SVB_CHECK(p.off_w + (size_t)p.wtile_bytes <= budget, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d)",
+                  p.n_tile);
+        // weight stage = as many taps of one chunk as fit in ~48 KB, fetched by a single bulk copy
+        const size_t avail = budget - p.off_w;
+        int tps = (int)std::min<size_t>(a.KS, std::max<size_t>(1, std::min<size_t>(48 * 1024, avail / 2) / p.wtile_bytes));
+        if ((size_t)a.KS * p.wtile_bytes <= avail && p.n_chunks == 1 && p.col_blocks == 1) tps = a.KS;   // whole layer fits
+        p.tps = tps;
+        p.n_st = (a.KS + tps - 1) / tps;
+        p.wstage_bytes = (uint32_t)tps * p.wtile_bytes;
+        p.w_resident = (p.n_chunks * p.n_st == 1 && p.col_blocks == 1) ? 1 : 0;
+        int nW = (int)(avail / p.wstage_bytes);
+        nW = std::max(1, std::min(std::min(nW, kMaxW), p.w_resident ? 1 : 1 << 30));
         p.nW = nW;
-        smem = p.off_w + (size_t)nW * p.wtile_bytes;
+        smem = p.off_w + (size_t)nW * p.wstage_bytes;
         break;
     }
     int cols = 32;
