@@ -86,6 +86,15 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -247,78 +256,96 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         b = r % a.B, nblk = r / a.B, t0 = tg * (kTcM * p.MT);
     };
 
+    // The two single-thread roles below are latency-critical (every instruction they execute sits
+    // between two TMA copies or two MMAs), so all ring indices / phases are kept as incrementing
+    // counters -- no runtime integer divisions in the loops.
     if (warp == 0) {
         // ================================ TMA producer ================================
         // lane 0 owns the barriers; lanes 0..7 each issue one quad of the slab so the eight copies
-        // leave in parallel.  A weight stage (tps taps of one chunk) is ONE bulk copy.
+        // leave in parallel.
         const int cin_q = a.Cin >> 2;
         const uint32_t qbytes = (uint32_t)p.R * 16;
-        int gc = 0, it = 0;
+        const size_t quad_stride = (size_t)a.in_Tp * 4;                       // floats between channel quads
+        const size_t chunk_w_bytes = (size_t)a.KS * p.wtile_bytes;
+        int sR = 0, phR = 1, sW = 0, phW = 1;                                 // "empty" barriers start free
+        int tg = blockIdx.x % p.groups_per_b, rb = blockIdx.x / p.groups_per_b;   // group -> (time group, b + B*nblk)
+        const int step_tg = gridDim.x % p.groups_per_b, step_rb = gridDim.x / p.groups_per_b;
+        bool first_group = true;
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
-            int nblk, b, t0;
-            decode(g, nblk, b, t0);
-            const float *in_b = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4;
-            for (int c = 0; c < p.n_chunks; ++c, ++gc) {
-                const int sR = gc % p.nR;
+            const int b = rb % a.B, nblk = rb / a.B;
+            const int t0 = tg * (kTcM * p.MT);
+            const float *in_q = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4 + (size_t)lane * quad_stride;
+            const unsigned char *w_c = p.w + (size_t)nblk * p.n_chunks * chunk_w_bytes;
+            for (int c = 0; c < p.n_chunks; ++c) {
                 if (lane == 0) {
-                    mbar_wait(raw_empty + sR, ((gc / p.nR) & 1) ^ 1);
+                    mbar_wait(raw_empty + sR, phR);
                     mbar_expect_tx(raw_full + sR, p.raw_bytes);
                 }
                 __syncwarp();
-                if (lane < 8)
-                    bulk_g2s(raw0 + sR * p.raw_bytes + lane * qbytes, in_b + (size_t)(c * 8 + lane) * a.in_Tp * 4, qbytes,
-                             raw_full + sR);
-                if (lane == 0 && !(p.w_resident && g != (int)blockIdx.x)) {
-                    for (int st = 0; st < p.n_st; ++st, ++it) {
-                        const int sW = it % p.nW;
-                        const int k0 = st * p.tps, nt = min(p.tps, a.KS - k0);
+                if (lane < 8) bulk_g2s(raw0 + sR * p.raw_bytes + lane * qbytes, in_q, qbytes, raw_full + sR);
+                in_q += 8 * quad_stride;
+                if (++sR == p.nR) sR = 0, phR ^= 1;
+                if (lane == 0 && !(p.w_resident && !first_group)) {
+                    const unsigned char *w_k = w_c;
+                    for (int st = 0; st < p.n_st; ++st) {
+                        const int nt = min(p.tps, a.KS - st * p.tps);
                         const uint32_t bytes = (uint32_t)nt * p.wtile_bytes;
-                        mbar_wait(w_empty + sW, ((it / p.nW) & 1) ^ 1);
+                        mbar_wait(w_empty + sW, phW);
                         mbar_expect_tx(w_full + sW, bytes);
-                        const size_t off = (((size_t)nblk * p.n_chunks + c) * a.KS + k0) * (size_t)p.wtile_bytes;
-                        bulk_g2s(wring + sW * p.wstage_bytes, p.w + off, bytes, w_full + sW);
+                        bulk_g2s(wring + sW * p.wstage_bytes, w_k, bytes, w_full + sW);
+                        w_k += bytes;
+                        if (++sW == p.nW) sW = 0, phW ^= 1;
                     }
                 }
+                w_c += chunk_w_bytes;
                 __syncwarp();
             }
+            first_group = false;
+            tg += step_tg, rb += step_rb;
+            if (tg >= p.groups_per_b) tg -= p.groups_per_b, ++rb;
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(BF ? 1 : 2, kTcM, p.n_tile);
-            const uint32_t hi_word = desc_hi_sw128(0);
-            const uint32_t a_lo_plane = X3 ? p.op_bytes / 2 : 64u;      // byte offset of the lo plane / half-row
-            const uint32_t b_lo_plane = X3 ? p.wtile_bytes / 2 : 64u;
-            int gc = 0, it = 0, gi = 0;
-            for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x, ++gi) {
-                const int as = gi & 1;
-                mbar_wait(acc_empty + as, ((gi >> 1) & 1) ^ 1);        // epilogue has drained this accumulator set
+        // The whole warp walks the loop (waits are warp-wide); one elected lane issues the MMAs.
+        const uint32_t elected = elect_one_sync();
+        const uint32_t idesc = umma_idesc(BF ? 1 : 2, kTcM, p.n_tile);
+        const uint32_t hi_word = desc_hi_sw128(0);
+        const uint32_t a_lo_plane = X3 ? p.op_bytes / 2 : 64u;      // byte offset of the lo plane / half-row
+        const uint32_t b_lo_plane = X3 ? p.wtile_bytes / 2 : 64u;
+        const uint32_t op_base = smem_u32(op0), w_base = smem_u32(wring);
+        const uint32_t tap_step = (uint32_t)a.dil * 128;            // a tap is a row shift of the operand
+        int sA = 0, phA = 0, sW = 0, phW = 0, as = 0, phE = 1;
+        bool first_group = true;
+        for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
+            mbar_wait(acc_empty + as, phE);                         // epilogue has drained this accumulator set
+            tc_fence_after();
+            const uint32_t d_set = tmem_base + (uint32_t)(as * acc_cols);
+            uint32_t fresh = 1;                                     // first MMA of the group overwrites
+            for (int c = 0; c < p.n_chunks; ++c) {
+                mbar_wait(a_ready + sA, phA);
                 tc_fence_after();
-                const uint32_t d_set = tmem_base + (uint32_t)(as * acc_cols);
-                uint32_t first = 1;
-                for (int c = 0; c < p.n_chunks; ++c, ++gc) {
-                    const int sA = gc % p.nA;
-                    mbar_wait(a_ready + sA, (gc / p.nA) & 1);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(op0 + sA * p.op_bytes);
-                    for (int k = 0; k < a.KS; ++k) {
-                        const int st = k / p.tps;
-                        const int sW = p.w_resident ? 0 : (it + st) % p.nW;
-                        if (k == st * p.tps && !(p.w_resident && gi > 0)) {     // first tap of a stage: wait for its copy
-                            mbar_wait(w_full + sW, ((it + st) / p.nW) & 1);
+                uint32_t a_tap = op_base + sA * p.op_bytes;
+                int in_stage = 0;
+                uint32_t b_tap = 0;
+                for (int k = 0; k < a.KS; ++k) {
+                    if (in_stage == 0) {                            // first tap of a weight stage
+                        if (!(p.w_resident && !first_group)) {
+                            mbar_wait(w_full + sW, phW);
                             tc_fence_after();
                         }
-                        const uint32_t b_base = smem_u32(wring + sW * p.wstage_bytes) + (uint32_t)(k - st * p.tps) * p.wtile_bytes;
+                        b_tap = w_base + sW * p.wstage_bytes;
+                    }
+                    if (elected && p.dbg != 1) {
+#pragma unroll 1
                         for (int m = 0; m < p.MT; ++m) {
                             const uint32_t d = d_set + (uint32_t)(m * p.n_tile);
-                            const uint32_t a_row = a_base + (uint32_t)(k * a.dil + m * kTcM) * 128;   // tap = row shift
-                            uint32_t acc = first ? 0u : 1u;
-                            if (p.dbg == 1) continue;
+                            const uint32_t a_row = a_tap + (uint32_t)m * (kTcM * 128);
+                            uint32_t acc = fresh ^ 1u;
                             if (BF) {
 #pragma unroll
-                                for (int kb = 0; kb < 2; ++kb) {      // 2 x 16 channels; small cross terms first
+                                for (int kb = 0; kb < 2; ++kb) {    // 2 x 16 channels; small cross terms first
                                     const uint32_t ah = desc_lo(a_row + kb * 32), al = desc_lo(a_row + a_lo_plane + kb * 32);
-                                    const uint32_t bh = desc_lo(b_base + kb * 32), bl = desc_lo(b_base + b_lo_plane + kb * 32);
+                                    const uint32_t bh = desc_lo(b_tap + kb * 32), bl = desc_lo(b_tap + b_lo_plane + kb * 32);
                                     if (p.dbg != 2) {
                                         umma<true>(d, al, hi_word, bh, hi_word, idesc, acc);
                                         umma<true>(d, ah, hi_word, bl, hi_word, idesc, 1u);
@@ -329,11 +356,11 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                                 }
                             } else {
 #pragma unroll
-                                for (int kb = 0; kb < 4; ++kb) {      // 4 x 8 channels
-                                    const uint32_t ah = desc_lo(a_row + kb * 32), bh = desc_lo(b_base + kb * 32);
+                                for (int kb = 0; kb < 4; ++kb) {    // 4 x 8 channels
+                                    const uint32_t ah = desc_lo(a_row + kb * 32), bh = desc_lo(b_tap + kb * 32);
                                     if (X3) {
                                         const uint32_t al = desc_lo(a_row + a_lo_plane + kb * 32);
-                                        const uint32_t bl = desc_lo(b_base + b_lo_plane + kb * 32);
+                                        const uint32_t bl = desc_lo(b_tap + b_lo_plane + kb * 32);
                                         umma<false>(d, al, hi_word, bh, hi_word, idesc, acc);
                                         umma<false>(d, ah, hi_word, bl, hi_word, idesc, 1u);
                                         acc = 1u;
@@ -343,25 +370,33 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                                 }
                             }
                         }
-                        first = 0;
-                        if (!p.w_resident && (k + 1 == a.KS || (k + 1) % p.tps == 0))
-                            umma_commit(w_empty + sW);  // frees the weight stage when these MMAs retire
                     }
-                    if (!p.w_resident) it += p.n_st;
-                    umma_commit(a_empty + sA);
+                    fresh = 0;
+                    a_tap += tap_step, b_tap += p.wtile_bytes;
+                    if (++in_stage == p.tps || k + 1 == a.KS) {     // stage consumed: release its ring slot
+                        in_stage = 0;
+                        if (!p.w_resident) {
+                            if (elected) umma_commit(w_empty + sW);
+                            if (++sW == p.nW) sW = 0, phW ^= 1;
+                        }
+                    }
                 }
-                umma_commit(acc_full + as);
+                if (elected) umma_commit(a_empty + sA);
+                if (++sA == p.nA) sA = 0, phA ^= 1;
             }
+            if (elected) umma_commit(acc_full + as);
+            as ^= 1;
+            if (as == 0) phE ^= 1;
+            first_group = false;
         }
     } else if (warp < 6) {
         // ====================== operand transform warps (128 threads) =================
         const int tid = threadIdx.x - 64;                       // 0..127
-        int gc = 0;
+        int sR = 0, phR = 0, sA = 0, phA = 1;
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
-            for (int c = 0; c < p.n_chunks; ++c, ++gc) {
-                const int sR = gc % p.nR, sA = gc % p.nA;
-                mbar_wait(raw_full + sR, (gc / p.nR) & 1);
-                mbar_wait(a_empty + sA, ((gc / p.nA) & 1) ^ 1);
+            for (int c = 0; c < p.n_chunks; ++c) {
+                mbar_wait(raw_full + sR, phR);
+                mbar_wait(a_empty + sA, phA);
                 const float4 *raw = reinterpret_cast<const float4 *>(raw0 + sR * p.raw_bytes);
                 uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
                 for (int r = tid; r < p.R; r += 128) {
@@ -397,6 +432,8 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(a_ready + sA);
                 mbar_arrive(raw_empty + sR);
+                if (++sR == p.nR) sR = 0, phR ^= 1;
+                if (++sA == p.nA) sA = 0, phA ^= 1;
             }
         }
     } else {
@@ -623,7 +660,10 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
                   p.n_tile);
         // weight stage = as many taps of one chunk as fit in ~48 KB, fetched by a single bulk copy
         const size_t avail = budget - p.off_w;
-        int tps = (int)std::min<size_t>(a.KS, std::max<size_t>(1, std::min<size_t>(48 * 1024, avail / 2) / p.wtile_bytes));
+        // (measured: one bulk copy per tap beats multi-tap stages -- a single large copy streams slowly)
+        int tps = 1;
+        if (const char *e = getenv("SVB_TC_TPS")) tps = std::max(1, std::min(a.KS, atoi(e)));
+        while (tps > 1 && (size_t)tps * p.wtile_bytes * 2 > avail) --tps;
         if ((size_t)a.KS * p.wtile_bytes <= avail && p.n_chunks == 1 && p.col_blocks == 1) tps = a.KS;   // whole layer fits
         p.tps = tps;
         p.n_st = (a.KS + tps - 1) / tps;
@@ -635,6 +675,9 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         smem = p.off_w + (size_t)nW * p.wstage_bytes;
         break;
     }
+    if (getenv("SVB_TC_VERBOSE"))
+        fprintf(stderr, "[tc] Cin %d CoutP %d KS %d dil %d Tq %d | n_tile %d MT %d R %d nR %d nA %d tps %d n_st %d nW %d resident %d smem %zu\n",
+                a.Cin, a.CoutP, a.KS, a.dil, a.Tq, p.n_tile, p.MT, p.R, p.nR, p.nA, p.tps, p.n_st, p.nW, p.w_resident, smem);
     int cols = 32;
     while (cols < 2 * p.MT * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
