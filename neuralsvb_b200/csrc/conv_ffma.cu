@@ -1,4 +1,4 @@
-// fp32 CUDA-core kernels of the HiFi-GAN-NSF generator on the C4T layout (common.cuh).
+// fp32 CUDA-core kernels of the HiFi-GAN-NSF generator on the G32T activation layout (common.cuh).
 //
 // conv1d_c4_ffma: implicit-GEMM 1-D convolution.  CTA tile = 256 time rows x (8 warps * CPT) output
 // columns; lanes run along time (consecutive 16-byte rows -> conflict-free LDS.128 and coalesced
@@ -36,20 +36,20 @@ __global__ void __launch_bounds__(256) conv1d_c4_ffma_kernel(ConvArgs a) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) acc[r][c] = 0.f;
 
-    const float4 *in4 = reinterpret_cast<const float4 *>(a.in) + (size_t)b * cin_q * a.in_Tp;
+    const float4 *in4 = reinterpret_cast<const float4 *>(a.in);
 
     for (int c0 = 0; c0 < a.Cin; c0 += kCK) {
         __syncthreads();
         // ---- stage the activation slab: 4 quads x rows, pre-activation fused
         for (int idx = tid; idx < 4 * rows; idx += 256) {
-            const int q = idx / rows, r = idx - q * rows;
+            const int q = idx & 3, r = idx >> 2;            // the 4 quads of a row are 64 contiguous bytes
             const int cq = (c0 >> 2) + q;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (cq < cin_q) {
-                v = __ldg(in4 + (size_t)cq * a.in_Tp + (kPad + t0 - halo + r));
+                v = __ldg(in4 + act_q4(b, a.Cin, a.in_Tp, cq, kPad + t0 - halo + r));
                 v = lrelu4(v, a.in_slope);
             }
-            xs[idx] = v;
+            xs[q * rows + r] = v;
         }
         // ---- stage the weight chunk [KS][kCK][CO_TILE]
         for (int idx = tid; idx < KS * kCK * (CO_TILE / 4); idx += 256) {
@@ -94,7 +94,6 @@ __global__ void __launch_bounds__(256) conv1d_c4_ffma_kernel(ConvArgs a) {
     if (!active) return;
 
     // ---- epilogue
-    const int out_q = a.Cout >> 2;
 #pragma unroll
     for (int c4 = 0; c4 < CPT / 4; ++c4) {
         const int cop = co0 + 4 * c4;                 // GEMM column of this quad
@@ -102,12 +101,11 @@ __global__ void __launch_bounds__(256) conv1d_c4_ffma_kernel(ConvArgs a) {
         int phi = 0, co = cop;
         if (a.ups_u > 0) { phi = cop / a.Cout; co = cop - phi * a.Cout; }
         const float4 bv = a.bias ? __ldg(reinterpret_cast<const float4 *>(a.bias + co)) : make_float4(0, 0, 0, 0);
-        const size_t base = ((size_t)b * out_q + (co >> 2)) * a.out_Tp + kPad;
 #pragma unroll
         for (int r = 0; r < kRowsPerThread; ++r) {
             const int q = t0 + lane + 32 * r;
             if (q >= a.Tq) continue;
-            const size_t row = base + (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q);
+            const size_t row = act_q4(b, a.Cout, a.out_Tp, co >> 2, kPad + (a.ups_u > 0 ? q * a.ups_u + phi : q));
             float4 v = make_float4(acc[r][4 * c4 + 0] + bv.x, acc[r][4 * c4 + 1] + bv.y,
                                    acc[r][4 * c4 + 2] + bv.z, acc[r][4 * c4 + 3] + bv.w);
             if (a.res) {
@@ -171,14 +169,14 @@ __global__ void nct_to_c4t_kernel(const float *__restrict__ nct, float4 *__restr
     const int cq = blockIdx.y, b = blockIdx.z;
     if (t >= T) return;
     const float *p = nct + ((size_t)b * C + cq * 4) * T + t;
-    c4t[((size_t)b * (C >> 2) + cq) * Tp + kPad + t] = make_float4(p[0], p[T], p[2 * (size_t)T], p[3 * (size_t)T]);
+    c4t[act_q4(b, C, Tp, cq, kPad + t)] = make_float4(p[0], p[T], p[2 * (size_t)T], p[3 * (size_t)T]);
 }
 
 __global__ void c4t_to_nct_kernel(const float4 *__restrict__ c4t, float *__restrict__ nct, int C, int T, int Tp) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int cq = blockIdx.y, b = blockIdx.z;
     if (t >= T) return;
-    const float4 v = c4t[((size_t)b * (C >> 2) + cq) * Tp + kPad + t];
+    const float4 v = c4t[act_q4(b, C, Tp, cq, kPad + t)];
     float *p = nct + ((size_t)b * C + cq * 4) * T + t;
     p[0] = v.x, p[T] = v.y, p[2 * (size_t)T] = v.z, p[3 * (size_t)T] = v.w;
 }
@@ -188,7 +186,7 @@ __global__ void btc_to_c4t_kernel(const float4 *__restrict__ btc, float4 *__rest
     const int cq = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = blockIdx.y, b = blockIdx.z;
     if (cq >= (C >> 2)) return;
-    c4t[((size_t)b * (C >> 2) + cq) * Tp + kPad + t] = btc[((size_t)b * T + t) * (C >> 2) + cq];
+    c4t[act_q4(b, C, Tp, cq, kPad + t)] = btc[((size_t)b * T + t) * (C >> 2) + cq];
 }
 
 int launch_nct_to_c4t(const float *nct, float *c4t, int B, int C, int T, int Tp, cudaStream_t st) {
@@ -231,7 +229,7 @@ __global__ void noise_conv_add_kernel(float4 *__restrict__ x, int C, int T, int 
         acc.z = fmaf(__ldg(w + 2 * K + j), hv, acc.z);
         acc.w = fmaf(__ldg(w + 3 * K + j), hv, acc.w);
     }
-    float4 *p = x + ((size_t)b * (C >> 2) + cq) * Tp + kPad + n;
+    float4 *p = x + act_q4(b, C, Tp, cq, kPad + n);
     float4 v = *p;
     v.x += acc.x, v.y += acc.y, v.z += acc.z, v.w += acc.w;
     *p = v;
@@ -257,7 +255,7 @@ __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const float4 *__res
     const int b = blockIdx.y, t0 = blockIdx.x * 256, tid = threadIdx.x;
     for (int idx = tid; idx < cq_n * rows; idx += 256) {
         const int cq = idx / rows, r = idx - cq * rows;
-        xs[idx] = lrelu4(__ldg(x + ((size_t)b * cq_n + cq) * Tp + kPad + t0 - halo + r), slope);
+        xs[idx] = lrelu4(__ldg(x + act_q4(b, C, Tp, cq, kPad + t0 - halo + r)), slope);
     }
     for (int idx = tid; idx < cq_n * K; idx += 256) ws[idx] = wq[idx];
     __syncthreads();

@@ -1,22 +1,21 @@
-// tcgen05 implicit-GEMM 1-D convolution on the C4T layout (sm_100a).
+// tcgen05 implicit-GEMM 1-D convolution on the G32T activation layout (sm_100a).
 //
-//   D[128 time rows x N columns] (fp32, TMEM) += A[128 x 8] (tf32, smem) * B[8 x N] (tf32, smem)
+//   D[128 time rows x N columns] (fp32, TMEM) += A[128 x 16] (bf16, smem) * B[16 x N] (bf16, smem)
 //
-// GEMM mapping: M = time (128 rows per CTA), N = output channels (<= 256 per CTA), K = taps x Cin.
-// * A operand = the activation slab.  C4T keeps, per channel quad, consecutive time steps as
-//   consecutive 16-byte rows, so a [rows x 4 ch] slab is one contiguous span: it is fetched with ONE
-//   cp.async.bulk (TMA, UBLKCP) per quad.  The transform warps turn the fp32 slab into the MMA
-//   operand: one 128-byte row per time step (K-major, SWIZZLE_128B -- the no-swizzle layout was
-//   measured at only ~40 B/clk of operand fetch).  A conv tap at dilation d is a ROW SHIFT of that
-//   operand = +128*k*d bytes on the descriptor start address, so one slab load (128 + halo rows)
-//   feeds all KS taps.
-// * B operand = weights, packed on the host per (column block, input-channel chunk, tap) in the
-//   same core-matrix order, streamed through a ring of bulk copies.
-// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-//   warps 2..5 = operand transform during the main loop (leaky-relu pre-activation of the ResBlock
-//   + round-to-nearest tf32, optional hi/lo split for 3xTF32, in place in shared memory) and
-//   epilogue afterwards (tcgen05.ld -> bias / residual / scale / accumulate -> 128-bit stores).
-// * HBM tensors stay exact fp32; tf32 rounding happens only on the operand copy in shared memory.
+// GEMM mapping: M = time (128 rows per MMA), N = output channels (<= 128 per CTA), K = taps x Cin.
+// * A operand = the activation slab.  G32T keeps, per 32-channel group, consecutive time steps as
+//   consecutive 128-byte rows, so the [rows x 32 ch] slab is one contiguous span fetched with ONE
+//   cp.async.bulk (TMA, UBLKCP) straight into the operand slot.  The transform warps rewrite it IN
+//   PLACE into the MMA operand: leaky-relu pre-activation, hi/lo split (or tf32 rounding) and the
+//   SWIZZLE_128B chunk permutation; one 128-byte K-major row per time step.  A conv tap at
+//   dilation d is a ROW SHIFT of that operand = +128*k*d bytes on the descriptor start address,
+//   so one slab (MT*128 + halo rows) feeds all KS taps of MT accumulator tiles.
+// * B operand = weights, packed and pre-swizzled on the host per (column block, input-channel
+//   chunk, tap), streamed through a ring of bulk copies (or kept resident for narrow layers).
+// * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + elected-lane
+//   MMA issuer, warps 2..5 = operand transform, warps 6..13 = epilogue (tcgen05.ld -> bias /
+//   residual / scale / accumulate -> 128-byte row stores) on the accumulator set the MMAs are not
+//   writing.  HBM tensors stay exact fp32; rounding happens only on the operand copy in smem.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -196,12 +195,12 @@ __device__ __forceinline__ void bf16_split2(float x0, float x1, uint32_t &hi, ui
 struct TcArgs {
     ConvArgs a;
     const unsigned char *w;     // packed, pre-swizzled weight tiles of this mode
-    int n_tile, n_chunks, MT, R, Rp, nW, nA, nR, tmem_cols;
+    int n_tile, n_chunks, MT, R, Rp, nW, nA, tmem_cols;
     int col_blocks, groups_per_b, total_groups;
     int tps, n_st, w_resident;  // taps per weight stage, stages per chunk, whole layer resident in smem
     uint32_t wstage_bytes;      // ring slot = tps weight tiles
     int dbg;                    // SVB_TC_DBG experiments: 1 = no MMAs, 2 = hi*hi only
-    uint32_t raw_bytes;         // fp32 slab as TMA delivers it: 8 quads x R rows x 16 B
+    uint32_t raw_bytes;         // fp32 slab as TMA delivers it: R rows x 128 B
     uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
     uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile (x2 with the 3xTF32 lo plane)
     uint32_t off_op, off_w;     // byte offsets of the operand slots / weight ring in dynamic smem
@@ -223,12 +222,11 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     const ConvArgs &a = p.a;
     // ---- shared memory carve-up (operand slots and weight ring are 1024-byte aligned: swizzle atoms)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    uint64_t *raw_full = bars, *raw_empty = bars + 2, *a_ready = bars + 4, *a_empty = bars + 6;
-    uint64_t *w_full = bars + 8, *w_empty = bars + 8 + kMaxW;
-    uint64_t *acc_full = bars + 8 + 2 * kMaxW, *acc_empty = acc_full + 2;
+    uint64_t *raw_full = bars, *a_ready = bars + 4, *a_empty = bars + 8;      // up to 4 operand slots
+    uint64_t *w_full = bars + 12, *w_empty = bars + 12 + kMaxW;
+    uint64_t *acc_full = bars + 12 + 2 * kMaxW, *acc_empty = acc_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
-    unsigned char *raw0 = smem + 256;                                // [nR][raw_bytes]
-    unsigned char *op0 = smem + p.off_op;                            // [nA][op_bytes]
+    unsigned char *op0 = smem + p.off_op;                            // [nA][op_bytes]: TMA target AND MMA operand
     unsigned char *wring = smem + p.off_w;                           // [nW][wtile_bytes]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -236,10 +234,8 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     const int acc_cols = p.MT * p.n_tile;                            // columns of one accumulator set
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(raw_full + i, 1), mbar_init(raw_empty + i, 128), mbar_init(a_ready + i, 128), mbar_init(a_empty + i, 1);
-            mbar_init(acc_full + i, 1), mbar_init(acc_empty + i, 256);
-        }
+        for (int i = 0; i < 4; ++i) mbar_init(raw_full + i, 1), mbar_init(a_ready + i, 128), mbar_init(a_empty + i, 1);
+        for (int i = 0; i < 2; ++i) mbar_init(acc_full + i, 1), mbar_init(acc_empty + i, 256);
         for (int i = 0; i < kMaxW; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, 1);
         fence_barrier_init();
     }
@@ -261,48 +257,44 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     // counters -- no runtime integer divisions in the loops.
     if (warp == 0) {
         // ================================ TMA producer ================================
-        // lane 0 owns the barriers; lanes 0..7 each issue one quad of the slab so the eight copies
-        // leave in parallel.
-        const int cin_q = a.Cin >> 2;
-        const uint32_t qbytes = (uint32_t)p.R * 16;
-        const size_t quad_stride = (size_t)a.in_Tp * 4;                       // floats between channel quads
-        const size_t chunk_w_bytes = (size_t)a.KS * p.wtile_bytes;
-        int sR = 0, phR = 1, sW = 0, phW = 1;                                 // "empty" barriers start free
-        int tg = blockIdx.x % p.groups_per_b, rb = blockIdx.x / p.groups_per_b;   // group -> (time group, b + B*nblk)
-        const int step_tg = gridDim.x % p.groups_per_b, step_rb = gridDim.x / p.groups_per_b;
-        bool first_group = true;
-        for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
-            const int b = rb % a.B, nblk = rb / a.B;
-            const int t0 = tg * (kTcM * p.MT);
-            const float *in_q = a.in + ((size_t)b * cin_q * a.in_Tp + (kPad + t0 - halo)) * 4 + (size_t)lane * quad_stride;
-            const unsigned char *w_c = p.w + (size_t)nblk * p.n_chunks * chunk_w_bytes;
-            for (int c = 0; c < p.n_chunks; ++c) {
-                if (lane == 0) {
-                    mbar_wait(raw_empty + sR, phR);
-                    mbar_expect_tx(raw_full + sR, p.raw_bytes);
-                }
-                __syncwarp();
-                if (lane < 8) bulk_g2s(raw0 + sR * p.raw_bytes + lane * qbytes, in_q, qbytes, raw_full + sR);
-                in_q += 8 * quad_stride;
-                if (++sR == p.nR) sR = 0, phR ^= 1;
-                if (lane == 0 && !(p.w_resident && !first_group)) {
-                    const unsigned char *w_k = w_c;
-                    for (int st = 0; st < p.n_st; ++st) {
-                        const int nt = min(p.tps, a.KS - st * p.tps);
-                        const uint32_t bytes = (uint32_t)nt * p.wtile_bytes;
-                        mbar_wait(w_empty + sW, phW);
-                        mbar_expect_tx(w_full + sW, bytes);
-                        bulk_g2s(wring + sW * p.wstage_bytes, w_k, bytes, w_full + sW);
-                        w_k += bytes;
-                        if (++sW == p.nW) sW = 0, phW ^= 1;
+        // One bulk copy per slab (R rows x 128 B, contiguous in G32T) and one per weight stage.
+        if (lane == 0) {
+            const int gin = c4t_groups(a.Cin);
+            const size_t group_stride = (size_t)a.in_Tp * 32;                     // floats between channel groups
+            const size_t chunk_w_bytes = (size_t)a.KS * p.wtile_bytes;
+            int sA = 0, phA = 1, sW = 0, phW = 1;                                 // "empty" barriers start free
+            int tg = blockIdx.x % p.groups_per_b, rb = blockIdx.x / p.groups_per_b;   // group -> (time group, b + B*nblk)
+            const int step_tg = gridDim.x % p.groups_per_b, step_rb = gridDim.x / p.groups_per_b;
+            bool first_group = true;
+            for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
+                const int b = rb % a.B, nblk = rb / a.B;
+                const int t0 = tg * (kTcM * p.MT);
+                const float *in_c = a.in + ((size_t)b * gin * a.in_Tp + (kPad + t0 - halo)) * 32;
+                const unsigned char *w_c = p.w + (size_t)nblk * p.n_chunks * chunk_w_bytes;
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    mbar_wait(a_empty + sA, phA);                                 // MMAs of the slot's previous slab retired
+                    mbar_expect_tx(raw_full + sA, p.raw_bytes);
+                    bulk_g2s(op0 + sA * p.op_bytes, in_c, p.raw_bytes, raw_full + sA);
+                    in_c += group_stride;
+                    if (++sA == p.nA) sA = 0, phA ^= 1;
+                    if (!(p.w_resident && !first_group)) {
+                        const unsigned char *w_k = w_c;
+                        for (int st = 0; st < p.n_st; ++st) {
+                            const int nt = min(p.tps, a.KS - st * p.tps);
+                            const uint32_t bytes = (uint32_t)nt * p.wtile_bytes;
+                            mbar_wait(w_empty + sW, phW);
+                            mbar_expect_tx(w_full + sW, bytes);
+                            bulk_g2s(wring + sW * p.wstage_bytes, w_k, bytes, w_full + sW);
+                            w_k += bytes;
+                            if (++sW == p.nW) sW = 0, phW ^= 1;
+                        }
                     }
+                    w_c += chunk_w_bytes;
                 }
-                w_c += chunk_w_bytes;
-                __syncwarp();
+                first_group = false;
+                tg += step_tg, rb += step_rb;
+                if (tg >= p.groups_per_b) tg -= p.groups_per_b, ++rb;
             }
-            first_group = false;
-            tg += step_tg, rb += step_rb;
-            if (tg >= p.groups_per_b) tg -= p.groups_per_b, ++rb;
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
@@ -391,48 +383,51 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         }
     } else if (warp < 6) {
         // ====================== operand transform warps (128 threads) =================
+        // In place, 8 lanes per 128-byte row (one 16-byte chunk = 4 channels each): conflict-free
+        // LDS.128 / STS.128.  Row r, logical chunk j is stored at chunk position j ^ (r & 7)
+        // (SWIZZLE_128B).  bf16 mode: lane pairs exchange halves so the even lane writes the
+        // 8-channel hi chunk (j = c/2) and the odd lane the lo chunk (4 + c/2).
         const int tid = threadIdx.x - 64;                       // 0..127
-        int sR = 0, phR = 0, sA = 0, phA = 1;
+        const int cl = tid & 7;                                 // chunk of the row this lane reads
+        int sA = 0, phA = 0;
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
             for (int c = 0; c < p.n_chunks; ++c) {
-                mbar_wait(raw_full + sR, phR);
-                mbar_wait(a_empty + sA, phA);
-                const float4 *raw = reinterpret_cast<const float4 *>(raw0 + sR * p.raw_bytes);
+                mbar_wait(raw_full + sA, phA);
                 uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
-                for (int r = tid; r < p.R; r += 128) {
-                    // row r: 8 quads (32 channels) -> one 128-byte operand row; chunk c16 lives at c16 ^ (r & 7)
-                    float4 v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = lrelu4(raw[q * p.R + r], a.in_slope);
+                for (int r0 = 0; r0 < p.R; r0 += 16) {          // 16 rows per pass over the 128 threads
+                    const int r = r0 + (tid >> 3);
+                    const bool ok = r < p.R;
                     uint4 *row = op + (size_t)r * 8;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) v = lrelu4(*reinterpret_cast<const float4 *>(row + cl), a.in_slope);
                     const int sw = r & 7;
                     if (BF) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {               // oct j = channels 8j .. 8j+7
-                            uint4 h, l;
-                            bf16_split2(v[2 * j].x, v[2 * j].y, h.x, l.x);
-                            bf16_split2(v[2 * j].z, v[2 * j].w, h.y, l.y);
-                            bf16_split2(v[2 * j + 1].x, v[2 * j + 1].y, h.z, l.z);
-                            bf16_split2(v[2 * j + 1].z, v[2 * j + 1].w, h.w, l.w);
-                            row[j ^ sw] = h;
-                            row[(4 + j) ^ sw] = l;
+                        uint32_t h0, l0, h1, l1;
+                        bf16_split2(v.x, v.y, h0, l0);
+                        bf16_split2(v.z, v.w, h1, l1);
+                        // even lane keeps hi and receives the neighbour's hi; odd lane keeps lo
+                        const bool odd = cl & 1;
+                        const uint32_t s0 = odd ? h0 : l0, s1 = odd ? h1 : l1;       // what the partner needs
+                        const uint32_t g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                        __syncwarp();                                               // all reads of the rows done
+                        if (ok) {
+                            if (!odd) row[(cl >> 1) ^ sw] = make_uint4(h0, h1, g0, g1);          // channels 8j..8j+7 hi
+                            else row[(4 + (cl >> 1)) ^ sw] = make_uint4(g0, g1, l0, l1);          // channels 8j..8j+7 lo
                         }
                     } else {
-                        uint4 *row_lo = row + (p.op_bytes / 32);    // lo plane (3xTF32): op_bytes / 2 bytes further
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 h = make_float4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
-                            row[q ^ sw] = make_uint4(__float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w));
+                        const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+                        __syncwarp();
+                        if (ok) {
+                            row[cl ^ sw] = make_uint4(__float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w));
                             if (X3)
-                                row_lo[q ^ sw] = make_uint4(__float_as_uint(to_tf32(v[q].x - h.x)), __float_as_uint(to_tf32(v[q].y - h.y)),
-                                                            __float_as_uint(to_tf32(v[q].z - h.z)), __float_as_uint(to_tf32(v[q].w - h.w)));
+                                (row + p.op_bytes / 32)[cl ^ sw] =
+                                    make_uint4(__float_as_uint(to_tf32(v.x - h.x)), __float_as_uint(to_tf32(v.y - h.y)),
+                                               __float_as_uint(to_tf32(v.z - h.z)), __float_as_uint(to_tf32(v.w - h.w)));
                         }
                     }
                 }
                 fence_proxy_async();                                // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(a_ready + sA);
-                mbar_arrive(raw_empty + sR);
-                if (++sR == p.nR) sR = 0, phR ^= 1;
                 if (++sA == p.nA) sA = 0, phA ^= 1;
             }
         }
@@ -445,7 +440,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         // overlaps the MMAs instead of serialising behind them.
         const int lane_base = 32 * (warp & 3);
         const int half = (warp - 6) >> 2;                           // 0 / 1: which blocks this warp takes
-        const int out_q = a.Cout >> 2;
+        const int gout = c4t_groups(a.Cout);
         const float4 *res4 = reinterpret_cast<const float4 *>(a.res);
         float4 *out4 = reinterpret_cast<float4 *>(a.out);
         const int jb = p.n_tile / 32, nblocks = p.MT * jb;
@@ -454,7 +449,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
             int nblk, b, t0;
             decode(g, nblk, b, t0);
             const int as = gi & 1;
-            // block -> first C4T row (float4 index) of this thread's 8 quads, or -1 if the row is padding
+            // block -> float4 index of this thread's 128-byte output row (8 quads), or -1 if the row is padding
             auto block_row0 = [&](int blk, int &co0) -> long long {
                 const int m = blk / jb, j = blk - m * jb;
                 const int q = t0 + m * kTcM + lane_base + lane;
@@ -463,8 +458,8 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 co0 = cop0;
                 if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
                 if (q >= a.Tq) return -1;
-                return (long long)(((size_t)b * out_q + (co0 >> 2)) * a.out_Tp + kPad +
-                                   (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q));
+                return (long long)((((size_t)b * gout + (co0 >> 5)) * a.out_Tp + kPad +
+                                    (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q)) * 8);
             };
             float4 rcur[8], rnxt[8];
             auto fetch_res = [&](int blk, float4 *dst) {
@@ -472,7 +467,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 const long long row0 = blk < nblocks ? block_row0(blk, co0) : -1;
 #pragma unroll
                 for (int gq = 0; gq < 8; ++gq)
-                    dst[gq] = (res4 && row0 >= 0) ? __ldg(res4 + row0 + (long long)gq * a.out_Tp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dst[gq] = (res4 && row0 >= 0) ? __ldg(res4 + row0 + gq) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             fetch_res(half, rcur);
             mbar_wait(acc_full + as, (gi >> 1) & 1);
@@ -487,7 +482,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 if (row0 >= 0) {
 #pragma unroll
                     for (int gq = 0; gq < 8; ++gq) {
-                        const size_t row = (size_t)row0 + (size_t)gq * a.out_Tp;
+                        const size_t row = (size_t)row0 + gq;
                         const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co0 + 4 * gq));
                         float4 o = make_float4(v[4 * gq] + bv.x + rcur[gq].x, v[4 * gq + 1] + bv.y + rcur[gq].y,
                                                v[4 * gq + 2] + bv.z + rcur[gq].z, v[4 * gq + 3] + bv.w + rcur[gq].w);
@@ -539,10 +534,10 @@ static float bf16_to_float(uint16_t h) {
     return r;
 }
 
-static int pick_n_tile(int CoutP) {
-    if (CoutP % 16 != 0) return 0;
+static int pick_n_tile(int CoutP) {      // columns per CTA: a multiple of 32 (one G32T channel group per epilogue block)
+    if (CoutP % 32 != 0) return 0;
     if (CoutP <= 128) return CoutP;
-    for (int n = 128; n >= 16; n -= 16)
+    for (int n = 128; n >= 32; n -= 32)
         if (CoutP % n == 0) return n;
     return 0;
 }
@@ -632,8 +627,6 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     p.col_blocks = a.CoutP / p.n_tile;
     const int planes = precision == SVB_PREC_TF32X3 ? 2 : 1;
     p.wtile_bytes = (uint32_t)p.n_tile * 128 * planes;
-    p.nA = std::min(2, p.n_chunks * 2), p.nR = 2;
-    p.nA = 2;
     p.dbg = 0;
     if (const char *e = getenv("SVB_TC_DBG")) p.dbg = atoi(e);
     int force_mt = 0;
@@ -649,12 +642,16 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         p.MT = MT;
         p.R = MT * kTcM + 2 * halo;
         p.Rp = round_up(p.R, 8);
-        p.raw_bytes = (uint32_t)8 * p.R * 16;
+        p.raw_bytes = (uint32_t)p.R * 128;
         p.op_bytes = (uint32_t)p.Rp * 128 * planes;
-        // wide (tensor-bound) layers need weight bytes in flight more than slab bytes: one raw slot
-        p.nR = p.n_tile >= 128 ? 1 : 2;
-        p.off_op = (uint32_t)round_up(256 + p.nR * (int)p.raw_bytes, 1024);
+        // operand slots double as TMA targets: 3 of them keep two slab copies in flight behind the MMAs
+        p.nA = 3;
+        p.off_op = 1024;
         p.off_w = p.off_op + (uint32_t)p.nA * p.op_bytes;
+        if (p.off_w + 2 * (size_t)p.wtile_bytes > budget) {
+            p.nA = 2;
+            p.off_w = p.off_op + (uint32_t)p.nA * p.op_bytes;
+        }
         if (p.off_w + 2 * (size_t)p.wtile_bytes > budget && MT != 1) continue;
         SVB_CHECK(p.off_w + (size_t)p.wtile_bytes <= budget, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d)",
                   p.n_tile);
@@ -676,8 +673,8 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         break;
     }
     if (getenv("SVB_TC_VERBOSE"))
-        fprintf(stderr, "[tc] Cin %d CoutP %d KS %d dil %d Tq %d | n_tile %d MT %d R %d nR %d nA %d tps %d n_st %d nW %d resident %d smem %zu\n",
-                a.Cin, a.CoutP, a.KS, a.dil, a.Tq, p.n_tile, p.MT, p.R, p.nR, p.nA, p.tps, p.n_st, p.nW, p.w_resident, smem);
+        fprintf(stderr, "[tc] Cin %d CoutP %d KS %d dil %d Tq %d | n_tile %d MT %d R %d nA %d tps %d n_st %d nW %d resident %d smem %zu\n",
+                a.Cin, a.CoutP, a.KS, a.dil, a.Tq, p.n_tile, p.MT, p.R, p.nA, p.tps, p.n_st, p.nW, p.w_resident, smem);
     int cols = 32;
     while (cols < 2 * p.MT * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
