@@ -199,15 +199,16 @@ struct TcArgs {
     int col_blocks, groups_per_b, total_groups;
     int tps, n_st, w_resident;  // taps per weight stage, stages per chunk, whole layer resident in smem
     uint32_t wstage_bytes;      // ring slot = tps weight tiles
-    int dbg;                    // SVB_TC_DBG experiments: 1 = no MMAs, 2 = hi*hi only
+    int dbg;                    // SVB_TC_DBG bit mask: 1 no MMAs, 2 hi*hi only, 4 no transform, 8 no epilogue ld/st
     uint32_t raw_bytes;         // fp32 slab as TMA delivers it: R rows x 128 B
     uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
     uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile (x2 with the 3xTF32 lo plane)
-    uint32_t off_op, off_w;     // byte offsets of the operand slots / weight ring in dynamic smem
+    uint32_t off_op, off_w, off_stage;   // byte offsets of operand slots / weight ring / epilogue tiles in dynamic smem
 };
 
 constexpr int kMaxW = 8;
-constexpr int kTcThreadsP = 448;   // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-13 epilogue
+constexpr int kTcThreadsP = 576;   // warp 0 TMA, warp 1 MMA, warps 2-9 transform, warps 10-17 epilogue
+constexpr int kStageBytes = 8 * 4096;   // epilogue transpose tiles: 32 rows x 128 B per epilogue warp
 
 // Persistent kernel: one CTA per SM walks "groups" (MT consecutive 128-row tiles of one clip for
 // one column block).  Every stage is decoupled by mbarriers, so the TMA producer runs ahead into
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     const int acc_cols = p.MT * p.n_tile;                            // columns of one accumulator set
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(raw_full + i, 1), mbar_init(a_ready + i, 128), mbar_init(a_empty + i, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(raw_full + i, 1), mbar_init(a_ready + i, 256), mbar_init(a_empty + i, 1);
         for (int i = 0; i < 2; ++i) mbar_init(acc_full + i, 1), mbar_init(acc_empty + i, 256);
         for (int i = 0; i < kMaxW; ++i) mbar_init(w_full + i, 1), mbar_init(w_empty + i, 1);
         fence_barrier_init();
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                         }
                         b_tap = w_base + sW * p.wstage_bytes;
                     }
-                    if (elected && p.dbg != 1) {
+                    if (elected && !(p.dbg & 1)) {
 #pragma unroll 1
                         for (int m = 0; m < p.MT; ++m) {
                             const uint32_t d = d_set + (uint32_t)(m * p.n_tile);
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                                 for (int kb = 0; kb < 2; ++kb) {    // 2 x 16 channels; small cross terms first
                                     const uint32_t ah = desc_lo(a_row + kb * 32), al = desc_lo(a_row + a_lo_plane + kb * 32);
                                     const uint32_t bh = desc_lo(b_tap + kb * 32), bl = desc_lo(b_tap + b_lo_plane + kb * 32);
-                                    if (p.dbg != 2) {
+                                    if (!(p.dbg & 2)) {
                                         umma<true>(d, al, hi_word, bh, hi_word, idesc, acc);
                                         umma<true>(d, ah, hi_word, bl, hi_word, idesc, 1u);
                                         acc = 1u;
@@ -381,35 +382,39 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
             if (as == 0) phE ^= 1;
             first_group = false;
         }
-    } else if (warp < 6) {
-        // ====================== operand transform warps (128 threads) =================
+    } else if (warp < 10) {
+        // ====================== operand transform warps (256 threads) =================
         // In place, 8 lanes per 128-byte row (one 16-byte chunk = 4 channels each): conflict-free
         // LDS.128 / STS.128.  Row r, logical chunk j is stored at chunk position j ^ (r & 7)
         // (SWIZZLE_128B).  bf16 mode: lane pairs exchange halves so the even lane writes the
         // 8-channel hi chunk (j = c/2) and the odd lane the lo chunk (4 + c/2).
-        const int tid = threadIdx.x - 64;                       // 0..127
+        const int tid = threadIdx.x - 64;                       // 0..255
         const int cl = tid & 7;                                 // chunk of the row this lane reads
+        const bool odd = cl & 1;
+        const float slope = a.in_slope;                         // 0 <= slope <= 1: lrelu(x) = max(x, slope * x)
         int sA = 0, phA = 0;
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
             for (int c = 0; c < p.n_chunks; ++c) {
                 mbar_wait(raw_full + sA, phA);
                 uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
-                for (int r0 = 0; r0 < p.R; r0 += 16) {          // 16 rows per pass over the 128 threads
+                for (int r0 = 0; r0 < ((p.dbg & 4) ? 0 : p.R); r0 += 32) {   // 32 rows per pass over the 256 threads
                     const int r = r0 + (tid >> 3);
                     const bool ok = r < p.R;
                     uint4 *row = op + (size_t)r * 8;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) v = lrelu4(*reinterpret_cast<const float4 *>(row + cl), a.in_slope);
+                    if (ok) v = *reinterpret_cast<const float4 *>(row + cl);
+                    v.x = fmaxf(v.x, v.x * slope), v.y = fmaxf(v.y, v.y * slope);
+                    v.z = fmaxf(v.z, v.z * slope), v.w = fmaxf(v.w, v.w * slope);
                     const int sw = r & 7;
                     if (BF) {
-                        uint32_t h0, l0, h1, l1;
-                        bf16_split2(v.x, v.y, h0, l0);
-                        bf16_split2(v.z, v.w, h1, l1);
+                        const __nv_bfloat162 hA = __floats2bfloat162_rn(v.x, v.y), hB = __floats2bfloat162_rn(v.z, v.w);
+                        const uint32_t h0 = *reinterpret_cast<const uint32_t *>(&hA), h1 = *reinterpret_cast<const uint32_t *>(&hB);
+                        const __nv_bfloat162 lA = __floats2bfloat162_rn(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u));
+                        const __nv_bfloat162 lB = __floats2bfloat162_rn(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u));
+                        const uint32_t l0 = *reinterpret_cast<const uint32_t *>(&lA), l1 = *reinterpret_cast<const uint32_t *>(&lB);
                         // even lane keeps hi and receives the neighbour's hi; odd lane keeps lo
-                        const bool odd = cl & 1;
                         const uint32_t s0 = odd ? h0 : l0, s1 = odd ? h1 : l1;       // what the partner needs
                         const uint32_t g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-                        __syncwarp();                                               // all reads of the rows done
                         if (ok) {
                             if (!odd) row[(cl >> 1) ^ sw] = make_uint4(h0, h1, g0, g1);          // channels 8j..8j+7 hi
                             else row[(4 + (cl >> 1)) ^ sw] = make_uint4(g0, g1, l0, l1);          // channels 8j..8j+7 lo
@@ -434,68 +439,95 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     } else {
         // ================================ epilogue warps (256 threads) ================
         // TMEM lane = time row, column = output channel; a warp may only touch lanes 32*(warp%4)..+31,
-        // so two warps share each lane quarter and alternate over the 32-column blocks.  The residual
-        // rows of the NEXT block are requested before the current block is drained from TMEM, and
-        // the first request is issued before the accumulator is even complete: residual latency
-        // overlaps the MMAs instead of serialising behind them.
+        // so two warps share each lane quarter and alternate over the 32-column blocks.  A block is
+        // 32 rows x 128 B, contiguous in G32T.  Global accesses use the "wide" mapping (lane l, step i
+        // -> row 4i + l/8, chunk l%8: 512 contiguous bytes per instruction); TMEM hands each thread
+        // one whole row, so a per-warp 4 KB swizzled smem tile transposes between the two views.
+        // The residual block for step n+1 is requested before block n is drained.
+        const int ew = warp - 10;
         const int lane_base = 32 * (warp & 3);
-        const int half = (warp - 6) >> 2;                           // 0 / 1: which blocks this warp takes
+        const int half = ew >> 2;                                   // 0 / 1: which blocks this warp takes
         const int gout = c4t_groups(a.Cout);
         const float4 *res4 = reinterpret_cast<const float4 *>(a.res);
         float4 *out4 = reinterpret_cast<float4 *>(a.out);
+        float4 *tile = reinterpret_cast<float4 *>(smem + p.off_stage + ew * 4096);   // [32 rows][8 chunks], chunk ^ (row & 7)
         const int jb = p.n_tile / 32, nblocks = p.MT * jb;
+        const int wr = lane >> 3, wc = lane & 7;                    // wide mapping: row offset / chunk
+        const bool no_mem = p.dbg & 8;
         int gi = 0;
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x, ++gi) {
             int nblk, b, t0;
             decode(g, nblk, b, t0);
             const int as = gi & 1;
-            // block -> float4 index of this thread's 128-byte output row (8 quads), or -1 if the row is padding
-            auto block_row0 = [&](int blk, int &co0) -> long long {
+            // block -> float4 index of row (q_base + 0) of its 32-row x 128-byte tile, rows are 8 float4 apart
+            // (u*8 apart for an upsampler); q_base = first GEMM row of this warp in the block
+            auto block_base = [&](int blk, int &co0, int &q_base) -> size_t {
                 const int m = blk / jb, j = blk - m * jb;
-                const int q = t0 + m * kTcM + lane_base + lane;
+                q_base = t0 + m * kTcM + lane_base;
                 const int cop0 = nblk * p.n_tile + j * 32;          // 32 columns never straddle an upsampler phase
                 int phi = 0;
                 co0 = cop0;
                 if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
-                if (q >= a.Tq) return -1;
-                return (long long)((((size_t)b * gout + (co0 >> 5)) * a.out_Tp + kPad +
-                                    (a.ups_u > 0 ? (size_t)q * a.ups_u + phi : (size_t)q)) * 8);
+                return (((size_t)b * gout + (co0 >> 5)) * a.out_Tp + kPad +
+                        (a.ups_u > 0 ? (size_t)q_base * a.ups_u + phi : (size_t)q_base)) * 8;
             };
-            float4 rcur[8], rnxt[8];
-            auto fetch_res = [&](int blk, float4 *dst) {
-                int co0;
-                const long long row0 = blk < nblocks ? block_row0(blk, co0) : -1;
+            const size_t rstep = (size_t)(a.ups_u > 0 ? a.ups_u : 1) * 8;      // float4 between consecutive GEMM rows
+            float4 rres[8];
+            auto fetch_res = [&](int blk) {
+                if (!res4 || no_mem || blk >= nblocks) return;
+                int co0, q_base;
+                const size_t base = block_base(blk, co0, q_base);
 #pragma unroll
-                for (int gq = 0; gq < 8; ++gq)
-                    dst[gq] = (res4 && row0 >= 0) ? __ldg(res4 + row0 + gq) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 4 * i + wr;
+                    rres[i] = (q_base + rr < a.Tq) ? __ldg(res4 + base + (size_t)rr * rstep + wc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             };
-            fetch_res(half, rcur);
+            fetch_res(half);
             mbar_wait(acc_full + as, (gi >> 1) & 1);
             tc_fence_after();
             for (int blk = half; blk < nblocks; blk += 2) {
-                fetch_res(blk + 2, rnxt);
                 const int m = blk / jb, j = blk - m * jb;
+                int co0, q_base;
+                const size_t base = block_base(blk, co0, q_base);
+                if (res4) {                                          // residual: wide registers -> tile
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) tile[(4 * i + wr) * 8 + (wc ^ ((4 * i + wr) & 7))] = rres[i];
+                    __syncwarp();
+                }
+                fetch_res(blk + 2);
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * acc_cols + m * p.n_tile + j * 32), v);
-                int co0;
-                const long long row0 = block_row0(blk, co0);
-                if (row0 >= 0) {
+                // own row: accumulator + bias (+ residual) -> tile
 #pragma unroll
-                    for (int gq = 0; gq < 8; ++gq) {
-                        const size_t row = (size_t)row0 + gq;
-                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co0 + 4 * gq));
-                        float4 o = make_float4(v[4 * gq] + bv.x + rcur[gq].x, v[4 * gq + 1] + bv.y + rcur[gq].y,
-                                               v[4 * gq + 2] + bv.z + rcur[gq].z, v[4 * gq + 3] + bv.w + rcur[gq].w);
-                        o.x *= a.out_scale, o.y *= a.out_scale, o.z *= a.out_scale, o.w *= a.out_scale;
+                for (int gq = 0; gq < 8; ++gq) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co0 + 4 * gq));
+                    float4 o = make_float4(v[4 * gq] + bv.x, v[4 * gq + 1] + bv.y, v[4 * gq + 2] + bv.z, v[4 * gq + 3] + bv.w);
+                    float4 *slot = tile + lane * 8 + (gq ^ (lane & 7));
+                    if (res4) {
+                        const float4 rv = *slot;
+                        o.x += rv.x, o.y += rv.y, o.z += rv.z, o.w += rv.w;
+                    }
+                    o.x *= a.out_scale, o.y *= a.out_scale, o.z *= a.out_scale, o.w *= a.out_scale;
+                    *slot = o;
+                }
+                __syncwarp();
+                // tile -> global, wide mapping (512 contiguous bytes per store instruction)
+                if (!no_mem) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + wr;
+                        if (q_base + rr >= a.Tq) continue;
+                        float4 o = tile[rr * 8 + (wc ^ (rr & 7))];
+                        float4 *dst = out4 + base + (size_t)rr * rstep + wc;
                         if (a.accumulate) {
-                            const float4 old = out4[row];
+                            const float4 old = *dst;
                             o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
                         }
-                        out4[row] = o;
+                        *dst = o;
                     }
                 }
-#pragma unroll
-                for (int gq = 0; gq < 8; ++gq) rcur[gq] = rnxt[gq];
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(acc_empty + as);                            // this accumulator set may be overwritten
@@ -634,7 +666,7 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     // ---- M tiles per group: each weight tile fetched from L2 feeds MT accumulators.  Two accumulator
     // sets live in TMEM (2 * MT * N <= 512 columns); slabs and the weight ring must fit shared memory.
     size_t smem = 0;
-    const size_t budget = 226 * 1024;
+    const size_t budget = 226 * 1024 - kStageBytes;
     for (int MT : {4, 2, 1}) {
         if (force_mt && MT != force_mt && MT != 1) continue;
         if (2 * MT * p.n_tile > 512) continue;
@@ -669,7 +701,8 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         int nW = (int)(avail / p.wstage_bytes);
         nW = std::max(1, std::min(std::min(nW, kMaxW), p.w_resident ? 1 : 1 << 30));
         p.nW = nW;
-        smem = p.off_w + (size_t)nW * p.wstage_bytes;
+        p.off_stage = p.off_w + (uint32_t)nW * p.wstage_bytes;
+        smem = (size_t)p.off_stage + kStageBytes;
         break;
     }
     if (getenv("SVB_TC_VERBOSE"))

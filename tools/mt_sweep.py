@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Tuning sweep for the tcgen05 conv kernel: cluster size of the weight multicast (SVB_TC_CL) x resident-CTA target
-(SVB_TC_CTAS) per generator layer shape at BASELINE config 2.  Prints one row per layer (us)."""
+"""Tuning / ablation sweep for the tcgen05 conv kernel at BASELINE config 2.
+    python tools/mt_sweep.py <precision> <ENV_VAR> <v1,v2,...> [FIXED=VAL ...]
+Prints one row per generator layer shape (us per launch) and one column per value."""
 import os
 import sys
 
@@ -12,9 +13,11 @@ from tools.layer_bench import B, SHAPES  # noqa: E402
 
 
 def main():
-    prec = sys.argv[1] if len(sys.argv) > 1 else 'bf16x3'
-    combos = [(cl, c) for cl in (1, 2, 4, 8) for c in (5, 2)]
-    print('layer'.ljust(24) + ''.join(f'CL{cl}/c{c}'.rjust(9) for cl, c in combos))
+    prec, var, vals = sys.argv[1], sys.argv[2], sys.argv[3].split(',')
+    for kv in sys.argv[4:]:
+        k, v = kv.split('=')
+        os.environ[k] = v
+    print('layer'.ljust(24) + ''.join(f'{var[-3:]}={v}'.rjust(9) for v in vals))
     for name, Cin, Cout, T, K, dil, u, with_res in SHAPES:
         g = torch.Generator().manual_seed(1)
         x = torch.randn(B, Cin, T, generator=g).cuda()
@@ -22,8 +25,8 @@ def main():
         b = torch.zeros(Cout).cuda()
         res = torch.randn(B, Cout, T * u if u else T, generator=g).cuda() if with_res else None
         row = name.ljust(24)
-        for mt, c in combos:
-            os.environ['SVB_TC_CL'], os.environ['SVB_TC_CTAS'] = str(mt), str(c)
+        for v in vals:
+            os.environ[var] = v
             _, ms = run_layer(x, w, b, res, K, max(dil, 1), u, 0.1, 1.0, prec, iters=10)
             row += f'{ms * 1e3:9.1f}'
         print(row, flush=True)
