@@ -210,24 +210,26 @@ int launch_btc_to_c4t(const float *btc, float *c4t, int B, int C, int T, int Tp,
 }
 
 // ------------------------------------------------------------------------------ NSF injection
+// one thread per (row n, channel quad): the 8 quads of a 32-channel group are 8 consecutive lanes, so
+// a warp touches 4 whole 128-byte rows; har[] is a broadcast within a row; nw is packed [K][C].
 __global__ void noise_conv_add_kernel(float4 *__restrict__ x, int C, int T, int Tp, const float *__restrict__ har,
                                       int Thar, const float *__restrict__ nw, const float *__restrict__ nb, int K,
                                       int stride, int pad) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int cq = blockIdx.y, b = blockIdx.z;
-    if (n >= T) return;
+    const int cq_n = c4t_groups(C) * 8;                       // quads per row incl. zero padding channels
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (idx >= (long long)T * cq_n) return;
+    const int n = (int)(idx / cq_n), cq = (int)(idx - (long long)n * cq_n);
+    if (cq * 4 >= C) return;
     const float *h = har + (size_t)b * Thar;
-    const float *w = nw + (size_t)cq * 4 * K;
-    float4 acc = make_float4(nb[cq * 4], nb[cq * 4 + 1], nb[cq * 4 + 2], nb[cq * 4 + 3]);
+    float4 acc = __ldg(reinterpret_cast<const float4 *>(nb) + cq);
     const int base = n * stride - pad;
     for (int j = 0; j < K; ++j) {
         const int i = base + j;
         if (i < 0 || i >= Thar) continue;
         const float hv = __ldg(h + i);
-        acc.x = fmaf(__ldg(w + j), hv, acc.x);
-        acc.y = fmaf(__ldg(w + K + j), hv, acc.y);
-        acc.z = fmaf(__ldg(w + 2 * K + j), hv, acc.z);
-        acc.w = fmaf(__ldg(w + 3 * K + j), hv, acc.w);
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(nw + (size_t)j * C) + cq);
+        acc.x = fmaf(w.x, hv, acc.x), acc.y = fmaf(w.y, hv, acc.y), acc.z = fmaf(w.z, hv, acc.z), acc.w = fmaf(w.w, hv, acc.w);
     }
     float4 *p = x + act_q4(b, C, Tp, cq, kPad + n);
     float4 v = *p;
@@ -237,9 +239,9 @@ __global__ void noise_conv_add_kernel(float4 *__restrict__ x, int C, int T, int 
 
 int launch_noise_conv_add(float *x, int B, int C, int T, int Tp, const float *har, int Thar, const float *nw,
                           const float *nb, int K, int stride, int pad, cudaStream_t st) {
-    dim3 grid((T + 127) / 128, C / 4, B);
-    noise_conv_add_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<float4 *>(x), C, T, Tp, har, Thar, nw, nb, K, stride,
-                                                pad);
+    const long long total = (long long)T * c4t_groups(C) * 8;
+    dim3 grid((unsigned)((total + 255) / 256), B);
+    noise_conv_add_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<float4 *>(x), C, T, Tp, har, Thar, nw, nb, K, stride, pad);
     SVB_CUDA(cudaGetLastError());
     return SVB_OK;
 }
@@ -254,8 +256,8 @@ __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const float4 *__res
     float4 *ws = sm4 + cq_n * rows; // [cq_n][K]
     const int b = blockIdx.y, t0 = blockIdx.x * 256, tid = threadIdx.x;
     for (int idx = tid; idx < cq_n * rows; idx += 256) {
-        const int cq = idx / rows, r = idx - cq * rows;
-        xs[idx] = lrelu4(__ldg(x + act_q4(b, C, Tp, cq, kPad + t0 - halo + r)), slope);
+        const int r = idx / cq_n, cq = idx - r * cq_n;      // quads of a row are contiguous in G32T
+        xs[cq * rows + r] = lrelu4(__ldg(x + act_q4(b, C, Tp, cq, kPad + t0 - halo + r)), slope);
     }
     for (int idx = tid; idx < cq_n * K; idx += 256) ws[idx] = wq[idx];
     __syncthreads();

@@ -363,7 +363,10 @@ extern "C" int svb_gen_finalize(svb_gen_t *g) {
             const HostTensor *w, *b;
             SVB_TRY(get_w(g, "noise_convs." + std::to_string(i) + ".weight", {s.C, 1, s.noise.K}, &w));
             SVB_TRY(get_w(g, "noise_convs." + std::to_string(i) + ".bias", {s.C}, &b));
-            SVB_TRY(upload(g, w->data, &s.noise.w));
+            std::vector<float> wt((size_t)s.noise.K * s.C);                       // [C][1][K] -> [K][C]
+            for (int ch = 0; ch < s.C; ++ch)
+                for (int j = 0; j < s.noise.K; ++j) wt[(size_t)j * s.C + ch] = w->data[(size_t)ch * s.noise.K + j];
+            SVB_TRY(upload(g, wt, &s.noise.w));
             SVB_TRY(upload(g, b->data, &s.noise.b));
         }
         s.c1.resize(c.n_resblock_kernels), s.c2.resize(c.n_resblock_kernels);
