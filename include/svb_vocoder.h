@@ -123,9 +123,15 @@ int64_t svb_gen_hop(const svb_gen_t *g);
 /* number of kernels launched by the last forward / their algorithmic FLOPs (for bench.py) */
 int64_t svb_gen_last_launches(const svb_gen_t *g);
 double svb_gen_last_flops(const svb_gen_t *g);
-/* CUDA-event time (ms) of the last forward on its stream when timing was enabled, else -1 */
+/* on = 1: CUDA events around the whole forward (svb_gen_last_ms, else -1).
+ * on = 2: additionally CUDA events around EVERY launch of the forward, on the launching stream;
+ *         svb_gen_profile_count / _get return, per launch of the last forward: the kernel family,
+ *         its event time, its algorithmic HBM bytes (layer-streaming model: each conv reads its
+ *         input once, writes its output once, reads the residual / running sum once) and FLOPs. */
 int svb_gen_enable_timing(svb_gen_t *g, int32_t on);
 float svb_gen_last_ms(svb_gen_t *g);
+int32_t svb_gen_profile_count(svb_gen_t *g);
+int svb_gen_profile_get(svb_gen_t *g, int32_t i, char *name, int32_t name_cap, float *ms, double *bytes, double *flops);
 
 /* One convolution layer of the generator on PyTorch-layout device tensors, through the CUDA-core
  * (precision 0) or tcgen05 (1, 2) kernel -- for kernel-level parity tests and per-layer timing.

@@ -105,6 +105,9 @@ _PROTOS = {
     'svb_gen_last_flops': (ctypes.c_double, [_P]),
     'svb_gen_enable_timing': (ctypes.c_int, [_P, _I32]),
     'svb_gen_last_ms': (ctypes.c_float, [_P]),
+    'svb_gen_profile_count': (_I32, [_P]),
+    'svb_gen_profile_get': (ctypes.c_int, [_P, _I32, ctypes.c_char_p, _I32, ctypes.POINTER(ctypes.c_float),
+                                            ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'svb_conv1d_run': (ctypes.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, ctypes.c_float,
                                       ctypes.c_float, _I32, _I32, _P, ctypes.POINTER(ctypes.c_float), _P]),
     'svb_stft_num_frames': (_I64, [ctypes.POINTER(StftConfig), _I64]),

@@ -79,6 +79,17 @@ struct svb_gen {
     double last_flops = 0;
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // per-launch profile of the last forward (svb_gen_enable_timing(g, 2)): CUDA events around every launch
+    struct LaunchRec {
+        const char *name;
+        cudaEvent_t e0, e1;
+        double bytes, flops;
+    };
+    bool profile = false;
+    std::vector<LaunchRec> recs;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
 };
 
 namespace {
@@ -170,10 +181,41 @@ Buffers plan_workspace(const svb_gen *g, int B, int T, size_t *total) {
     return b;
 }
 
+cudaEvent_t prof_event(svb_gen *g) {
+    if (g->ev_used == g->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        g->ev_pool.push_back(e);
+    }
+    return g->ev_pool[g->ev_used++];
+}
+// wraps one launch with events when profiling; `bytes` = algorithmic HBM bytes of the launch
+struct ProfScope {
+    svb_gen *g;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(svb_gen *g_, cudaStream_t st_, const char *name, double bytes, double flops) : g(g_), st(st_) {
+        if (!g->profile) return;
+        cudaEvent_t e0 = prof_event(g);
+        e1 = prof_event(g);
+        cudaEventRecord(e0, st);
+        g->recs.push_back({name, e0, e1, bytes, flops});
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
+};
+
 int run_conv(svb_gen *g, const ConvLayer &L, const float *in, int in_Tp, float *out, int out_Tp, const float *res,
              int B, int Tq, float in_slope, float scale, int accumulate, cudaStream_t st) {
     g->last_launches += 1;
     g->last_flops += 2.0 * L.macs_per_row * (double)B * Tq;
+    const bool tc = g->cfg.precision != SVB_PREC_FP32 && L.tc.ok && L.Cin % 32 == 0;
+    const double rows_out = (double)B * Tq * (L.ups_u > 0 ? L.ups_u : 1);
+    // layer-streaming bytes: input once, output once, residual / accumulated sum once more each
+    const double bytes = 4.0 * ((double)B * Tq * L.Cin + rows_out * L.Cout * (1 + (res ? 1 : 0) + (accumulate ? 1 : 0)));
+    ProfScope ps(g, st, tc ? (L.ups_u ? "conv1d_c4_tc (upsampler)" : "conv1d_c4_tc (resblock)") : "conv1d_c4_ffma", bytes,
+                 2.0 * L.macs_per_row * (double)B * Tq);
     ConvArgs a;
     a.in = in, a.w = L.w, a.bias = L.b, a.res = res, a.out = out;
     a.B = B, a.Cin = L.Cin, a.in_Tp = in_Tp, a.Cout = L.Cout, a.out_Tp = out_Tp, a.CoutP = L.CoutP, a.Tq = Tq;
@@ -204,13 +246,17 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
     }
     g->last_launches = 0, g->last_flops = 0, g->last_B = B;
     g->taps.clear();
+    g->recs.clear(), g->ev_used = 0;
     if (g->timing) SVB_CUDA(cudaEventRecord(g->ev0, st));
 
     auto F = [&](size_t off) { return reinterpret_cast<float *>(g->ws + off); };
     const int n_mel = g->cfg.n_mel, C0 = g->cfg.upsample_initial_channel;
     const int Tp0 = c4t_rows(T);
-    if (mel_frame_major) SVB_TRY(launch_btc_to_c4t(mel, F(bf.mel), B, n_mel, T, Tp0, st));
-    else SVB_TRY(launch_nct_to_c4t(mel, F(bf.mel), B, n_mel, T, Tp0, st));
+    {
+        ProfScope ps(g, st, "mel layout", 8.0 * B * n_mel * T, 0);
+        if (mel_frame_major) SVB_TRY(launch_btc_to_c4t(mel, F(bf.mel), B, n_mel, T, Tp0, st));
+        else SVB_TRY(launch_nct_to_c4t(mel, F(bf.mel), B, n_mel, T, Tp0, st));
+    }
     g->last_launches += 1;
 
     const int Tw = T * g->hop;
@@ -218,6 +264,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
     if (f0) {
         har = F(bf.har);
         int l = 0;
+        ProfScope ps(g, st, "nsf source (4 kernels)", 4.0 * B * (T + (double)Tw * (noise ? 10 : 1)), 60.0 * B * Tw * 9);
         SVB_TRY(launch_nsf_source(f0, rand_ini, noise, seed, B, T, g->hop, (float)g->cfg.audio_sample_rate, g->lin_w,
                                   g->lin_b, g->ws + bf.nsf, har, st, &l));
         g->last_launches += l;
@@ -237,6 +284,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         // x = ups[i](leaky_relu(x, 0.1))            hifigan.py:153-154
         SVB_TRY(run_conv(g, s.up, x_in, Tin_p, X, Tip, nullptr, B, Tin, 0.1f, 1.f, 0, st));
         if (f0) {                                   // x = x + noise_convs[i](har_source)   :155-157
+            ProfScope ps(g, st, "noise_conv_add", 4.0 * B * (2.0 * Ti * s.C + Tw), 2.0 * B * (double)Ti * s.C * s.noise.K);
             SVB_TRY(launch_noise_conv_add(X, B, s.C, Ti, Tip, har, Tw, s.noise.w, s.noise.b, s.noise.K, s.noise.stride,
                                           s.noise.pad, st));
             g->last_launches += 1;
@@ -263,7 +311,10 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         x_in = S, Tin = Ti, Tin_p = Tip;
     }
     // x = tanh(conv_post(leaky_relu(x)))   default slope 0.01   :165-167
-    SVB_TRY(launch_conv_post_tanh(x_in, B, g->post_C, Tin, Tin_p, g->post_wq, g->post_bias, g->post_K, 0.01f, wav, st));
+    {
+        ProfScope ps(g, st, "conv_post_tanh", 4.0 * B * Tin * (g->post_C + 1.0), 2.0 * B * (double)Tin * g->post_C * g->post_K);
+        SVB_TRY(launch_conv_post_tanh(x_in, B, g->post_C, Tin, Tin_p, g->post_wq, g->post_bias, g->post_K, 0.01f, wav, st));
+    }
     g->last_launches += 1;
     g->last_flops += 2.0 * B * (double)Tin * g->post_C * g->post_K;
     if (g->timing) SVB_CUDA(cudaEventRecord(g->ev1, st));
@@ -319,6 +370,7 @@ extern "C" void svb_gen_destroy(svb_gen_t *g) {
     if (g->pin_out) cudaFreeHost(g->pin_out);
     if (g->dev_in) cudaFree(g->dev_in);
     if (g->dev_out) cudaFree(g->dev_out);
+    for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     delete g;
@@ -476,6 +528,19 @@ extern "C" double svb_gen_last_flops(const svb_gen_t *g) { return g ? g->last_fl
 extern "C" int svb_gen_enable_timing(svb_gen_t *g, int32_t on) {
     SVB_CHECK(g, SVB_ERR_INVALID, "enable_timing: null handle");
     g->timing = on != 0;
+    g->profile = on == 2;
+    return SVB_OK;
+}
+extern "C" int32_t svb_gen_profile_count(svb_gen_t *g) { return g ? (int32_t)g->recs.size() : 0; }
+extern "C" int svb_gen_profile_get(svb_gen_t *g, int32_t i, char *name, int32_t name_cap, float *ms, double *bytes,
+                                   double *flops) {
+    SVB_CHECK(g && i >= 0 && i < (int32_t)g->recs.size() && name && ms && bytes && flops && name_cap > 0, SVB_ERR_INVALID,
+              "profile_get: bad argument");
+    const auto &r = g->recs[i];
+    SVB_CUDA(cudaEventSynchronize(r.e1));
+    SVB_CUDA(cudaEventElapsedTime(ms, r.e0, r.e1));
+    snprintf(name, name_cap, "%s", r.name);
+    *bytes = r.bytes, *flops = r.flops;
     return SVB_OK;
 }
 extern "C" float svb_gen_last_ms(svb_gen_t *g) {
