@@ -147,6 +147,27 @@ int svb_conv1d_run(const float *x_nct_dev, const float *w_host, const float *bia
                    int32_t transposed_stride, float in_slope, float out_scale, int32_t precision, int32_t iters,
                    float *y_nct_dev, float *avg_ms, void *stream);
 
+/* ---- discriminator-side operators of the vocoder losses (forward; fp32 CUDA cores) ------------ */
+
+/* y = leaky_relu(conv(x) + bias, out_slope) on PyTorch-layout tensors [B, C, T, W] with W independent inner
+ * columns: W = 1 is F.conv1d(stride, dilation, padding, groups) (DiscriminatorS, hifigan.py:262-271);
+ * W = period is the (K,1)-kernel / (stride,1)-stride Conv2d of DiscriminatorP (hifigan.py:193-200).
+ * w_dev [Cout, Cin/groups, K], bias_dev [Cout] or NULL; Tout = (Tin + 2*pad - dil*(K-1) - 1)/stride + 1. */
+int svb_conv_nct_forward(const float *x_dev, const float *w_dev, const float *bias_dev, float *y_dev, int32_t B,
+                         int32_t Cin, int32_t Cout, int32_t Tin, int32_t W, int32_t K, int32_t stride, int32_t dil,
+                         int32_t pad, int32_t groups, float out_slope, void *stream);
+/* AvgPool1d(4, 2, padding=1) over the last dim of [rows, Tin] (MultiScaleDiscriminator.meanpools, hifigan.py:304-307) */
+int svb_avgpool1d_4_2_1(const float *x_dev, float *y_dev, int64_t rows, int32_t Tin, void *stream);
+/* F.pad(x, (0, Tpad - T), 'reflect') over the last dim of [rows, T] (DiscriminatorP.forward, hifigan.py:209-212) */
+int svb_pad_reflect_right(const float *x_dev, float *y_dev, int64_t rows, int32_t T, int32_t Tpad, void *stream);
+/* out6_dev (double[6]) = { sum (a-b)^2, sum a^2, sum |ln a - ln b| (if want_log), sum |a-b|, sum (1-a)^2, sum b^2 }
+ * -- the reductions behind feature_loss / discriminator_loss / generator_loss (hifigan.py:328-365) and the
+ * spectral-convergence / log-magnitude STFT losses (losses/stft_loss.py:34-73).  b_dev may be NULL. */
+int svb_pair_stats(const float *a_dev, const float *b_dev, int64_t n, int32_t want_log, double *out6_dev, void *stream);
+/* sigma = u . (W v) of torch.nn.utils.spectral_norm in eval mode (no power iteration), W [rows, inner] */
+int svb_spectral_sigma_host(const float *w_host, const float *u_host, const float *v_host, int64_t rows, int64_t inner,
+                            int device, float *sigma);
+
 /* ---- STFT / mel front end ------------------------------------------------------------------ */
 
 typedef enum svb_pad_mode {

@@ -15,7 +15,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libsvb_vocoder.so')
 HEADER = os.path.join(_ROOT, 'include', 'svb_vocoder.h')
-SOURCES = ['api.cu', 'conv_ffma.cu', 'conv_tc.cu', 'nsf_source.cu', 'frontend.cu', 'generator.cu', 'layer_api.cu',
+SOURCES = ['api.cu', 'conv_ffma.cu', 'conv_tc.cu', 'nsf_source.cu', 'frontend.cu', 'generator.cu', 'layer_api.cu', 'disc_ops.cu',
            'train_ops.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
@@ -110,6 +110,12 @@ _PROTOS = {
                                             ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     'svb_conv1d_run': (ctypes.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, ctypes.c_float,
                                       ctypes.c_float, _I32, _I32, _P, ctypes.POINTER(ctypes.c_float), _P]),
+    'svb_conv_nct_forward': (ctypes.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                            ctypes.c_float, _P]),
+    'svb_avgpool1d_4_2_1': (ctypes.c_int, [_P, _P, _I64, _I32, _P]),
+    'svb_pad_reflect_right': (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P]),
+    'svb_pair_stats': (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    'svb_spectral_sigma_host': (ctypes.c_int, [_P, _P, _P, _I64, _I64, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     'svb_stft_num_frames': (_I64, [ctypes.POINTER(StftConfig), _I64]),
     'svb_stft_forward': (ctypes.c_int, [ctypes.POINTER(StftConfig), _P, _I32, _I64, _P, _P, _P]),
     'svb_wav2spec_host': (_I64, [ctypes.POINTER(StftConfig), _P, _I64, _P, _P, _P, ctypes.c_int, _P]),

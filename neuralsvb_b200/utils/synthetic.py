@@ -183,3 +183,54 @@ def make_wave_batch(batch, samples, sr=22050, seed=1234):
         sig += 0.02 * rs.standard_normal(samples)
         out[b] = np.clip(sig, -1.0, 1.0)
     return torch.from_numpy(out)
+
+
+# ---------------------------------------------------------------------------------- discriminators
+MPD_PERIODS = (2, 3, 5, 7, 11)
+_MPD_CH = [(1, 32), (32, 128), (128, 512), (512, 1024), (1024, 1024)]
+MSD_LAYERS = [(1, 128, 15, 1, 1, 7), (128, 128, 41, 2, 4, 20), (128, 256, 41, 2, 16, 20), (256, 512, 41, 4, 16, 20),
+              (512, 1024, 41, 4, 16, 20), (1024, 1024, 41, 1, 16, 20), (1024, 1024, 5, 1, 1, 2)]
+
+
+def make_mpd_state_dict(seed=1234):
+    """MultiPeriodDiscriminator state_dict (use_cond=False): 5 x DiscriminatorP, weight-normed
+    Conv2d [Cout, Cin, 5, 1] (+ conv_post [1, 1024, 3, 1]) -- modules/hifigan/hifigan.py:181-235."""
+    rs = np.random.RandomState(seed + 101)
+    sd = OrderedDict()
+    for d in range(len(MPD_PERIODS)):
+        layers = [(f'convs.{i}', cin, cout, 5) for i, (cin, cout) in enumerate(_MPD_CH)] + [('conv_post', 1024, 1, 3)]
+        for name, cin, cout, k in layers:
+            sd[f'discriminators.{d}.{name}.bias'] = _uniform(rs, (cout,), 0.05)
+            g, v = _wn_pair(rs, (cout, cin, k, 1), 1.3 / np.sqrt(cin * k), (1, 2, 3))
+            sd[f'discriminators.{d}.{name}.weight_g'], sd[f'discriminators.{d}.{name}.weight_v'] = g, v
+    return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v))) for k, v in sd.items())
+
+
+def make_msd_state_dict(seed=1234):
+    """MultiScaleDiscriminator state_dict (use_cond=False): discriminator 0 is spectral-normed
+    (weight_orig / weight_u / weight_v), 1 and 2 weight-normed -- modules/hifigan/hifigan.py:253-302."""
+    rs = np.random.RandomState(seed + 202)
+    sd = OrderedDict()
+    for d in range(3):
+        layers = [(f'convs.{i}', cin, cout, k, g) for i, (cin, cout, k, _, g, _) in enumerate(MSD_LAYERS)] + \
+                 [('conv_post', 1024, 1, 3, 1)]
+        for name, cin, cout, k, groups in layers:
+            cg = cin // groups
+            sd[f'discriminators.{d}.{name}.bias'] = _uniform(rs, (cout,), 0.05)
+            if d == 0:
+                w = _normal(rs, (cout, cg, k), 1.3 / np.sqrt(cg * k))
+                # u, v as one power iteration from a random start leaves them (what spectral_norm stores),
+                # so sigma = u . (W v) is a sensible estimate of the top singular value
+                wm = w.reshape(cout, -1).astype(np.float64)
+                u = rs.standard_normal(cout)
+                v = wm.T @ (u / np.linalg.norm(u))
+                v /= np.linalg.norm(v)
+                u = wm @ v
+                u /= np.linalg.norm(u)
+                sd[f'discriminators.{d}.{name}.weight_orig'] = w
+                sd[f'discriminators.{d}.{name}.weight_u'] = u.astype(np.float32)
+                sd[f'discriminators.{d}.{name}.weight_v'] = v.astype(np.float32)
+            else:
+                g, v = _wn_pair(rs, (cout, cg, k), 1.3 / np.sqrt(cg * k), (1, 2))
+                sd[f'discriminators.{d}.{name}.weight_g'], sd[f'discriminators.{d}.{name}.weight_v'] = g, v
+    return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v))) for k, v in sd.items())

@@ -109,13 +109,41 @@ def gen_losses():
     print('losses.npz', out['mr_stft/sc_mag'])
 
 
+def gen_discriminators():
+    """MPD / MSD (eval mode: spectral norm without power iteration) + GAN losses from the reference modules."""
+    R.install()
+    from utils.hparams import hparams as ref_hp
+    ref_hp['hop_size'] = 256                                   # MultiScaleDiscriminator reads it at construction (:292-301)
+    from modules.hifigan.hifigan import (MultiPeriodDiscriminator, MultiScaleDiscriminator, discriminator_loss, feature_loss,
+                                         generator_loss)
+    out = {}
+    y = S.make_wave_batch(2, 8192, seed=SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=SEED + 5)[:, None]).clamp(-1, 1)
+    for name, cls, sd in (('mpd', MultiPeriodDiscriminator, S.make_mpd_state_dict(SEED)),
+                          ('msd', MultiScaleDiscriminator, S.make_msd_state_dict(SEED))):
+        m = cls()
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        with torch.no_grad():
+            rs, gs, fr, fg = m(y, y_hat)
+            out[f'{name}/losses'] = np.array([float(feature_loss(fr, fg)), *[float(v) for v in discriminator_loss(rs, gs)],
+                                              float(generator_loss(gs))], np.float64)
+        for i, (r, g) in enumerate(zip(rs, gs)):
+            out[f'{name}/logit_r{i}'], out[f'{name}/logit_g{i}'] = r.numpy(), g.numpy()
+            for j, f in enumerate(fr[i]):
+                out[f'{name}/fmap_r{i}_{j}_shape'] = np.array(f.shape, np.int64)
+                out[f'{name}/fmap_r{i}_{j}_sub'] = f.numpy().reshape(-1)[::211].astype(np.float32)
+        print(name, out[f'{name}/losses'])
+    np.savez_compressed(os.path.join(OUT, 'discriminators.npz'), **out)
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
-    which = sys.argv[1:] or ['frontend', 'generator', 'losses']
+    which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators']
     for w in which:
         globals()[f'gen_{w}']()
 

@@ -300,3 +300,26 @@ def mr_stft_loss(x, y, resolutions=MR_STFT, use_mel_loss=False):
         sc_loss, mag_loss = sc_loss + sc, mag_loss + mag
     n = len(resolutions)
     return sc_loss / n, mag_loss / n
+
+
+def fold_discriminator_weights(sd):
+    """Effective conv weights of an MPD / MSD state_dict: weight norm folded (dim 0) and, for the
+    spectral-normed MSD[0], weight_orig / sigma with sigma = u . (W v) -- torch.nn.utils.spectral_norm
+    in eval mode (no power iteration; hifigan.py:294-296 wraps DiscriminatorS(use_spectral_norm=True))."""
+    out = {}
+    for k, v in sd.items():
+        if k.endswith('.weight_g') or k.endswith('.weight_u'):
+            continue
+        if k.endswith('.weight_orig'):
+            p = k[:-len('weight_orig')]
+            w_mat = v.reshape(v.shape[0], -1)
+            sigma = torch.dot(sd[p + 'weight_u'], torch.mv(w_mat, sd[p + 'weight_v']))
+            out[p + 'weight'] = v / sigma
+        elif k.endswith('.weight_v'):
+            p = k[:-len('weight_v')]
+            if p + 'weight_orig' in sd:
+                continue
+            out[p + 'weight'] = torch._weight_norm(v, sd[p + 'weight_g'], 0)
+        else:
+            out[k] = v
+    return out

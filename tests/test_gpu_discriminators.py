@@ -1,0 +1,81 @@
+"""-m gpu: MPD / MSD forward, GAN / feature losses and the multi-resolution STFT loss on the CUDA
+operators, against the fixtures the reference modules produced (tests/golden/discriminators.npz,
+losses.npz) and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from neuralsvb_b200.utils import synthetic as S
+from oracle import hifigan as O
+
+pytestmark = pytest.mark.gpu
+SEED = 1234
+REL = 2e-4          # fp32 kernels, different summation order than cuDNN / MKL: relative L-inf per tensor
+
+
+def _signals():
+    y = S.make_wave_batch(2, 8192, seed=SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=SEED + 5)[:, None]).clamp(-1, 1)
+    return y, y_hat
+
+
+@pytest.mark.parametrize('name', ['mpd', 'msd'])
+def test_discriminator_forward_matches_reference_fixture(golden_dir, name):
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    g = np.load(os.path.join(golden_dir, 'discriminators.npz'))
+    if name == 'mpd':
+        m, sd = D.MultiPeriodDiscriminator(), S.make_mpd_state_dict(SEED)
+    else:
+        m, sd = D.MultiScaleDiscriminator(), S.make_msd_state_dict(SEED)
+    m.load_state_dict(sd, strict=True)                    # reference key names and shapes
+    m = m.eval().cuda()
+    y, y_hat = _signals()
+    rs, gs, fr, fg = m(y.cuda(), y_hat.cuda())
+    torch.cuda.synchronize()
+    for i, (r, gg) in enumerate(zip(rs, gs)):
+        ref_r, ref_g = g[f'{name}/logit_r{i}'], g[f'{name}/logit_g{i}']
+        assert tuple(r.shape) == ref_r.shape                                  # bit-exact logit / fmap indexing
+        assert np.abs(r.cpu().numpy() - ref_r).max() <= REL * np.abs(ref_r).max() + 1e-6
+        assert np.abs(gg.cpu().numpy() - ref_g).max() <= REL * np.abs(ref_g).max() + 1e-6
+        for j, f in enumerate(fr[i]):
+            assert tuple(f.shape) == tuple(g[f'{name}/fmap_r{i}_{j}_shape'])
+            sub = f.cpu().numpy().reshape(-1)[::211]
+            ref = g[f'{name}/fmap_r{i}_{j}_sub']
+            assert np.abs(sub - ref).max() <= REL * np.abs(ref).max() + 1e-6, (i, j)
+    losses = [D.feature_loss(fr, fg), *D.discriminator_loss(rs, gs), D.generator_loss(gs)]
+    np.testing.assert_allclose(losses, g[f'{name}/losses'], rtol=1e-4)
+
+
+def test_multi_resolution_stft_loss_matches_reference_fixture(golden_dir):
+    from neuralsvb_b200.modules.parallel_wavegan.losses.stft_loss import multi_resolution_stft_loss
+    g = np.load(os.path.join(golden_dir, 'losses.npz'))
+    y = S.make_wave_batch(2, 8192, seed=SEED)
+    x = (y + 0.05 * S.make_wave_batch(2, 8192, seed=SEED + 1)).clamp(-1, 1)
+    sc, mag = multi_resolution_stft_loss(x.cuda(), y.cuda())
+    np.testing.assert_allclose([sc, mag], g['mr_stft/sc_mag'], rtol=1e-3)      # north star: 1e-3 on spectral features
+    sc_o, mag_o = O.mr_stft_loss(x, y)
+    np.testing.assert_allclose([sc, mag], [float(sc_o), float(mag_o)], rtol=1e-3)
+
+
+def test_generic_conv_edge_cases_against_torch():
+    """ragged / tiny shapes of the general conv: odd lengths, stride > 1, groups, W > 1, no bias."""
+    import torch.nn.functional as F
+    from neuralsvb_b200.modules.hifigan.discriminators import avg_pool_4_2_1, conv_nct
+    g = torch.Generator().manual_seed(3)
+    for (B, Cin, Cout, T, K, s, p, grp) in [(1, 1, 5, 17, 15, 1, 7, 1), (2, 8, 12, 101, 41, 4, 20, 4), (1, 6, 6, 9, 5, 2, 2, 3),
+                                           (2, 3, 7, 64, 3, 1, 1, 1)]:
+        x = torch.randn(B, Cin, T, generator=g)
+        w = torch.randn(Cout, Cin // grp, K, generator=g) * 0.2
+        b = torch.randn(Cout, generator=g)
+        ref = F.leaky_relu(F.conv1d(x.double(), w.double(), b.double(), stride=s, padding=p, groups=grp), 0.1)
+        got = conv_nct(x.cuda(), w.cuda(), b.cuda(), K, stride=s, pad=p, groups=grp, slope=0.1).cpu().double()
+        assert got.shape == ref.shape and (got - ref).abs().max() < 1e-4 * ref.abs().max()
+    x = torch.randn(2, 4, 30, 3, generator=g)                 # W = 3 inner columns, (5,1) kernel, stride (3,1)
+    w = torch.randn(6, 4, 5, generator=g) * 0.2
+    ref = F.conv2d(x.double(), w.double()[..., None], None, stride=(3, 1), padding=(2, 0))
+    got = conv_nct(x.cuda(), w.cuda(), None, 5, stride=3, pad=2, W=3).cpu().double()
+    assert got.shape == ref.shape and (got - ref).abs().max() < 1e-4 * ref.abs().max()
+    x = torch.randn(2, 1, 33, generator=g)
+    assert torch.allclose(avg_pool_4_2_1(x.cuda()).cpu(), F.avg_pool1d(x, 4, 2, padding=1), atol=1e-6)

@@ -85,3 +85,22 @@ def test_mel_filterbank_matches_torchaudio_slaney():
         mine = FE.mel_filterbank(sr, nfft, 80, fmin, fmax)
         assert np.abs(fb - mine).max() < 1e-6
         assert (mine.sum(axis=1) > 0).all()                             # no empty filters
+
+
+@pytest.mark.parametrize('name', ['mpd', 'msd'])
+def test_discriminators_and_gan_losses_match_reference(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, 'discriminators.npz'))
+    sd = S.make_mpd_state_dict(SEED) if name == 'mpd' else S.make_msd_state_dict(SEED)
+    w = O.fold_discriminator_weights(sd)
+    y = S.make_wave_batch(2, 8192, seed=SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=SEED + 5)[:, None]).clamp(-1, 1)
+    with torch.no_grad():
+        rs, gs, fr, fg = (O.mpd_forward if name == 'mpd' else O.msd_forward)(y, y_hat, w)
+        losses = [float(O.feature_loss(fr, fg)), *[float(v) for v in O.discriminator_loss(rs, gs)], float(O.generator_loss(gs))]
+    np.testing.assert_allclose(losses, g[f'{name}/losses'], rtol=2e-5)
+    for i, (r, gg) in enumerate(zip(rs, gs)):
+        assert r.shape == g[f'{name}/logit_r{i}'].shape
+        assert np.abs(r.numpy() - g[f'{name}/logit_r{i}']).max() < 2e-5 * max(1.0, np.abs(g[f'{name}/logit_r{i}']).max())
+        assert np.abs(gg.numpy() - g[f'{name}/logit_g{i}']).max() < 2e-5 * max(1.0, np.abs(g[f'{name}/logit_g{i}']).max())
+        for j, f in enumerate(fr[i]):
+            assert tuple(f.shape) == tuple(g[f'{name}/fmap_r{i}_{j}_shape'])
