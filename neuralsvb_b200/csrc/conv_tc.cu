@@ -199,6 +199,7 @@ struct TcArgs {
     int col_blocks, groups_per_b, total_groups;
     int tps, n_st, w_resident;  // taps per weight stage, stages per chunk, whole layer resident in smem
     uint32_t wstage_bytes;      // ring slot = tps weight tiles
+    int pdl;                    // launched with programmatic stream serialization
     int dbg;                    // SVB_TC_DBG bit mask: 1 no MMAs, 2 hi*hi only, 4 no transform, 8 no epilogue ld/st
     uint32_t raw_bytes;         // fp32 slab as TMA delivers it: R rows x 128 B
     uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
@@ -248,6 +249,13 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the
+    // tail of the previous kernel in the stream; its results are needed from here on.  The next
+    // kernel may begin ITS prologue as soon as every CTA of this grid has reached this point.
+    if (p.pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     // group id -> (column block, clip, first row); consecutive ids are neighbours in time
     auto decode = [&](int g, int &nblk, int &b, int &t0) {
@@ -637,8 +645,18 @@ static int launch_mode(const TcArgs &p, int grid, size_t smem, cudaStream_t st) 
         SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<grid, kTcThreadsP, smem, st>>>(p);
-    SVB_CUDA(cudaGetLastError());
+    static bool carve = false;
+    if (!carve) {   // keep the SM's smem/L1 split fixed across the differently-sized launches of a forward
+        SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        carve = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kTcThreadsP), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    SVB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     return SVB_OK;
 }
 
@@ -666,6 +684,8 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     p.wtile_bytes = (uint32_t)p.n_tile * 128 * planes;
     p.dbg = 0;
     if (const char *e = getenv("SVB_TC_DBG")) p.dbg = atoi(e);
+    p.pdl = 1;
+    if (const char *e = getenv("SVB_TC_PDL")) p.pdl = atoi(e) != 0;
     int force_mt = 0;
     if (const char *e = getenv("SVB_TC_MT")) force_mt = atoi(e);
     // ---- M tiles per group: each weight tile fetched from L2 feeds MT accumulators.  Two accumulator
