@@ -671,7 +671,7 @@ static int sm_count() {
     return n;
 }
 
-int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st) {
+int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st, int max_ctas) {
     SVB_CHECK(precision >= SVB_PREC_TF32 && precision <= SVB_PREC_BF16X3, SVB_ERR_INVALID, "tc conv: bad precision %d",
               precision);
     TcArgs p;
@@ -740,7 +740,7 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     p.tmem_cols = cols;
     p.groups_per_b = (tiles + p.MT - 1) / p.MT;
     p.total_groups = p.groups_per_b * a.B * p.col_blocks;
-    const int grid = std::min(p.total_groups, sm_count());
+    const int grid = std::min(p.total_groups, max_ctas > 0 ? std::min(max_ctas, sm_count()) : sm_count());
     switch (precision) {
         case SVB_PREC_TF32: return launch_mode<SVB_PREC_TF32>(p, grid, smem, st);
         case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3>(p, grid, smem, st);

@@ -16,6 +16,7 @@ struct TcWeights {
 // packed_ffma: [KS][Cin][CoutP] fp32 (the FFMA packing).  Allocations are appended to `allocs`.
 int tc_pack_weights(const float *packed_ffma, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs);
 bool tc_supported(const TcWeights &w, const ConvArgs &a);
-int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st);
+// max_ctas > 0 caps the persistent grid (used to run independent ResBlock chains side by side on SM subsets)
+int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st, int max_ctas = 0);
 
 }  // namespace svb

@@ -86,6 +86,12 @@ struct svb_gen {
         cudaEvent_t e0, e1;
         double bytes, flops;
     };
+    // independent ResBlock chains of a stage run side by side (SM subsets) on these streams
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_chain[3] = {nullptr, nullptr, nullptr};
+    int chains = 1;     // measured on B200: side-by-side chains on SM subsets are SLOWER (7.0 vs 5.7 ms/step); kept for experiments
+    double chain_bias = 4.0;
+
     bool profile = false;
     std::vector<LaunchRec> recs;
     std::vector<cudaEvent_t> ev_pool;
@@ -161,7 +167,8 @@ struct Plan {
 
 struct Buffers {
     size_t mel, pre, har, nsf;
-    std::vector<size_t> X, A, R, S;
+    std::vector<size_t> X, S;
+    std::vector<std::vector<size_t>> A, R;      // per ResBlock chain
 };
 
 Buffers plan_workspace(const svb_gen *g, int B, int T, size_t *total) {
@@ -175,7 +182,9 @@ Buffers plan_workspace(const svb_gen *g, int B, int T, size_t *total) {
     for (auto &s : g->stages) {
         Ti *= s.u;
         const size_t n = c4t_floats(B, s.C, Ti) * 4;
-        b.X.push_back(p.take(n)), b.A.push_back(p.take(n)), b.R.push_back(p.take(n)), b.S.push_back(p.take(n));
+        b.X.push_back(p.take(n)), b.S.push_back(p.take(n));
+        b.A.emplace_back(), b.R.emplace_back();
+        for (int j = 0; j < g->cfg.n_resblock_kernels; ++j) b.A.back().push_back(p.take(n)), b.R.back().push_back(p.take(n));
     }
     *total = p.total;
     return b;
@@ -207,7 +216,7 @@ struct ProfScope {
 };
 
 int run_conv(svb_gen *g, const ConvLayer &L, const float *in, int in_Tp, float *out, int out_Tp, const float *res,
-             int B, int Tq, float in_slope, float scale, int accumulate, cudaStream_t st) {
+             int B, int Tq, float in_slope, float scale, int accumulate, cudaStream_t st, int max_ctas = 0) {
     g->last_launches += 1;
     g->last_flops += 2.0 * L.macs_per_row * (double)B * Tq;
     const bool tc = g->cfg.precision != SVB_PREC_FP32 && L.tc.ok && L.Cin % 32 == 0;
@@ -220,7 +229,7 @@ int run_conv(svb_gen *g, const ConvLayer &L, const float *in, int in_Tp, float *
     a.in = in, a.w = L.w, a.bias = L.b, a.res = res, a.out = out;
     a.B = B, a.Cin = L.Cin, a.in_Tp = in_Tp, a.Cout = L.Cout, a.out_Tp = out_Tp, a.CoutP = L.CoutP, a.Tq = Tq;
     a.KS = L.KS, a.dil = L.dil, a.ups_u = L.ups_u, a.in_slope = in_slope, a.out_scale = scale, a.accumulate = accumulate;
-    if (g->cfg.precision != SVB_PREC_FP32 && tc_supported(L.tc, a)) return launch_conv_tc(L.tc, a, g->cfg.precision, st);
+    if (g->cfg.precision != SVB_PREC_FP32 && tc_supported(L.tc, a)) return launch_conv_tc(L.tc, a, g->cfg.precision, st, max_ctas);
     return launch_conv_ffma(a, st);
 }
 
@@ -280,7 +289,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
     for (size_t i = 0; i < g->stages.size(); ++i) {
         Stage &s = g->stages[i];
         const int Ti = Tin * s.u, Tip = c4t_rows(Ti);
-        float *X = F(bf.X[i]), *A = F(bf.A[i]), *R = F(bf.R[i]), *S = F(bf.S[i]);
+        float *X = F(bf.X[i]), *S = F(bf.S[i]);
         // x = ups[i](leaky_relu(x, 0.1))            hifigan.py:153-154
         SVB_TRY(run_conv(g, s.up, x_in, Tin_p, X, Tip, nullptr, B, Tin, 0.1f, 1.f, 0, st));
         if (f0) {                                   // x = x + noise_convs[i](har_source)   :155-157
@@ -292,7 +301,27 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         }
         g->taps["ups" + std::to_string(i)] = Tap{X, s.C, Ti, Tip, false};
         // xs = sum_j resblocks[i*nk + j](x) ; x = xs / nk      :158-164
+        // The nk ResBlocks only share their input: each chain runs on its own stream and SM subset, which
+        // amortises the per-launch fill/drain of the persistent kernels; the final convs (which add
+        // into S) are ordered by events.
+        const bool par = g->chains > 1 && nk > 1 && nk <= 3 && g->cfg.precision != SVB_PREC_FP32 && !g->profile;
+        const int sms = 148;
+        if (par) SVB_CUDA(cudaEventRecord(g->ev_fork, st));
         for (int j = 0; j < nk; ++j) {
+            cudaStream_t cs = par ? g->side[j] : st;
+            // SM share of a chain ~ its cost: kernel size plus a constant for the memory-bound part
+            int cap = 0;
+            if (par) {
+                double wsum = 0, wj = 0;
+                for (int jj = 0; jj < nk; ++jj) {
+                    const double wv = g->cfg.resblock_kernel_sizes[jj] + g->chain_bias;
+                    wsum += wv;
+                    if (jj == j) wj = wv;
+                }
+                cap = std::max(8, (int)(sms * wj / wsum + 0.5));
+            }
+            if (par) SVB_CUDA(cudaStreamWaitEvent(cs, g->ev_fork, 0));
+            float *A = F(bf.A[i][j]), *R = F(bf.R[i][j]);
             for (int m = 0; m < nd; ++m) {
                 const float *xin = m == 0 ? X : R;
                 const bool last = m == nd - 1;
@@ -300,13 +329,17 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
                 const float scale = last ? 1.f / nk : 1.f;
                 const int accum = (last && j > 0) ? 1 : 0;
                 if (g->cfg.resblock == 1) {         // ResBlock1.forward :54-61
-                    SVB_TRY(run_conv(g, s.c1[j][m], xin, Tip, A, Tip, nullptr, B, Ti, 0.1f, 1.f, 0, st));
-                    SVB_TRY(run_conv(g, s.c2[j][m], A, Tip, dst, Tip, xin, B, Ti, 0.1f, scale, accum, st));
+                    SVB_TRY(run_conv(g, s.c1[j][m], xin, Tip, A, Tip, nullptr, B, Ti, 0.1f, 1.f, 0, cs, cap));
+                    if (par && last && j > 0) SVB_CUDA(cudaStreamWaitEvent(cs, g->ev_chain[j - 1], 0));
+                    SVB_TRY(run_conv(g, s.c2[j][m], A, Tip, dst, Tip, xin, B, Ti, 0.1f, scale, accum, cs, cap));
                 } else {                            // ResBlock2.forward :81-86
-                    SVB_TRY(run_conv(g, s.c1[j][m], xin, Tip, dst, Tip, xin, B, Ti, 0.1f, scale, accum, st));
+                    if (par && last && j > 0) SVB_CUDA(cudaStreamWaitEvent(cs, g->ev_chain[j - 1], 0));
+                    SVB_TRY(run_conv(g, s.c1[j][m], xin, Tip, dst, Tip, xin, B, Ti, 0.1f, scale, accum, cs, cap));
                 }
             }
+            if (par) SVB_CUDA(cudaEventRecord(g->ev_chain[j], cs));
         }
+        if (par) SVB_CUDA(cudaStreamWaitEvent(st, g->ev_chain[nk - 1], 0));
         g->taps["stage" + std::to_string(i)] = Tap{S, s.C, Ti, Tip, false};
         x_in = S, Tin = Ti, Tin_p = Tip;
     }
@@ -357,6 +390,13 @@ extern "C" int svb_gen_create(const svb_gen_config *cfg, int device, svb_gen_t *
     for (int i = 0; i < cfg->n_ups; ++i) g->hop *= cfg->upsample_rates[i];
     SVB_CUDA(cudaEventCreate(&g->ev0));
     SVB_CUDA(cudaEventCreate(&g->ev1));
+    SVB_CUDA(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) {
+        SVB_CUDA(cudaStreamCreateWithFlags(&g->side[i], cudaStreamNonBlocking));
+        SVB_CUDA(cudaEventCreateWithFlags(&g->ev_chain[i], cudaEventDisableTiming));
+    }
+    if (const char *e = getenv("SVB_CHAINS")) g->chains = atoi(e);
+    if (const char *e = getenv("SVB_CHAIN_BIAS")) g->chain_bias = atof(e);
     *out = g;
     return SVB_OK;
 }
@@ -371,6 +411,11 @@ extern "C" void svb_gen_destroy(svb_gen_t *g) {
     if (g->dev_in) cudaFree(g->dev_in);
     if (g->dev_out) cudaFree(g->dev_out);
     for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 3; ++i) {
+        if (g->side[i]) cudaStreamDestroy(g->side[i]);
+        if (g->ev_chain[i]) cudaEventDestroy(g->ev_chain[i]);
+    }
+    if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     delete g;
