@@ -196,6 +196,7 @@ struct TcArgs {
     ConvArgs a;
     const unsigned char *w;     // packed, pre-swizzled weight tiles of this mode
     int n_tile, n_chunks, MT, R, Rp, nW, nA, tmem_cols;
+    int n_sets;                 // accumulator sets in TMEM: 2 = epilogue of group g overlaps MMAs of g+1; 1 = MT can be twice as large
     int col_blocks, groups_per_b, total_groups;
     int tps, n_st, w_resident;  // taps per weight stage, stages per chunk, whole layer resident in smem
     uint32_t wstage_bytes;      // ring slot = tps weight tiles
@@ -389,8 +390,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 if (++sA == p.nA) sA = 0, phA ^= 1;
             }
             if (elected) umma_commit(acc_full + as);
-            as ^= 1;
-            if (as == 0) phE ^= 1;
+            if (++as == p.n_sets) as = 0, phE ^= 1;
             first_group = false;
         }
     } else if (warp >= kWarpTransform0) {
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x, ++gi) {
             int nblk, b, t0;
             decode(g, nblk, b, t0);
-            const int as = gi & 1;
+            const int as = p.n_sets == 2 ? (gi & 1) : 0;
             // block -> float4 index of row (q_base + 0) of its 32-row x 128-byte tile, rows are 8 float4 apart
             // (u*8 apart for an upsampler); q_base = first GEMM row of this warp in the block
             auto block_base = [&](int blk, int &co0, int &q_base) -> size_t {
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 }
             };
             fetch_res(half);
-            mbar_wait(acc_full + as, (gi >> 1) & 1);
+            mbar_wait(acc_full + as, (p.n_sets == 2 ? (gi >> 1) : gi) & 1);
             tc_fence_after();
             for (int blk = half; blk < nblocks; blk += 2) {
                 const int m = blk / jb, j = blk - m * jb;
@@ -692,10 +692,23 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     // sets live in TMEM (2 * MT * N <= 512 columns); slabs and the weight ring must fit shared memory.
     size_t smem = 0;
     const size_t budget = 226 * 1024 - kStageBytes;
+    int force_sets = 0;
+    if (const char *e = getenv("SVB_TC_SETS")) force_sets = atoi(e);
+    const long long tile_units = (long long)tiles * p.col_blocks * a.B;
     for (int MT : {4, 2, 1}) {
         if (force_mt && MT != force_mt && MT != 1) continue;
-        if (!force_mt && (MT == 4 || (MT == 2 && tiles < 2))) continue;   // measured: MT = 2 wins; single-tile clips use 1
-        if (2 * MT * p.n_tile > 512) continue;
+        // Two accumulator sets (epilogue overlapped) need 2*MT*N <= 512 TMEM columns.  Wide layers
+        // (N = 128) that are bound by weight streaming from L2 take MT = 4 with ONE set instead:
+        // every weight tile then feeds 512 rows.  Needs enough groups to keep all SMs busy.
+        int sets = 2 * MT * p.n_tile <= 512 ? 2 : 1;
+        if (force_sets) sets = force_sets;
+        if (sets * MT * p.n_tile > 512) continue;
+        if (!force_mt) {
+            if (MT == 4) continue;      // measured: MT = 4 (one or two accumulator sets) is slower than MT = 2 on every layer
+            (void)tile_units;
+            if (MT == 2 && tiles < 2) continue;
+        }
+        p.n_sets = sets;
         if ((tiles + MT - 1) / MT * MT * kTcM > round_up(a.Tq, kTileT) && MT != 1) continue;   // stay inside the allocation
         p.MT = MT;
         p.R = MT * kTcM + 2 * halo;
@@ -733,10 +746,10 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         break;
     }
     if (getenv("SVB_TC_VERBOSE"))
-        fprintf(stderr, "[tc] Cin %d CoutP %d KS %d dil %d Tq %d | n_tile %d MT %d R %d nA %d tps %d n_st %d nW %d resident %d smem %zu\n",
-                a.Cin, a.CoutP, a.KS, a.dil, a.Tq, p.n_tile, p.MT, p.R, p.nA, p.tps, p.n_st, p.nW, p.w_resident, smem);
+        fprintf(stderr, "[tc] Cin %d CoutP %d KS %d dil %d Tq %d | n_tile %d MT %d sets %d R %d nA %d tps %d n_st %d nW %d resident %d smem %zu\n",
+                a.Cin, a.CoutP, a.KS, a.dil, a.Tq, p.n_tile, p.MT, p.n_sets, p.R, p.nA, p.tps, p.n_st, p.nW, p.w_resident, smem);
     int cols = 32;
-    while (cols < 2 * p.MT * p.n_tile) cols <<= 1;
+    while (cols < p.n_sets * p.MT * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
     p.groups_per_b = (tiles + p.MT - 1) / p.MT;
     p.total_groups = p.groups_per_b * a.B * p.col_blocks;
