@@ -205,7 +205,7 @@ struct TcArgs {
     uint32_t raw_bytes;         // fp32 slab as TMA delivers it: R rows x 128 B
     uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
     uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile (x2 with the 3xTF32 lo plane)
-    uint32_t off_op, off_w, off_stage;   // byte offsets of operand slots / weight ring / epilogue tiles in dynamic smem
+    uint32_t off_op, off_w, off_stage, off_bias;   // byte offsets of operand slots / weight ring / epilogue tiles / bias in dynamic smem
 };
 
 constexpr int kMaxW = 8;
@@ -214,6 +214,7 @@ constexpr int kMaxW = 8;
 constexpr int kTcThreadsP = 576;
 constexpr int kWarpProducer = 16, kWarpMma = 17, kWarpTransform0 = 8;
 constexpr int kStageBytes = 8 * 4096;   // epilogue transpose tiles: 32 rows x 128 B per epilogue warp
+constexpr int kBiasBytes = 4096;        // bias of the layer (Cout <= 1024 floats)
 
 // Persistent kernel: one CTA per SM walks "groups" (MT consecutive 128-row tiles of one clip for
 // one column block).  Every stage is decoupled by mbarriers, so the TMA producer runs ahead into
@@ -246,6 +247,10 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         fence_barrier_init();
     }
     if (warp == kWarpMma) tmem_alloc(tmem_ptr, p.tmem_cols);
+    {   // bias is constant data (not produced by the previous kernel): stage it once, before the PDL wait
+        float *sb = reinterpret_cast<float *>(smem + p.off_bias);
+        for (int i = threadIdx.x; i < a.Cout; i += kTcThreadsP) sb[i] = __ldg(a.bias + i);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -408,37 +413,63 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
             for (int c = 0; c < p.n_chunks; ++c) {
                 mbar_wait(raw_full + sA, phA);
                 uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
-                for (int r0 = 0; r0 < ((p.dbg & 4) ? 0 : p.R); r0 += 32) {   // 32 rows per pass over the 256 threads
-                    const int r = r0 + (tid >> 3);
-                    const bool ok = r < p.R;
-                    uint4 *row = op + (size_t)r * 8;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) v = *reinterpret_cast<const float4 *>(row + cl);
-                    v.x = fmaxf(v.x, v.x * slope), v.y = fmaxf(v.y, v.y * slope);
-                    v.z = fmaxf(v.z, v.z * slope), v.w = fmaxf(v.w, v.w * slope);
-                    const int sw = r & 7;
+                // 64 rows per pass over the 256 threads: two independent rows per thread for ILP
+                for (int r0 = 0; r0 < ((p.dbg & 4) ? 0 : p.R); r0 += 64) {
+                    int rr[2];
+                    bool ok[2];
+                    float4 v[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        rr[u] = r0 + 32 * u + (tid >> 3);
+                        ok[u] = rr[u] < p.R;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok[u]) v[u] = *reinterpret_cast<const float4 *>(op + (size_t)rr[u] * 8 + cl);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        float4 &x = v[u];
+                        x.x = fmaxf(x.x, x.x * slope), x.y = fmaxf(x.y, x.y * slope);
+                        x.z = fmaxf(x.z, x.z * slope), x.w = fmaxf(x.w, x.w * slope);
+                    }
                     if (BF) {
-                        const __nv_bfloat162 hA = __floats2bfloat162_rn(v.x, v.y), hB = __floats2bfloat162_rn(v.z, v.w);
-                        const uint32_t h0 = *reinterpret_cast<const uint32_t *>(&hA), h1 = *reinterpret_cast<const uint32_t *>(&hB);
-                        const __nv_bfloat162 lA = __floats2bfloat162_rn(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u));
-                        const __nv_bfloat162 lB = __floats2bfloat162_rn(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u));
-                        const uint32_t l0 = *reinterpret_cast<const uint32_t *>(&lA), l1 = *reinterpret_cast<const uint32_t *>(&lB);
-                        // even lane keeps hi and receives the neighbour's hi; odd lane keeps lo
-                        const uint32_t s0 = odd ? h0 : l0, s1 = odd ? h1 : l1;       // what the partner needs
-                        const uint32_t g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-                        if (ok) {
-                            if (!odd) row[(cl >> 1) ^ sw] = make_uint4(h0, h1, g0, g1);          // channels 8j..8j+7 hi
-                            else row[(4 + (cl >> 1)) ^ sw] = make_uint4(g0, g1, l0, l1);          // channels 8j..8j+7 lo
+                        uint32_t h0[2], h1[2], l0[2], l1[2], g0[2], g1[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const __nv_bfloat162 hA = __floats2bfloat162_rn(v[u].x, v[u].y), hB = __floats2bfloat162_rn(v[u].z, v[u].w);
+                            h0[u] = *reinterpret_cast<const uint32_t *>(&hA), h1[u] = *reinterpret_cast<const uint32_t *>(&hB);
+                            const __nv_bfloat162 lA = __floats2bfloat162_rn(v[u].x - __uint_as_float(h0[u] << 16),
+                                                                           v[u].y - __uint_as_float(h0[u] & 0xffff0000u));
+                            const __nv_bfloat162 lB = __floats2bfloat162_rn(v[u].z - __uint_as_float(h1[u] << 16),
+                                                                           v[u].w - __uint_as_float(h1[u] & 0xffff0000u));
+                            l0[u] = *reinterpret_cast<const uint32_t *>(&lA), l1[u] = *reinterpret_cast<const uint32_t *>(&lB);
+                        }
+                        // even lane keeps hi and receives the neighbour's hi; odd lane keeps lo (shuffles also order reads before writes)
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            g0[u] = __shfl_xor_sync(0xffffffffu, odd ? h0[u] : l0[u], 1);
+                            g1[u] = __shfl_xor_sync(0xffffffffu, odd ? h1[u] : l1[u], 1);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (!ok[u]) continue;
+                            uint4 *row = op + (size_t)rr[u] * 8;
+                            const int sw = rr[u] & 7;
+                            if (!odd) row[(cl >> 1) ^ sw] = make_uint4(h0[u], h1[u], g0[u], g1[u]);          // channels 8j..8j+7 hi
+                            else row[(4 + (cl >> 1)) ^ sw] = make_uint4(g0[u], g1[u], l0[u], l1[u]);          // channels 8j..8j+7 lo
                         }
                     } else {
-                        const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
                         __syncwarp();
-                        if (ok) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (!ok[u]) continue;
+                            uint4 *row = op + (size_t)rr[u] * 8;
+                            const int sw = rr[u] & 7;
+                            const float4 h = make_float4(to_tf32(v[u].x), to_tf32(v[u].y), to_tf32(v[u].z), to_tf32(v[u].w));
                             row[cl ^ sw] = make_uint4(__float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w));
                             if (X3)
                                 (row + p.op_bytes / 32)[cl ^ sw] =
-                                    make_uint4(__float_as_uint(to_tf32(v.x - h.x)), __float_as_uint(to_tf32(v.y - h.y)),
-                                               __float_as_uint(to_tf32(v.z - h.z)), __float_as_uint(to_tf32(v.w - h.w)));
+                                    make_uint4(__float_as_uint(to_tf32(v[u].x - h.x)), __float_as_uint(to_tf32(v[u].y - h.y)),
+                                               __float_as_uint(to_tf32(v[u].z - h.z)), __float_as_uint(to_tf32(v[u].w - h.w)));
                         }
                     }
                 }
@@ -513,7 +544,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 // own row: accumulator + bias (+ residual) -> tile
 #pragma unroll
                 for (int gq = 0; gq < 8; ++gq) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + co0 + 4 * gq));
+                    const float4 bv = *reinterpret_cast<const float4 *>(smem + p.off_bias + (size_t)(co0 + 4 * gq) * 4);
                     float4 o = make_float4(v[4 * gq] + bv.x, v[4 * gq + 1] + bv.y, v[4 * gq + 2] + bv.z, v[4 * gq + 3] + bv.w);
                     float4 *slot = tile + lane * 8 + (gq ^ (lane & 7));
                     if (res4) {
@@ -634,7 +665,7 @@ int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *
 
 bool tc_supported(const TcWeights &w, const ConvArgs &a) {
     return w.ok && a.Cin % kTcCK == 0 && a.bias != nullptr && (a.KS - 1) / 2 * a.dil <= kPad &&
-           (a.ups_u == 0 || a.Cout % 32 == 0);
+           (a.ups_u == 0 || a.Cout % 32 == 0) && a.Cout <= 1024;
 }
 
 template <int MODE>
@@ -691,7 +722,7 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     // ---- M tiles per group: each weight tile fetched from L2 feeds MT accumulators.  Two accumulator
     // sets live in TMEM (2 * MT * N <= 512 columns); slabs and the weight ring must fit shared memory.
     size_t smem = 0;
-    const size_t budget = 226 * 1024 - kStageBytes;
+    const size_t budget = 226 * 1024 - kStageBytes - kBiasBytes;
     int force_sets = 0;
     if (const char *e = getenv("SVB_TC_SETS")) force_sets = atoi(e);
     const long long tile_units = (long long)tiles * p.col_blocks * a.B;
@@ -742,7 +773,8 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         nW = std::max(1, std::min(std::min(nW, kMaxW), p.w_resident ? 1 : 1 << 30));
         p.nW = nW;
         p.off_stage = p.off_w + (uint32_t)nW * p.wstage_bytes;
-        smem = (size_t)p.off_stage + kStageBytes;
+        p.off_bias = p.off_stage + kStageBytes;
+        smem = (size_t)p.off_bias + kBiasBytes;
         break;
     }
     if (getenv("SVB_TC_VERBOSE"))

@@ -11,6 +11,9 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 
 def pytest_configure(config):
+    # torch's intra-op pool does not scale to 100+ threads on the oracle's small convolutions
+    import torch
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 

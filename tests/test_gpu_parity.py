@@ -130,7 +130,6 @@ def test_generator_full_size_against_oracle():
     cfg, B, T = 'hop256', 16, 128
     h, hop, mel, f0, ri, nz = U.inputs(cfg, True, B, T)
     w = O.fold_weight_norm(S.make_generator_state_dict(h, U.SEED))
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
     with torch.no_grad():
         y_o = O.generator_forward(w, h, mel, f0, ri, nz).numpy()[:, 0]
     for precision in PRECISIONS:
