@@ -623,9 +623,10 @@ static int pick_n_tile(int CoutP) {      // columns per CTA: a multiple of 32 (o
 int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs) {
     out->KS = KS, out->Cin = Cin, out->CoutP = CoutP, out->ok = false;
     const int n_tile = pick_n_tile(CoutP);
-    if (n_tile == 0 || n_tile % 8 != 0 || Cin % kTcCK != 0) return SVB_OK;    // CUDA cores handle it
+    if (n_tile == 0 || n_tile % 8 != 0 || Cin % 4 != 0) return SVB_OK;    // CUDA cores handle it
     out->n_tile = n_tile;
-    const int n_chunks = Cin / kTcCK, n_blk = CoutP / n_tile;
+    // input channels are padded to whole 32-channel groups (zero weights against the zero pad channels of G32T)
+    const int n_chunks = (Cin + kTcCK - 1) / kTcCK, n_blk = CoutP / n_tile;
     const size_t tile_b = (size_t)n_tile * 128;                    // bytes per tile plane
     const size_t n_tiles = (size_t)n_blk * n_chunks * KS;
     std::vector<unsigned char> tf(n_tiles * tile_b), tf3(n_tiles * tile_b * 2), bf(n_tiles * tile_b);
@@ -639,7 +640,8 @@ int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *
                 uint16_t *tb = reinterpret_cast<uint16_t *>(bf.data() + t * tile_b);
                 for (int n = 0; n < n_tile; ++n)
                     for (int ci = 0; ci < kTcCK; ++ci) {
-                        const float w = packed[((size_t)k * Cin + c * kTcCK + ci) * CoutP + nb * n_tile + n];
+                        const int cin_i = c * kTcCK + ci;
+                        const float w = cin_i < Cin ? packed[((size_t)k * Cin + cin_i) * CoutP + nb * n_tile + n] : 0.f;
                         const float h = host_tf32(w);
                         const int c16 = ci >> 2;                   // fp32: 4 channels per 16-byte chunk
                         const size_t i4 = (size_t)n * 32 + ((c16 ^ (n & 7)) << 2) + (ci & 3);
@@ -664,7 +666,7 @@ int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *
 }
 
 bool tc_supported(const TcWeights &w, const ConvArgs &a) {
-    return w.ok && a.Cin % kTcCK == 0 && a.bias != nullptr && (a.KS - 1) / 2 * a.dil <= kPad &&
+    return w.ok && a.Cin % 4 == 0 && a.bias != nullptr && (a.KS - 1) / 2 * a.dil <= kPad &&
            (a.ups_u == 0 || a.Cout % 32 == 0) && a.Cout <= 1024;
 }
 
@@ -707,7 +709,7 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
               precision);
     TcArgs p;
     p.a = a, p.w = reinterpret_cast<const unsigned char *>(w.blob[precision]);
-    p.n_tile = w.n_tile, p.n_chunks = a.Cin / kTcCK;
+    p.n_tile = w.n_tile, p.n_chunks = (a.Cin + kTcCK - 1) / kTcCK;
     const int halo = (a.KS - 1) / 2 * a.dil;
     const int tiles = (a.Tq + kTcM - 1) / kTcM;              // 128-row tiles per clip
     p.col_blocks = a.CoutP / p.n_tile;

@@ -219,7 +219,7 @@ int run_conv(svb_gen *g, const ConvLayer &L, const float *in, int in_Tp, float *
              int B, int Tq, float in_slope, float scale, int accumulate, cudaStream_t st, int max_ctas = 0) {
     g->last_launches += 1;
     g->last_flops += 2.0 * L.macs_per_row * (double)B * Tq;
-    const bool tc = g->cfg.precision != SVB_PREC_FP32 && L.tc.ok && L.Cin % 32 == 0;
+    const bool tc = g->cfg.precision != SVB_PREC_FP32 && L.tc.ok;
     const double rows_out = (double)B * Tq * (L.ups_u > 0 ? L.ups_u : 1);
     // layer-streaming bytes: input once, output once, residual / accumulated sum once more each
     const double bytes = 4.0 * ((double)B * Tq * L.Cin + rows_out * L.Cout * (1 + (res ? 1 : 0) + (accumulate ? 1 : 0)));
