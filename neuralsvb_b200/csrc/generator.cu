@@ -270,12 +270,24 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
 
     const int Tw = T * g->hop;
     float *har = nullptr;
+    bool har_on_side = false;
     if (f0) {
+        // The NSF source only meets the main chain at the first noise_conv_add: run it on a side stream
+        // so it overlaps conv_pre and the first upsampler.
         har = F(bf.har);
+        har_on_side = !g->profile;
+        cudaStream_t ns = har_on_side ? g->side[0] : st;
+        if (har_on_side) {
+            SVB_CUDA(cudaEventRecord(g->ev_fork, st));
+            SVB_CUDA(cudaStreamWaitEvent(ns, g->ev_fork, 0));
+        }
         int l = 0;
-        ProfScope ps(g, st, "nsf source (4 kernels)", 4.0 * B * (T + (double)Tw * (noise ? 10 : 1)), 60.0 * B * Tw * 9);
-        SVB_TRY(launch_nsf_source(f0, rand_ini, noise, seed, B, T, g->hop, (float)g->cfg.audio_sample_rate, g->lin_w,
-                                  g->lin_b, g->ws + bf.nsf, har, st, &l));
+        {
+            ProfScope ps(g, ns, "nsf source (4 kernels)", 4.0 * B * (T + (double)Tw * (noise ? 10 : 1)), 60.0 * B * Tw * 9);
+            SVB_TRY(launch_nsf_source(f0, rand_ini, noise, seed, B, T, g->hop, (float)g->cfg.audio_sample_rate, g->lin_w,
+                                      g->lin_b, g->ws + bf.nsf, har, ns, &l));
+        }
+        if (har_on_side) SVB_CUDA(cudaEventRecord(g->ev_chain[0], ns));
         g->last_launches += l;
         g->taps["har_source"] = Tap{har, 1, Tw, 0, true};
     }
@@ -293,6 +305,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         // x = ups[i](leaky_relu(x, 0.1))            hifigan.py:153-154
         SVB_TRY(run_conv(g, s.up, x_in, Tin_p, X, Tip, nullptr, B, Tin, 0.1f, 1.f, 0, st));
         if (f0) {                                   // x = x + noise_convs[i](har_source)   :155-157
+            if (har_on_side && i == 0) SVB_CUDA(cudaStreamWaitEvent(st, g->ev_chain[0], 0));
             ProfScope ps(g, st, "noise_conv_add", 4.0 * B * (2.0 * Ti * s.C + Tw), 2.0 * B * (double)Ti * s.C * s.noise.K);
             SVB_TRY(launch_noise_conv_add(X, B, s.C, Ti, Tip, har, Tw, s.noise.w, s.noise.b, s.noise.K, s.noise.stride,
                                           s.noise.pad, st));
