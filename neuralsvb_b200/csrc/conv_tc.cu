@@ -498,12 +498,38 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         const int wr = lane >> 3, wc = lane & 7;                    // wide mapping: row offset / chunk
         const bool no_mem = p.dbg & 8;
         int gi = 0;
+        const size_t rstep = (size_t)(a.ups_u > 0 ? a.ups_u : 1) * 8;      // float4 between consecutive GEMM rows
+        float4 rres[8];
+        // (group, block) -> float4 index of row (q_base + 0) of its 32-row x 128-byte tile; rows are rstep apart;
+        // q_base = first GEMM row of this warp in the block
+        auto block_base_g = [&](int g, int blk, int &co0, int &q_base) -> size_t {
+            int nblk, b, t0;
+            decode(g, nblk, b, t0);
+            const int m = blk / jb, j = blk - m * jb;
+            q_base = t0 + m * kTcM + lane_base;
+            const int cop0 = nblk * p.n_tile + j * 32;              // 32 columns never straddle an upsampler phase
+            int phi = 0;
+            co0 = cop0;
+            if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
+            return (((size_t)b * gout + (co0 >> 5)) * a.out_Tp + kPad +
+                    (a.ups_u > 0 ? (size_t)q_base * a.ups_u + phi : (size_t)q_base)) * 8;
+        };
+        // residual rows of one block in the wide mapping -> registers (latency hidden behind the current block)
+        auto fetch_res = [&](int g, int blk) {
+            if (!res4 || no_mem || g >= p.total_groups) return;
+            int co0, q_base;
+            const size_t base = block_base_g(g, blk, co0, q_base);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + wr;
+                rres[i] = (q_base + rr < a.Tq) ? __ldg(res4 + base + (size_t)rr * rstep + wc) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (half < nblocks) fetch_res(blockIdx.x, half);
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x, ++gi) {
             int nblk, b, t0;
             decode(g, nblk, b, t0);
             const int as = p.n_sets == 2 ? (gi & 1) : 0;
-            // block -> float4 index of row (q_base + 0) of its 32-row x 128-byte tile, rows are 8 float4 apart
-            // (u*8 apart for an upsampler); q_base = first GEMM row of this warp in the block
             auto block_base = [&](int blk, int &co0, int &q_base) -> size_t {
                 const int m = blk / jb, j = blk - m * jb;
                 q_base = t0 + m * kTcM + lane_base;
@@ -514,19 +540,6 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 return (((size_t)b * gout + (co0 >> 5)) * a.out_Tp + kPad +
                         (a.ups_u > 0 ? (size_t)q_base * a.ups_u + phi : (size_t)q_base)) * 8;
             };
-            const size_t rstep = (size_t)(a.ups_u > 0 ? a.ups_u : 1) * 8;      // float4 between consecutive GEMM rows
-            float4 rres[8];
-            auto fetch_res = [&](int blk) {
-                if (!res4 || no_mem || blk >= nblocks) return;
-                int co0, q_base;
-                const size_t base = block_base(blk, co0, q_base);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = 4 * i + wr;
-                    rres[i] = (q_base + rr < a.Tq) ? __ldg(res4 + base + (size_t)rr * rstep + wc) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            fetch_res(half);
             mbar_wait(acc_full + as, (p.n_sets == 2 ? (gi >> 1) : gi) & 1);
             tc_fence_after();
             for (int blk = half; blk < nblocks; blk += 2) {
@@ -538,7 +551,9 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                     for (int i = 0; i < 8; ++i) tile[(4 * i + wr) * 8 + (wc ^ ((4 * i + wr) & 7))] = rres[i];
                     __syncwarp();
                 }
-                fetch_res(blk + 2);
+                // prefetch the residual of this warp's NEXT block: same group, or the first one of its next group
+                if (blk + 2 < nblocks) fetch_res(g, blk + 2);
+                else fetch_res(g + gridDim.x, half);
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * acc_cols + m * p.n_tile + j * 32), v);
                 // own row: accumulator + bias (+ residual) -> tile
