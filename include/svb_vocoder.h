@@ -133,6 +133,29 @@ float svb_gen_last_ms(svb_gen_t *g);
 int32_t svb_gen_profile_count(svb_gen_t *g);
 int svb_gen_profile_get(svb_gen_t *g, int32_t i, char *name, int32_t name_cap, float *ms, double *bytes, double *flops);
 
+/* ---- training: backward of the generator -------------------------------------------------------------
+ * Replaces torch autograd through HifiGanGenerator.forward (modules/hifigan/hifigan.py:144-169; ResBlock1/2
+ * :54-61 / :81-86; weight_norm :35-50,118,124; SourceModuleHnNSF.l_linear source.py:393-394) for the
+ * vocoder training step (SURVEY 8(d) cfg 3).
+ *   svb_gen_set_training(g, 1): forwards keep every conv input (the tape), the flipped / transposed weight
+ *     packings of the data-gradient convs are built and one gradient buffer per folded tensor is allocated.
+ *   svb_gen_backward(g, dwav [B, T*hop]): ACCUMULATES d(loss)/d(folded tensor) for the last forward into those
+ *     buffers (svb_gen_zero_grad clears them), in the reference's tensor names and layouts
+ *     ("conv_pre.weight" [Cout,Cin,K], "ups.0.weight" [Cin,Cout,K], "noise_convs.0.weight",
+ *     "resblocks.3.convs1.0.bias", "conv_post.weight", "m_source.l_linear.weight", ...).
+ *   svb_gen_get_grad copies one of them to a device buffer of exactly svb_gen_grad_numel floats.
+ *   After an optimizer step: svb_gen_set_weight(...) for the changed tensors, then svb_gen_update_weights(g).
+ *   svb_weight_norm_backward: (dv, dg) of w = g * v / ||v|| (norm over all dims but 0) from dw. */
+int svb_gen_set_training(svb_gen_t *g, int32_t on);
+int svb_gen_update_weights(svb_gen_t *g);
+int svb_gen_zero_grad(svb_gen_t *g, void *stream);
+int svb_gen_backward(svb_gen_t *g, const float *dwav_dev, void *stream);
+int64_t svb_gen_grad_numel(svb_gen_t *g, const char *name);
+int svb_gen_get_grad(svb_gen_t *g, const char *name, float *dst_dev, int64_t n, void *stream);
+int64_t svb_gen_bwd_launches(const svb_gen_t *g);
+int svb_weight_norm_backward(const float *v_dev, const float *g_dev, const float *dw_dev, int64_t rows, int64_t cols,
+                             float *dv_dev, float *dg_dev, void *stream);
+
 /* One convolution layer of the generator on PyTorch-layout device tensors, through the CUDA-core
  * (precision 0) or tcgen05 (1, 2) kernel -- for kernel-level parity tests and per-layer timing.
  *   y = out_scale * (conv(leaky_relu(x, in_slope)) + bias [+ res])

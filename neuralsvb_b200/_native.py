@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libsvb_vocoder.so')
 HEADER = os.path.join(_ROOT, 'include', 'svb_vocoder.h')
 SOURCES = ['api.cu', 'conv_ffma.cu', 'conv_tc.cu', 'nsf_source.cu', 'frontend.cu', 'generator.cu', 'layer_api.cu', 'disc_ops.cu',
-           'train_ops.cu']
+           'train_ops.cu', 'generator_bwd.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -105,6 +105,14 @@ _PROTOS = {
     'svb_gen_last_flops': (ctypes.c_double, [_P]),
     'svb_gen_enable_timing': (ctypes.c_int, [_P, _I32]),
     'svb_gen_last_ms': (ctypes.c_float, [_P]),
+    'svb_gen_set_training': (ctypes.c_int, [_P, _I32]),
+    'svb_gen_update_weights': (ctypes.c_int, [_P]),
+    'svb_gen_zero_grad': (ctypes.c_int, [_P, _P]),
+    'svb_gen_backward': (ctypes.c_int, [_P, _P, _P]),
+    'svb_gen_grad_numel': (_I64, [_P, ctypes.c_char_p]),
+    'svb_gen_get_grad': (ctypes.c_int, [_P, ctypes.c_char_p, _P, _I64, _P]),
+    'svb_gen_bwd_launches': (_I64, [_P]),
+    'svb_weight_norm_backward': (ctypes.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P]),
     'svb_gen_profile_count': (_I32, [_P]),
     'svb_gen_profile_get': (ctypes.c_int, [_P, _I32, ctypes.c_char_p, _I32, ctypes.POINTER(ctypes.c_float),
                                             ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

@@ -5,102 +5,11 @@
 #include <string>
 #include <vector>
 
-#include "conv_ffma.cuh"
-#include "conv_tc.cuh"
-#include "nsf_source.cuh"
+#include "generator.cuh"
 
 using namespace svb;
 
-namespace {
-
-struct HostTensor {
-    std::vector<int64_t> shape;
-    std::vector<float> data;
-};
-
-struct ConvLayer {          // one GEMM-shaped layer on the C4T layout
-    float *w = nullptr;     // FFMA packing [KS][Cin][CoutP]
-    float *b = nullptr;     // [Cout]
-    TcWeights tc;           // tensor-core packing (optional)
-    int Cin = 0, Cout = 0, CoutP = 0, KS = 1, dil = 1, ups_u = 0;
-    double macs_per_row = 0;   // algorithmic MACs per GEMM row (true taps only)
-};
-
-struct NoiseConv {
-    float *w = nullptr, *b = nullptr;
-    int C = 0, K = 1, stride = 1, pad = 0;
-};
-
-struct Stage {
-    int C = 0;              // channels after the upsampler
-    int u = 1;
-    ConvLayer up;
-    NoiseConv noise;
-    // resblocks[j].c1[m], c2[m]  (ResBlock2: only c1 used)
-    std::vector<std::vector<ConvLayer>> c1, c2;
-};
-
-struct Tap {
-    const float *p = nullptr;
-    int C = 0, T = 0, Tp = 0;
-    bool plain = false;     // [B][T] instead of C4T
-};
-
-}  // namespace
-
-struct svb_gen {
-    svb_gen_config cfg{};
-    int device = 0;
-    bool finalized = false;
-    std::map<std::string, HostTensor> host_w;
-    std::vector<void *> dev_allocs;
-
-    ConvLayer conv_pre;
-    std::vector<Stage> stages;
-    float *post_wq = nullptr;
-    float post_bias = 0.f;
-    int post_K = 7, post_C = 0;
-    float *lin_w = nullptr;
-    float lin_b = 0.f;
-    int hop = 1;
-
-    // workspace
-    char *ws = nullptr;
-    size_t ws_cap = 0;
-    int ws_B = 0, ws_T = 0;
-    std::map<std::string, Tap> taps;
-    int last_B = 0;
-
-    // host staging (spec2wav_host)
-    float *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
-    size_t pin_in_cap = 0, pin_out_cap = 0;
-
-    int64_t last_launches = 0;
-    double last_flops = 0;
-    bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-
-    // per-launch profile of the last forward (svb_gen_enable_timing(g, 2)): CUDA events around every launch
-    struct LaunchRec {
-        const char *name;
-        cudaEvent_t e0, e1;
-        double bytes, flops;
-    };
-    // independent ResBlock chains of a stage run side by side (SM subsets) on these streams
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_chain[3] = {nullptr, nullptr, nullptr};
-    int chains = 1;     // measured on B200: side-by-side chains on SM subsets are SLOWER (7.0 vs 5.7 ms/step); kept for experiments
-    double chain_bias = 4.0;
-
-    bool profile = false;
-    std::vector<LaunchRec> recs;
-    std::vector<cudaEvent_t> ev_pool;
-    size_t ev_used = 0;
-};
-
-namespace {
-
-int upload(svb_gen *g, const std::vector<float> &h, float **out) {
+int svb::gen_upload(svb_gen *g, const std::vector<float> &h, float **out) {
     float *d = nullptr;
     SVB_CUDA(cudaMalloc((void **)&d, std::max<size_t>(h.size(), 4) * sizeof(float)));
     SVB_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -109,7 +18,7 @@ int upload(svb_gen *g, const std::vector<float> &h, float **out) {
     return SVB_OK;
 }
 
-int get_w(svb_gen *g, const std::string &name, std::vector<int64_t> want, const HostTensor **out) {
+int svb::gen_get_w(svb_gen *g, const std::string &name, std::vector<int64_t> want, const HostTensor **out) {
     auto it = g->host_w.find(name);
     SVB_CHECK(it != g->host_w.end(), SVB_ERR_MISSING, "weight '%s' was never set", name.c_str());
     if (!want.empty()) {
@@ -128,30 +37,32 @@ int get_w(svb_gen *g, const std::string &name, std::vector<int64_t> want, const 
     return SVB_OK;
 }
 
+namespace {
+
 int pack_conv(svb_gen *g, const std::string &prefix, int Cin, int Cout, int K, int dil, ConvLayer *L) {
     const HostTensor *w, *b;
-    SVB_TRY(get_w(g, prefix + ".weight", {Cout, Cin, K}, &w));
-    SVB_TRY(get_w(g, prefix + ".bias", {Cout}, &b));
+    SVB_TRY(gen_get_w(g, prefix + ".weight", {Cout, Cin, K}, &w));
+    SVB_TRY(gen_get_w(g, prefix + ".bias", {Cout}, &b));
     const std::vector<float> p = pack_conv_weights(w->data.data(), Cout, Cin, K);
     L->Cin = Cin, L->Cout = Cout, L->CoutP = Cout, L->KS = K, L->dil = dil, L->ups_u = 0;
     L->macs_per_row = (double)Cin * Cout * K;
-    SVB_TRY(upload(g, p, &L->w));
-    SVB_TRY(upload(g, b->data, &L->b));
+    SVB_TRY(gen_upload(g, p, &L->w));
+    SVB_TRY(gen_upload(g, b->data, &L->b));
     SVB_TRY(tc_pack_weights(p.data(), K, Cin, Cout, &L->tc, &g->dev_allocs));
     return SVB_OK;
 }
 
 int pack_convT(svb_gen *g, const std::string &prefix, int Cin, int Cout, int K, int u, int pad, ConvLayer *L) {
     const HostTensor *w, *b;
-    SVB_TRY(get_w(g, prefix + ".weight", {Cin, Cout, K}, &w));
-    SVB_TRY(get_w(g, prefix + ".bias", {Cout}, &b));
+    SVB_TRY(gen_get_w(g, prefix + ".weight", {Cin, Cout, K}, &w));
+    SVB_TRY(gen_get_w(g, prefix + ".bias", {Cout}, &b));
     int KS = 0;
     const std::vector<float> p = pack_convT_weights(w->data.data(), Cin, Cout, K, u, pad, &KS);
     SVB_CHECK(KS <= 11, SVB_ERR_INVALID, "upsampler %s: kernel %d / stride %d needs %d taps", prefix.c_str(), K, u, KS);
     L->Cin = Cin, L->Cout = Cout, L->CoutP = u * Cout, L->KS = KS, L->dil = 1, L->ups_u = u;
     L->macs_per_row = (double)Cin * Cout * K;    // per input row: u outputs x K/u taps
-    SVB_TRY(upload(g, p, &L->w));
-    SVB_TRY(upload(g, b->data, &L->b));
+    SVB_TRY(gen_upload(g, p, &L->w));
+    SVB_TRY(gen_upload(g, b->data, &L->b));
     SVB_TRY(tc_pack_weights(p.data(), KS, Cin, u * Cout, &L->tc, &g->dev_allocs));
     return SVB_OK;
 }
@@ -163,12 +74,6 @@ struct Plan {
         total += (bytes + 255) / 256 * 256;
         return off;
     }
-};
-
-struct Buffers {
-    size_t mel, pre, har, nsf;
-    std::vector<size_t> X, S;
-    std::vector<std::vector<size_t>> A, R;      // per ResBlock chain
 };
 
 Buffers plan_workspace(const svb_gen *g, int B, int T, size_t *total) {
@@ -184,7 +89,19 @@ Buffers plan_workspace(const svb_gen *g, int B, int T, size_t *total) {
         const size_t n = c4t_floats(B, s.C, Ti) * 4;
         b.X.push_back(p.take(n)), b.S.push_back(p.take(n));
         b.A.emplace_back(), b.R.emplace_back();
-        for (int j = 0; j < g->cfg.n_resblock_kernels; ++j) b.A.back().push_back(p.take(n)), b.R.back().push_back(p.take(n));
+        for (int j = 0; j < g->cfg.n_resblock_kernels; ++j) {
+            // inference: one A / R buffer per chain, reused by every dilation; training: every conv input is kept (the tape)
+            std::vector<size_t> a(g->cfg.n_dilations), r(g->cfg.n_dilations);
+            for (int m = 0; m < g->cfg.n_dilations; ++m) {
+                a[m] = (m == 0 || g->training) ? p.take(n) : a[0];
+                r[m] = (m == 0 || g->training) ? p.take(n) : r[0];
+            }
+            b.A.back().push_back(a), b.R.back().push_back(r);
+        }
+    }
+    if (g->training) {
+        b.sines = p.take((size_t)B * T * g->hop * 9 * 4);
+        b.wav = p.take((size_t)B * T * g->hop * 4);
     }
     *total = p.total;
     return b;
@@ -236,6 +153,7 @@ int run_conv(svb_gen *g, const ConvLayer &L, const float *in, int in_Tp, float *
 int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float *f0, const float *rand_ini,
                  const float *noise, uint64_t seed, int B, int T, float *wav, cudaStream_t st) {
     SVB_CHECK(g && g->finalized, SVB_ERR_STATE, "generator: forward before finalize");
+    SVB_CHECK(!g->dirty, SVB_ERR_STATE, "generator: weights were set after finalize; call svb_gen_update_weights first");
     SVB_CHECK(mel && wav && B > 0 && T > 0, SVB_ERR_INVALID, "generator: null buffer or empty batch (B %d T %d)", B, T);
     SVB_CHECK(!f0 || g->cfg.use_pitch_embed, SVB_ERR_INVALID, "generator: f0 given but use_pitch_embed is off");
     SVB_CHECK((rand_ini == nullptr) == (noise == nullptr), SVB_ERR_INVALID,
@@ -249,10 +167,11 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         SVB_CUDA(cudaMalloc((void **)&g->ws, need));
         g->ws_cap = need, g->ws_B = 0;
     }
-    if (g->ws_B != B || g->ws_T != T) {   // new shape: the zero padding of every C4T buffer must be rebuilt
+    if (g->ws_B != B || g->ws_T != T || g->ws_training != g->training) {   // new layout: rebuild the zero padding of every buffer
         SVB_CUDA(cudaMemsetAsync(g->ws, 0, need, st));
-        g->ws_B = B, g->ws_T = T;
+        g->ws_B = B, g->ws_T = T, g->ws_training = g->training;
     }
+    g->bf = bf, g->last_T = T, g->last_nsf = f0 != nullptr;
     g->last_launches = 0, g->last_flops = 0, g->last_B = B;
     g->taps.clear();
     g->recs.clear(), g->ev_used = 0;
@@ -285,7 +204,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         {
             ProfScope ps(g, ns, "nsf source (4 kernels)", 4.0 * B * (T + (double)Tw * (noise ? 10 : 1)), 60.0 * B * Tw * 9);
             SVB_TRY(launch_nsf_source(f0, rand_ini, noise, seed, B, T, g->hop, (float)g->cfg.audio_sample_rate, g->lin_w,
-                                      g->lin_b, g->ws + bf.nsf, har, ns, &l));
+                                      g->lin_b, g->ws + bf.nsf, har, g->training ? F(bf.sines) : nullptr, ns, &l));
         }
         if (har_on_side) SVB_CUDA(cudaEventRecord(g->ev_chain[0], ns));
         g->last_launches += l;
@@ -334,20 +253,22 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
                 cap = std::max(8, (int)(sms * wj / wsum + 0.5));
             }
             if (par) SVB_CUDA(cudaStreamWaitEvent(cs, g->ev_fork, 0));
-            float *A = F(bf.A[i][j]), *R = F(bf.R[i][j]);
             for (int m = 0; m < nd; ++m) {
-                const float *xin = m == 0 ? X : R;
+                float *A = F(bf.A[i][j][m]);
+                const float *xin = m == 0 ? X : F(bf.R[i][j][m - 1]);
                 const bool last = m == nd - 1;
-                float *dst = last ? S : R;
+                float *dst = last ? S : F(bf.R[i][j][m]);
                 const float scale = last ? 1.f / nk : 1.f;
                 const int accum = (last && j > 0) ? 1 : 0;
                 if (g->cfg.resblock == 1) {         // ResBlock1.forward :54-61
                     SVB_TRY(run_conv(g, s.c1[j][m], xin, Tip, A, Tip, nullptr, B, Ti, 0.1f, 1.f, 0, cs, cap));
                     if (par && last && j > 0) SVB_CUDA(cudaStreamWaitEvent(cs, g->ev_chain[j - 1], 0));
                     SVB_TRY(run_conv(g, s.c2[j][m], A, Tip, dst, Tip, xin, B, Ti, 0.1f, scale, accum, cs, cap));
-                } else {                            // ResBlock2.forward :81-86
+                } else {                            // ResBlock2.forward :81-86 (never in place: ping-pong A / R)
+                    const float *xin2 = m == 0 ? X : (m % 2 ? F(bf.R[i][j][m - 1]) : F(bf.A[i][j][m - 1]));
+                    float *dst2 = last ? S : (m % 2 ? F(bf.A[i][j][m]) : F(bf.R[i][j][m]));
                     if (par && last && j > 0) SVB_CUDA(cudaStreamWaitEvent(cs, g->ev_chain[j - 1], 0));
-                    SVB_TRY(run_conv(g, s.c1[j][m], xin, Tip, dst, Tip, xin, B, Ti, 0.1f, scale, accum, cs, cap));
+                    SVB_TRY(run_conv(g, s.c1[j][m], xin2, Tip, dst2, Tip, xin2, B, Ti, 0.1f, scale, accum, cs, cap));
                 }
             }
             if (par) SVB_CUDA(cudaEventRecord(g->ev_chain[j], cs));
@@ -363,6 +284,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
     }
     g->last_launches += 1;
     g->last_flops += 2.0 * B * (double)Tin * g->post_C * g->post_K;
+    if (g->training) SVB_CUDA(cudaMemcpyAsync(F(bf.wav), wav, (size_t)B * Tw * 4, cudaMemcpyDeviceToDevice, st));
     if (g->timing) SVB_CUDA(cudaEventRecord(g->ev1, st));
     return SVB_OK;
 }
@@ -419,6 +341,8 @@ extern "C" void svb_gen_destroy(svb_gen_t *g) {
     cudaSetDevice(g->device);
     for (void *p : g->dev_allocs) cudaFree(p);
     if (g->ws) cudaFree(g->ws);
+    if (g->bws) cudaFree(g->bws);
+    if (g->grad_flat) cudaFree(g->grad_flat);
     if (g->pin_in) cudaFreeHost(g->pin_in);
     if (g->pin_out) cudaFreeHost(g->pin_out);
     if (g->dev_in) cudaFree(g->dev_in);
@@ -436,7 +360,8 @@ extern "C" void svb_gen_destroy(svb_gen_t *g) {
 
 extern "C" int svb_gen_set_weight(svb_gen_t *g, const char *name, const float *data, const int64_t *shape, int32_t ndim) {
     SVB_CHECK(g && name && data && shape && ndim >= 1 && ndim <= 4, SVB_ERR_INVALID, "set_weight: bad argument");
-    SVB_CHECK(!g->finalized, SVB_ERR_STATE, "set_weight('%s') after finalize", name);
+    SVB_CHECK(!g->finalized || g->training, SVB_ERR_STATE, "set_weight('%s') after finalize (only a training handle takes new weights)", name);
+    if (g->finalized) g->dirty = true;
     HostTensor t;
     size_t n = 1;
     for (int i = 0; i < ndim; ++i) {
@@ -449,10 +374,13 @@ extern "C" int svb_gen_set_weight(svb_gen_t *g, const char *name, const float *d
     return SVB_OK;
 }
 
-extern "C" int svb_gen_finalize(svb_gen_t *g) {
-    SVB_CHECK(g, SVB_ERR_INVALID, "finalize: null handle");
-    SVB_CHECK(!g->finalized, SVB_ERR_STATE, "finalize called twice");
+// (re)build every device packing from the host copies of the weights
+int svb::gen_build_layers(svb_gen *g) {
     SVB_CUDA(cudaSetDevice(g->device));
+    for (void *p : g->dev_allocs) cudaFree(p);
+    g->dev_allocs.clear();
+    g->stages.clear();
+    g->conv_pre = ConvLayer();
     const svb_gen_config &c = g->cfg;
     const int C0 = c.upsample_initial_channel;
     SVB_TRY(pack_conv(g, "conv_pre", c.n_mel, C0, 7, 1, &g->conv_pre));          // hifigan.py:118
@@ -471,13 +399,13 @@ extern "C" int svb_gen_finalize(svb_gen_t *g) {
             s.noise.C = s.C, s.noise.K = last ? 1 : 2 * stride, s.noise.stride = last ? 1 : stride;
             s.noise.pad = last ? 0 : stride / 2;
             const HostTensor *w, *b;
-            SVB_TRY(get_w(g, "noise_convs." + std::to_string(i) + ".weight", {s.C, 1, s.noise.K}, &w));
-            SVB_TRY(get_w(g, "noise_convs." + std::to_string(i) + ".bias", {s.C}, &b));
+            SVB_TRY(gen_get_w(g, "noise_convs." + std::to_string(i) + ".weight", {s.C, 1, s.noise.K}, &w));
+            SVB_TRY(gen_get_w(g, "noise_convs." + std::to_string(i) + ".bias", {s.C}, &b));
             std::vector<float> wt((size_t)s.noise.K * s.C);                       // [C][1][K] -> [K][C]
             for (int ch = 0; ch < s.C; ++ch)
                 for (int j = 0; j < s.noise.K; ++j) wt[(size_t)j * s.C + ch] = w->data[(size_t)ch * s.noise.K + j];
-            SVB_TRY(upload(g, wt, &s.noise.w));
-            SVB_TRY(upload(g, b->data, &s.noise.b));
+            SVB_TRY(gen_upload(g, wt, &s.noise.w));
+            SVB_TRY(gen_upload(g, b->data, &s.noise.b));
         }
         s.c1.resize(c.n_resblock_kernels), s.c2.resize(c.n_resblock_kernels);
         for (int j = 0; j < c.n_resblock_kernels; ++j) {
@@ -498,24 +426,30 @@ extern "C" int svb_gen_finalize(svb_gen_t *g) {
     }
     {   // conv_post: Conv1d(ch, 1, 7, padding 3)   :140
         const HostTensor *w, *b;
-        SVB_TRY(get_w(g, "conv_post.weight", {1, cin, 7}, &w));
-        SVB_TRY(get_w(g, "conv_post.bias", {1}, &b));
+        SVB_TRY(gen_get_w(g, "conv_post.weight", {1, cin, 7}, &w));
+        SVB_TRY(gen_get_w(g, "conv_post.bias", {1}, &b));
         std::vector<float> p((size_t)cin * 7);
         for (int cq = 0; cq < cin / 4; ++cq)
             for (int k = 0; k < 7; ++k)
                 for (int e = 0; e < 4; ++e) p[((size_t)cq * 7 + k) * 4 + e] = w->data[(size_t)(cq * 4 + e) * 7 + k];
-        SVB_TRY(upload(g, p, &g->post_wq));
+        SVB_TRY(gen_upload(g, p, &g->post_wq));
         g->post_bias = b->data[0], g->post_K = 7, g->post_C = cin;
     }
     if (c.use_pitch_embed) {   // m_source.l_linear: Linear(9, 1)   source.py:378
         const HostTensor *w, *b;
-        SVB_TRY(get_w(g, "m_source.l_linear.weight", {1, 9}, &w));
-        SVB_TRY(get_w(g, "m_source.l_linear.bias", {1}, &b));
-        SVB_TRY(upload(g, w->data, &g->lin_w));
+        SVB_TRY(gen_get_w(g, "m_source.l_linear.weight", {1, 9}, &w));
+        SVB_TRY(gen_get_w(g, "m_source.l_linear.bias", {1}, &b));
+        SVB_TRY(gen_upload(g, w->data, &g->lin_w));
         g->lin_b = b->data[0];
     }
-    g->host_w.clear();
-    g->finalized = true;
+    return SVB_OK;
+}
+
+extern "C" int svb_gen_finalize(svb_gen_t *g) {
+    SVB_CHECK(g, SVB_ERR_INVALID, "finalize: null handle");
+    SVB_CHECK(!g->finalized, SVB_ERR_STATE, "finalize called twice");
+    SVB_TRY(gen_build_layers(g));
+    g->finalized = true;        // host copies are kept: training re-packs from them after every optimizer step
     return SVB_OK;
 }
 

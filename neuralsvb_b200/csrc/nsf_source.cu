@@ -146,7 +146,7 @@ __global__ void nsf_chunk_scan_kernel(NsfDims d, double *__restrict__ csum) {
 __global__ void nsf_synth_kernel(NsfDims d, const float *__restrict__ f0, const float *__restrict__ rand_ini,
                                  const float *__restrict__ noise, uint64_t seed, const double *__restrict__ base1,
                                  const double *__restrict__ cbase, const float *__restrict__ lin_w, float lin_b,
-                                 float *__restrict__ har) {
+                                 float *__restrict__ har, float *__restrict__ sines) {
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= (long long)d.B * d.nchunk) return;
@@ -190,6 +190,7 @@ __global__ void nsf_synth_kernel(NsfDims d, const float *__restrict__ f0, const 
         const float sine = sinf(s2 * 2.0f * 3.14159274101257324f) * 0.1f;     // (:72-73,121)
         const float x = sine * uv + noise_amp * nz[k];                         // (:132-136)
         merged = fmaf(__ldg(lin_w + k), x, merged);                            // l_linear (:393)
+        if (sines && valid) sines[((size_t)b * d.T + t) * kH + k] = x;         // kept for the l_linear gradient (training)
     }
     if (valid) har[(size_t)b * d.T + t] = tanhf(merged);                       // l_tanh (:394)
 }
@@ -200,8 +201,8 @@ size_t nsf_workspace_bytes(int B, int F, int U) {
 }
 
 int launch_nsf_source(const float *f0, const float *rand_ini, const float *noise, uint64_t seed, int B, int F, int U,
-                      float sr, const float *lin_w_dev, float lin_b, void *workspace, float *har, cudaStream_t st,
-                      int *launches) {
+                      float sr, const float *lin_w_dev, float lin_b, void *workspace, float *har, float *sines,
+                      cudaStream_t st, int *launches) {
     NsfDims d;
     d.B = B, d.F = F, d.U = U, d.T = F * U, d.nchunk = (d.T + 31) / 32, d.sr = sr;
     double *base1 = reinterpret_cast<double *>(workspace);
@@ -222,7 +223,7 @@ int launch_nsf_source(const float *f0, const float *rand_ini, const float *noise
     {
         const long long threads = (long long)B * d.nchunk * 32;
         nsf_synth_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(d, f0, rand_ini, noise, seed, base1, csum,
-                                                                               lin_w_dev, lin_b, har);
+                                                                               lin_w_dev, lin_b, har, sines);
     }
     SVB_CUDA(cudaGetLastError());
     if (launches) *launches += 4;

@@ -68,6 +68,23 @@ class _PlainConv(nn.Module):
         self.bias = nn.Parameter(torch.empty(n_bias).uniform_(-bound, bound))
 
 
+class _GenTrainFn(torch.autograd.Function):
+    """Autograd node of one training forward of the native generator (replaces torch autograd through
+    hifigan.py:144-169).  Inputs after ``seed`` are the parameters, in ``_param_entries`` order."""
+
+    @staticmethod
+    def forward(ctx, gen, x, f0, rand_ini, noise, seed, *params):
+        ctx.gen = gen
+        ctx.n_params = len(params)
+        return gen._run_forward(x, f0, rand_ini, noise, seed, train=True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        grads = ctx.gen._native_backward(dy)
+        assert len(grads) == ctx.n_params
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
 class ResBlock1(nn.Module):
     """Parameter container for hifigan.py:30-67."""
 
@@ -138,6 +155,7 @@ class HifiGanGenerator(nn.Module):
         self.conv_post = _WNConv((c_out, ch, 7), c_out)
         self._handle = None
         self._handle_key = None
+        self._synced_version = None
         self.seed = 0
 
     # ------------------------------------------------------------------ reference API
@@ -159,12 +177,27 @@ class HifiGanGenerator(nn.Module):
     def forward(self, x, f0=None, rand_ini=None, noise=None, seed=None):
         """x [B, n_mel, T] fp32 on a CUDA device, f0 [B, T] Hz or None -> [B, 1, T*hop].
         ``rand_ini`` [B,9] / ``noise`` [B,T*hop,9] inject the NSF source's random draws
-        (parity testing); otherwise they are drawn in-kernel from ``seed``."""
+        (parity testing); otherwise they are drawn in-kernel from ``seed``.
+
+        In ``train()`` mode with grad enabled the result carries a grad_fn: ``backward`` runs
+        ``svb_gen_backward`` (native data / weight gradients) and hands every parameter its gradient
+        (weight-norm ``weight_g`` / ``weight_v`` through ``svb_weight_norm_backward``)."""
         if not x.is_cuda:
             raise RuntimeError('HifiGanGenerator.forward needs CUDA tensors: there is no CPU fallback '
                                '(the reference CPU path lives in the oracle, for tests only)')
+        train = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if seed is None:
+            self.seed += 1
+            seed = self.seed
+        if train:
+            entries = self._param_entries()
+            return _GenTrainFn.apply(self, x, f0, rand_ini, noise, seed, *[p for e in entries for p in e[2]])
+        return self._run_forward(x, f0, rand_ini, noise, seed, train=False)
+
+    def _run_forward(self, x, f0, rand_ini, noise, seed, train):
         lib = _native.lib()
         g = self._ensure_handle(x.device)
+        g = self._sync_weights(g, train)
         B, C, T = x.shape
         if C != self.n_mel:
             raise ValueError(f'expected {self.n_mel} mel bins, got {C}')
@@ -172,9 +205,6 @@ class HifiGanGenerator(nn.Module):
         f0 = None if f0 is None else f0.contiguous().float().to(x.device)
         hop = int(lib.svb_gen_hop(g))
         y = torch.empty(B, 1, T * hop, device=x.device, dtype=torch.float32)
-        if seed is None:
-            self.seed += 1
-            seed = self.seed
         ri = None if rand_ini is None else rand_ini.contiguous().float().to(x.device)
         nz = None if noise is None else noise.contiguous().float().to(x.device)
         with torch.cuda.device(x.device):
@@ -182,6 +212,80 @@ class HifiGanGenerator(nn.Module):
             _native.check(lib.svb_gen_forward(g, _native.ptr(x), _native.ptr(f0), _native.ptr(ri), _native.ptr(nz),
                                               ctypes.c_uint64(seed), B, T, _native.ptr(y), st), 'gen_forward')
         return y
+
+    # ------------------------------------------------------------------ training
+    def _param_entries(self):
+        """[(reference prefix, module, [parameters in the order backward returns their gradients])]"""
+        out = []
+
+        def put(prefix, m):
+            ps = [m.bias, m.weight] if (isinstance(m, _PlainConv) or m.folded) else [m.bias, m.weight_g, m.weight_v]
+            out.append((prefix, m, ps))
+        put('conv_pre', self.conv_pre)
+        put('conv_post', self.conv_post)
+        for i, l in enumerate(self.ups):
+            put(f'ups.{i}', l)
+        for n, rb in enumerate(self.resblocks):
+            for attr in (('convs1', 'convs2') if isinstance(rb, ResBlock1) else ('convs',)):
+                for m, l in enumerate(getattr(rb, attr)):
+                    put(f'resblocks.{n}.{attr}.{m}', l)
+        if self.h['use_pitch_embed']:
+            for i, l in enumerate(self.noise_convs):
+                put(f'noise_convs.{i}', l)
+            out.append(('m_source.l_linear', self.m_source.l_linear, [self.m_source.l_linear.bias, self.m_source.l_linear.weight]))
+        return out
+
+    def _sync_weights(self, g, train):
+        """Keep the native packings in step with the parameters (they change after every optimizer step)."""
+        lib = _native.lib()
+        _native.check(lib.svb_gen_set_training(g, 1 if train else 0), 'set_training')
+        ver = tuple(p._version for p in self.parameters())
+        if ver == self._synced_version:
+            return g
+        if not train:                                   # inference handle: rebuild from scratch
+            dev = torch.device('cuda', self._handle_key)
+            self._drop_handle()
+            return self._ensure_handle(dev)
+        for name, t in self.folded_state().items():
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            _native.check(lib.svb_gen_set_weight(g, name.encode(), _native.ptr(t), shape, t.dim()), f'set_weight({name})')
+        _native.check(lib.svb_gen_update_weights(g), 'update_weights')
+        self._synced_version = ver
+        return g
+
+    def _native_backward(self, dy):
+        """d(loss)/d(wav) [B,1,T*hop] -> flat list of parameter gradients in ``_param_entries`` order."""
+        lib = _native.lib()
+        g = self._handle
+        dev = dy.device
+        dy = dy.contiguous().float()
+        grads = []
+        with torch.cuda.device(dev):
+            st = _native.current_stream_ptr(dev)
+            _native.check(lib.svb_gen_zero_grad(g, st), 'zero_grad')
+            _native.check(lib.svb_gen_backward(g, _native.ptr(dy), st), 'gen_backward')
+
+            def fetch(name, like):
+                n = int(lib.svb_gen_grad_numel(g, name.encode()))
+                if n != like.numel():
+                    raise RuntimeError(f'gradient {name}: native {n} elements, parameter {like.numel()}')
+                t = torch.empty(like.shape, device=dev, dtype=torch.float32)
+                _native.check(lib.svb_gen_get_grad(g, name.encode(), _native.ptr(t), n, st), f'get_grad({name})')
+                return t
+            for prefix, m, ps in self._param_entries():
+                db = fetch(prefix + '.bias', ps[0])
+                if len(ps) == 2:
+                    grads += [db, fetch(prefix + '.weight', ps[1])]
+                    continue
+                v = m.weight_v.detach().float().contiguous()
+                gv = m.weight_g.detach().float().contiguous()
+                dw = fetch(prefix + '.weight', v)
+                dv, dg = torch.empty_like(v), torch.empty_like(gv)
+                _native.check(lib.svb_weight_norm_backward(_native.ptr(v), _native.ptr(gv), _native.ptr(dw), v.shape[0],
+                                                           v[0].numel(), _native.ptr(dv), _native.ptr(dg), st),
+                              'weight_norm_backward')
+                grads += [db, dg, dv]
+        return grads
 
     # ------------------------------------------------------------------ native handle
     def folded_state(self):
@@ -264,6 +368,7 @@ class HifiGanGenerator(nn.Module):
             lib.svb_gen_destroy(hnd)
             raise
         self._handle, self._handle_key = hnd, key
+        self._synced_version = tuple(p._version for p in self.parameters())
         return hnd
 
     def native_handle(self, device=None):

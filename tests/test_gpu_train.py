@@ -1,0 +1,111 @@
+"""-m gpu: the native generator backward (svb_gen_backward through HifiGanGenerator's autograd node) against
+torch autograd through the CPU oracle (the reference's forward, oracle/hifigan.py) on the same weights, inputs and
+cotangent.  Gradients are compared per parameter tensor (weight-norm g / v, biases, noise convs, l_linear) in
+relative L2; the reference has no training fixtures for the vocoder, so the oracle is the checker."""
+import numpy as np
+import pytest
+import torch
+
+from neuralsvb_b200.modules.hifigan.hifigan import HifiGanGenerator
+from neuralsvb_b200.utils import synthetic as S
+from oracle import hifigan as O
+from tests import gpu_util as U
+
+pytestmark = pytest.mark.gpu
+
+# fp32 mode (every kernel on CUDA cores) pins the backward LOGIC: relative L2 per parameter tensor.
+# bf16x3 mode (data gradients on split-bf16 tensor cores) moves the forward by ~1e-6..1e-5, which flips the
+# leaky-relu mask of a handful of near-zero pre-activations; on these tiny test tensors one flip is a ~1e-2 change
+# of that tensor's gradient (the CPU oracle shows the same jump when its own input is perturbed by 1e-4:
+# 8e-6 -> 6.6e-3, not linear).  So bf16x3 is held to: the global gradient, most tensors tight, every tensor loose.
+REL_TOL = {'fp32': 2e-4}
+BF_GLOBAL_TOL, BF_MEDIAN_TOL, BF_TENSOR_TOL = 3e-3, 2e-4, 8e-2
+
+
+def _cfg(name, nsf):
+    if name == 'small_rb2':
+        h = S.small_config(nsf)
+        h['resblock'] = '2'
+        h['resblock_dilation_sizes'] = [[1, 3], [1, 3], [1, 3]]
+        return h
+    return U.config(name, nsf)
+
+
+def _oracle_grads(h, sd, mel, f0, ri, nz, cot):
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    w = O.fold_weight_norm(p)
+    y = O.generator_forward(w, h, mel, f0, ri, nz)
+    (y * cot).sum().backward()
+    return y.detach(), {k: v.grad for k, v in p.items()}
+
+
+@pytest.mark.parametrize('cfg,nsf,B,T,prec', [
+    ('small', True, 2, 24, 'fp32'),
+    ('small', True, 2, 24, 'bf16x3'),
+    ('small', False, 1, 37, 'bf16x3'),
+    ('small_rb2', True, 2, 24, 'bf16x3'),
+    ('hop256', True, 1, 12, 'bf16x3'),
+])
+def test_generator_backward_matches_oracle_autograd(cfg, nsf, B, T, prec):
+    h = _cfg(cfg, nsf)
+    hop = int(np.prod(h['upsample_rates']))
+    sd = S.make_generator_state_dict(h, U.SEED)
+    mel, f0 = S.make_mel_f0(B, T, U.SEED)
+    f0 = f0 if nsf else None
+    ri = nz = None
+    if nsf:
+        ri, nz = S.make_nsf_noise(B, T * hop, U.SEED)
+    cot = torch.randn(B, 1, T * hop, generator=torch.Generator().manual_seed(7))
+    y_ref, g_ref = _oracle_grads(h, sd, mel, f0, ri, nz, cot)
+
+    m = HifiGanGenerator(h, precision=prec)
+    m.load_state_dict(sd, strict=True)
+    m = m.to('cuda:0').train()
+    cu = lambda t: None if t is None else t.cuda()
+    y = m(cu(mel), cu(f0), rand_ini=cu(ri), noise=cu(nz))
+    assert y.requires_grad
+    assert U.rms(y.detach().cpu().numpy(), y_ref.numpy()) < 1e-4
+    (y * cot.cuda()).sum().backward()
+    names = dict(m.named_parameters())
+    assert set(names) == set(g_ref)
+    errs = {}
+    for k, p in names.items():
+        assert p.grad is not None, k
+        ref = g_ref[k].double()
+        errs[k] = float((p.grad.cpu().double() - ref).norm() / ref.norm().clamp_min(1e-30))
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    num = sum(float((names[k].grad.cpu().double() - g_ref[k].double()).pow(2).sum()) for k in names)
+    den = sum(float(g_ref[k].double().pow(2).sum()) for k in names)
+    glob, med = (num / den) ** 0.5, float(np.median(list(errs.values())))
+    print(f'{cfg} nsf={nsf} {prec}: global {glob:.1e} median {med:.1e} worst {[(k, f"{e:.1e}") for k, e in top]}')
+    if prec == 'fp32':
+        for k, e in errs.items():
+            assert e < REL_TOL[prec], (k, e)
+    else:
+        assert glob < BF_GLOBAL_TOL and med < BF_MEDIAN_TOL, (glob, med)
+        for k, e in errs.items():
+            assert e < BF_TENSOR_TOL, (k, e)
+
+
+def test_training_step_updates_native_weights():
+    """An SGD step changes the parameters; the next forward must see them (re-packed weights)."""
+    h = S.small_config(True)
+    sd = S.make_generator_state_dict(h, U.SEED)
+    mel, f0 = S.make_mel_f0(2, 24, U.SEED)
+    ri, nz = S.make_nsf_noise(2, 24 * 16, U.SEED)
+    m = HifiGanGenerator(h, precision='bf16x3')
+    m.load_state_dict(sd, strict=True)
+    m = m.to('cuda:0').train()
+    opt = torch.optim.SGD(m.parameters(), lr=1e-2)
+    y0 = m(mel.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda())
+    (y0 ** 2).mean().backward()
+    opt.step()
+    y1 = m(mel.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda()).detach()
+    p = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    y_ref = O.generator_forward(O.fold_weight_norm(p), h, mel, f0, ri, nz)
+    assert U.rms(y1.cpu().numpy(), y_ref.numpy()) < 1e-4
+    assert U.rms(y1.cpu().numpy(), y0.detach().cpu().numpy()) > 1e-6        # the step did change the output
+    m.eval()
+    with torch.no_grad():
+        y2 = m(mel.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda())
+    assert U.rms(y2.cpu().numpy(), y_ref.numpy()) < 1e-4
