@@ -148,6 +148,12 @@ int svb_gen_profile_get(svb_gen_t *g, int32_t i, char *name, int32_t name_cap, f
  *   svb_weight_norm_backward: (dv, dg) of w = g * v / ||v|| (norm over all dims but 0) from dw. */
 int svb_gen_set_training(svb_gen_t *g, int32_t on);
 int svb_gen_update_weights(svb_gen_t *g);
+/* Device-side variant (no host round trip): the folded tensor `name` is copied from a device buffer, then ALL
+ * kernel packings (forward, data-gradient twins, tcgen05 tiles) are rebuilt by gather / tile kernels on `stream`.
+ * svb_fold_weight_norm_dev: w = g * v / ||v|| on device buffers (hifigan.py:35-50 weight_norm, dim 0). */
+int svb_gen_set_weight_dev(svb_gen_t *g, const char *name, const float *src_dev, int64_t n, void *stream);
+int svb_gen_update_weights_dev(svb_gen_t *g, void *stream);
+int svb_fold_weight_norm_dev(const float *v_dev, const float *g_dev, int64_t d0, int64_t inner, float *w_dev, void *stream);
 int svb_gen_zero_grad(svb_gen_t *g, void *stream);
 int svb_gen_backward(svb_gen_t *g, const float *dwav_dev, void *stream);
 int64_t svb_gen_grad_numel(svb_gen_t *g, const char *name);

@@ -108,6 +108,9 @@ _PROTOS = {
     'svb_gen_set_training': (ctypes.c_int, [_P, _I32]),
     'svb_gen_update_weights': (ctypes.c_int, [_P]),
     'svb_gen_zero_grad': (ctypes.c_int, [_P, _P]),
+    'svb_gen_set_weight_dev': (ctypes.c_int, [_P, ctypes.c_char_p, _P, _I64, _P]),
+    'svb_gen_update_weights_dev': (ctypes.c_int, [_P, _P]),
+    'svb_fold_weight_norm_dev': (ctypes.c_int, [_P, _P, _I64, _I64, _P, _P]),
     'svb_gen_backward': (ctypes.c_int, [_P, _P, _P]),
     'svb_gen_grad_numel': (_I64, [_P, ctypes.c_char_p]),
     'svb_gen_get_grad': (ctypes.c_int, [_P, ctypes.c_char_p, _P, _I64, _P]),

@@ -69,3 +69,11 @@ extern "C" int svb_fold_weight_norm_host(const float *v_host, const float *g_hos
     }
     return SVB_OK;
 }
+
+extern "C" int svb_fold_weight_norm_dev(const float *v_dev, const float *g_dev, int64_t d0, int64_t inner, float *w_dev,
+                                        void *stream) {
+    SVB_CHECK(v_dev && g_dev && w_dev && d0 > 0 && inner > 0, SVB_ERR_INVALID, "fold_weight_norm_dev: bad argument");
+    weight_norm_fold_kernel<<<(unsigned)d0, 256, 0, as_stream(stream)>>>(v_dev, g_dev, inner, w_dev);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}

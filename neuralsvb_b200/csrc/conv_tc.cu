@@ -680,6 +680,52 @@ int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *
     return SVB_OK;
 }
 
+// device twin of the loops in tc_pack_weights: one thread per (tile, output column n, input channel ci)
+__global__ void tc_repack_kernel(const float *__restrict__ packed, int KS, int Cin, int CoutP, int n_tile, int n_chunks,
+                                 long long total, unsigned char *__restrict__ tf, unsigned char *__restrict__ tf3,
+                                 unsigned char *__restrict__ bf) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ci = (int)(i % kTcCK);
+    const int n = (int)((i / kTcCK) % n_tile);
+    const long long t = i / ((long long)kTcCK * n_tile);
+    const int k = (int)(t % KS);
+    const int c = (int)((t / KS) % n_chunks);
+    const int nb = (int)(t / ((long long)KS * n_chunks));
+    const int cin_i = c * kTcCK + ci;
+    const float w = cin_i < Cin ? packed[((size_t)k * Cin + cin_i) * CoutP + nb * n_tile + n] : 0.f;
+    auto tf32 = [](float x) {      // host_tf32: round half up in magnitude to 10 mantissa bits
+        uint32_t u = __float_as_uint(x);
+        if ((u & 0x7F800000u) == 0x7F800000u) return x;
+        u += 0x1000u;
+        u &= 0xFFFFE000u;
+        return __uint_as_float(u);
+    };
+    const size_t tile_b = (size_t)n_tile * 128;
+    const float h = tf32(w);
+    const size_t i4 = (size_t)n * 32 + (((ci >> 2) ^ (n & 7)) << 2) + (ci & 3);
+    reinterpret_cast<float *>(tf + t * tile_b)[i4] = h;
+    reinterpret_cast<float *>(tf3 + t * tile_b * 2)[i4] = h;
+    reinterpret_cast<float *>(tf3 + t * tile_b * 2 + tile_b)[i4] = tf32(w - h);
+    const __nv_bfloat16 bh = __float2bfloat16_rn(w);
+    const __nv_bfloat16 bl = __float2bfloat16_rn(w - __bfloat162float(bh));
+    uint16_t *tb = reinterpret_cast<uint16_t *>(bf + t * tile_b);
+    const int ch = ci >> 3, cl = 4 + (ci >> 3);
+    tb[(size_t)n * 64 + ((ch ^ (n & 7)) << 3) + (ci & 7)] = __bfloat16_as_ushort(bh);
+    tb[(size_t)n * 64 + ((cl ^ (n & 7)) << 3) + (ci & 7)] = __bfloat16_as_ushort(bl);
+}
+
+int tc_repack_weights_dev(const float *packed_dev, const TcWeights &w, cudaStream_t st) {
+    if (!w.ok) return SVB_OK;
+    const int n_chunks = (w.Cin + kTcCK - 1) / kTcCK, n_blk = w.CoutP / w.n_tile;
+    const long long total = (long long)n_blk * n_chunks * w.KS * w.n_tile * kTcCK;
+    tc_repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        packed_dev, w.KS, w.Cin, w.CoutP, w.n_tile, n_chunks, total, reinterpret_cast<unsigned char *>(w.blob[SVB_PREC_TF32]),
+        reinterpret_cast<unsigned char *>(w.blob[SVB_PREC_TF32X3]), reinterpret_cast<unsigned char *>(w.blob[SVB_PREC_BF16X3]));
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
 bool tc_supported(const TcWeights &w, const ConvArgs &a) {
     return w.ok && a.Cin % 4 == 0 && a.bias != nullptr && (a.KS - 1) / 2 * a.dil <= kPad &&
            (a.ups_u == 0 || a.Cout % 32 == 0) && a.Cout <= 1024;

@@ -15,6 +15,9 @@ struct TcWeights {
 
 // packed_ffma: [KS][Cin][CoutP] fp32 (the FFMA packing).  Allocations are appended to `allocs`.
 int tc_pack_weights(const float *packed_ffma, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs);
+// same packing on the device, from a device copy of the FFMA packing into the blobs tc_pack_weights allocated
+// (training: the weights change after every optimizer step)
+int tc_repack_weights_dev(const float *packed_ffma_dev, const TcWeights &w, cudaStream_t st);
 bool tc_supported(const TcWeights &w, const ConvArgs &a);
 // max_ctas > 0 caps the persistent grid (used to run independent ResBlock chains side by side on SM subsets)
 int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st, int max_ctas = 0);

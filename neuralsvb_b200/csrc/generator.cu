@@ -342,6 +342,8 @@ extern "C" void svb_gen_destroy(svb_gen_t *g) {
     for (void *p : g->dev_allocs) cudaFree(p);
     if (g->ws) cudaFree(g->ws);
     if (g->bws) cudaFree(g->bws);
+    for (void *p : g->job_allocs) cudaFree(p);
+    for (auto &kv : g->nat_dev) cudaFree(kv.second.p);
     if (g->grad_flat) cudaFree(g->grad_flat);
     if (g->pin_in) cudaFreeHost(g->pin_in);
     if (g->pin_out) cudaFreeHost(g->pin_out);

@@ -57,6 +57,15 @@ struct BwdStage {
     float *up_wt = nullptr;
 };
 
+// one device-side re-packing step: dst[i] = idx[i] ? nat[src][idx[i] - 1] : 0, then (optionally) the tcgen05 tiles
+struct PackJob {
+    std::string src;            // name of the folded tensor in the reference's layout
+    float *dst = nullptr;
+    int *idx = nullptr;         // nullptr: plain copy
+    size_t n = 0;
+    const TcWeights *tc = nullptr;
+};
+
 struct GradBuf {
     float *p = nullptr;
     size_t n = 0;
@@ -101,6 +110,10 @@ struct svb_gen {
     size_t bws_cap = 0;
     int bws_B = 0, bws_T = 0;
     int64_t bwd_launches = 0;
+    std::map<std::string, svb::GradBuf> nat_dev;    // device copies of the folded tensors (svb_gen_set_weight_dev)
+    std::vector<svb::PackJob> jobs;
+    std::vector<void *> job_allocs;
+    bool dev_dirty = false;
 
     // host staging (spec2wav_host)
     float *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;

@@ -35,7 +35,15 @@ int pack_dgrad(svb_gen *g, const HostTensor &w, int C, int K, int dil, ConvLayer
     return SVB_OK;
 }
 
+// SVB_BWD_SKIP bit mask (timing ablations only; results are wrong): 1 = no weight / bias gradients, 2 = no data-gradient convs
+int bwd_skip() {
+    static int v = -1;
+    if (v < 0) v = getenv("SVB_BWD_SKIP") ? atoi(getenv("SVB_BWD_SKIP")) : 0;
+    return v;
+}
+
 int run_dgrad(svb_gen *g, const ConvLayer &L, const float *in, float *out, int Tp, int B, int Tq, cudaStream_t st) {
+    if (bwd_skip() & 2) return SVB_OK;
     ConvArgs a;
     a.in = in, a.w = L.w, a.bias = L.b, a.res = nullptr, a.out = out;
     a.B = B, a.Cin = L.Cin, a.in_Tp = Tp, a.Cout = L.Cout, a.out_Tp = Tp, a.CoutP = L.CoutP, a.Tq = Tq;
@@ -43,6 +51,132 @@ int run_dgrad(svb_gen *g, const ConvLayer &L, const float *in, float *out, int T
     g->bwd_launches += 1;
     if (g->cfg.precision != SVB_PREC_FP32 && tc_supported(L.tc, a)) return launch_conv_tc(L.tc, a, g->cfg.precision, st);
     return launch_conv_ffma(a, st);
+}
+
+// ---- device-side re-packing after an optimizer step -----------------------------------------------------------
+// Every packed array is a permutation (with zeros) of one folded tensor, so the host packers are run ONCE on an
+// index tensor (values i + 1, exact in fp32 up to 2^24 elements) and the result is kept as a gather map.
+__global__ void gather_kernel(float *__restrict__ dst, const float *__restrict__ nat, const int *__restrict__ idx, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = idx ? (idx[i] ? nat[idx[i] - 1] : 0.f) : nat[i];
+}
+
+std::vector<float> iota1(size_t n) {
+    std::vector<float> v(n);
+    for (size_t i = 0; i < n; ++i) v[i] = (float)(i + 1);
+    return v;
+}
+
+int add_job(svb_gen *g, const std::string &src, float *dst, const std::vector<float> &coded, const TcWeights *tc) {
+    std::vector<int> idx(coded.size());
+    for (size_t i = 0; i < coded.size(); ++i) idx[i] = (int)coded[i];
+    int *d = nullptr;
+    SVB_CUDA(cudaMalloc((void **)&d, std::max<size_t>(idx.size(), 1) * sizeof(int)));
+    g->job_allocs.push_back(d);
+    SVB_CUDA(cudaMemcpy(d, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    PackJob j;
+    j.src = src, j.dst = dst, j.idx = d, j.n = idx.size(), j.tc = (tc && tc->ok) ? tc : nullptr;
+    g->jobs.push_back(j);
+    return SVB_OK;
+}
+
+int add_copy_job(svb_gen *g, const std::string &src, float *dst, size_t n) {
+    PackJob j;
+    j.src = src, j.dst = dst, j.idx = nullptr, j.n = n;
+    g->jobs.push_back(j);
+    return SVB_OK;
+}
+
+std::vector<float> flip_transpose(const std::vector<float> &w, int C, int K) {   // as pack_dgrad
+    std::vector<float> wd((size_t)C * C * K);
+    for (int co = 0; co < C; ++co)
+        for (int ci = 0; ci < C; ++ci)
+            for (int k = 0; k < K; ++k) wd[((size_t)ci * C + co) * K + (K - 1 - k)] = w[((size_t)co * C + ci) * K + k];
+    return wd;
+}
+
+int build_jobs(svb_gen *g) {
+    for (void *p : g->job_allocs) cudaFree(p);
+    g->job_allocs.clear(), g->jobs.clear();
+    const svb_gen_config &c = g->cfg;
+    const int C0 = c.upsample_initial_channel;
+    SVB_TRY(add_job(g, "conv_pre.weight", g->conv_pre.w, pack_conv_weights(iota1((size_t)C0 * c.n_mel * 7).data(), C0, c.n_mel, 7),
+                    &g->conv_pre.tc));
+    SVB_TRY(add_copy_job(g, "conv_pre.bias", g->conv_pre.b, C0));
+    for (int i = 0; i < c.n_ups; ++i) {
+        Stage &s = g->stages[i];
+        BwdStage &bs = g->bwd[i];
+        const int Cin = s.up.Cin, C = s.C, K = c.upsample_kernel_sizes[i], u = s.u;
+        const std::string up = "ups." + std::to_string(i);
+        int KS = 0;
+        SVB_TRY(add_job(g, up + ".weight", s.up.w, pack_convT_weights(iota1((size_t)Cin * C * K).data(), Cin, C, K, u, (K - u) / 2, &KS),
+                        &s.up.tc));
+        SVB_TRY(add_copy_job(g, up + ".bias", s.up.b, C));
+        {
+            std::vector<float> m((size_t)K * C * Cin);
+            for (int ci = 0; ci < Cin; ++ci)
+                for (int co = 0; co < C; ++co)
+                    for (int k = 0; k < K; ++k) m[((size_t)k * C + co) * Cin + ci] = (float)(((size_t)ci * C + co) * K + k + 1);
+            SVB_TRY(add_job(g, up + ".weight", bs.up_wt, m, nullptr));
+        }
+        if (c.use_pitch_embed) {
+            const std::string nc = "noise_convs." + std::to_string(i);
+            std::vector<float> m((size_t)s.noise.K * C);
+            for (int ch = 0; ch < C; ++ch)
+                for (int j = 0; j < s.noise.K; ++j) m[(size_t)j * C + ch] = (float)((size_t)ch * s.noise.K + j + 1);
+            SVB_TRY(add_job(g, nc + ".weight", s.noise.w, m, nullptr));
+            SVB_TRY(add_copy_job(g, nc + ".bias", s.noise.b, C));
+        }
+        for (int j = 0; j < c.n_resblock_kernels; ++j) {
+            const int rk = c.resblock_kernel_sizes[j];
+            const std::vector<float> id = iota1((size_t)C * C * rk);
+            const std::vector<float> fw = pack_conv_weights(id.data(), C, C, rk);
+            const std::vector<float> bw = pack_conv_weights(flip_transpose(id, C, rk).data(), C, C, rk);
+            const std::string base = "resblocks." + std::to_string(i * c.n_resblock_kernels + j);
+            for (int m = 0; m < c.n_dilations; ++m) {
+                if (c.resblock == 1) {
+                    const std::string n1 = base + ".convs1." + std::to_string(m), n2 = base + ".convs2." + std::to_string(m);
+                    SVB_TRY(add_job(g, n1 + ".weight", s.c1[j][m].w, fw, &s.c1[j][m].tc));
+                    SVB_TRY(add_copy_job(g, n1 + ".bias", s.c1[j][m].b, C));
+                    SVB_TRY(add_job(g, n2 + ".weight", s.c2[j][m].w, fw, &s.c2[j][m].tc));
+                    SVB_TRY(add_copy_job(g, n2 + ".bias", s.c2[j][m].b, C));
+                    SVB_TRY(add_job(g, n1 + ".weight", bs.d1[j][m].w, bw, &bs.d1[j][m].tc));
+                    SVB_TRY(add_job(g, n2 + ".weight", bs.d2[j][m].w, bw, &bs.d2[j][m].tc));
+                } else {
+                    const std::string n1 = base + ".convs." + std::to_string(m);
+                    SVB_TRY(add_job(g, n1 + ".weight", s.c1[j][m].w, fw, &s.c1[j][m].tc));
+                    SVB_TRY(add_copy_job(g, n1 + ".bias", s.c1[j][m].b, C));
+                    SVB_TRY(add_job(g, n1 + ".weight", bs.d1[j][m].w, bw, &bs.d1[j][m].tc));
+                }
+            }
+        }
+    }
+    {   // conv_post: [cq][k][4] for the forward kernel, natural [C][K] for the backward
+        const int C = g->post_C, K = g->post_K;
+        std::vector<float> m((size_t)C * K);
+        for (int cq = 0; cq < C / 4; ++cq)
+            for (int k = 0; k < K; ++k)
+                for (int e = 0; e < 4; ++e) m[((size_t)cq * K + k) * 4 + e] = (float)((size_t)(cq * 4 + e) * K + k + 1);
+        SVB_TRY(add_job(g, "conv_post.weight", g->post_wq, m, nullptr));
+        SVB_TRY(add_copy_job(g, "conv_post.weight", g->post_w_nat, (size_t)C * K));
+    }
+    if (c.use_pitch_embed) SVB_TRY(add_copy_job(g, "m_source.l_linear.weight", g->lin_w, 9));
+    return SVB_OK;
+}
+
+int nat_buffer(svb_gen *g, const std::string &name, GradBuf **out) {
+    auto it = g->nat_dev.find(name);
+    if (it == g->nat_dev.end()) {
+        auto hw = g->host_w.find(name);
+        SVB_CHECK(hw != g->host_w.end(), SVB_ERR_MISSING, "no tensor named '%s' in this generator", name.c_str());
+        GradBuf b;
+        b.n = hw->second.data.size();
+        SVB_CUDA(cudaMalloc((void **)&b.p, std::max<size_t>(b.n, 4) * 4));
+        SVB_CUDA(cudaMemcpy(b.p, hw->second.data.data(), b.n * 4, cudaMemcpyHostToDevice));
+        it = g->nat_dev.emplace(name, b).first;
+    }
+    *out = &it->second;
+    return SVB_OK;
 }
 
 float *grad_of(svb_gen *g, const std::string &name) {
@@ -110,6 +244,7 @@ extern "C" int svb_gen_set_training(svb_gen_t *g, int32_t on) {
     if (g->training) return SVB_OK;
     SVB_CHECK(!g->host_w.empty(), SVB_ERR_STATE, "set_training: host weights are gone");
     SVB_TRY(gen_build_bwd_layers(g));
+    SVB_TRY(build_jobs(g));
     if (!g->grad_flat) {        // one flat buffer, one view per folded tensor (the reference's names and layouts)
         size_t total = 0;
         for (auto &kv : g->host_w) total += (kv.second.data.size() + 63) / 64 * 64;
@@ -129,8 +264,53 @@ extern "C" int svb_gen_set_training(svb_gen_t *g, int32_t on) {
 extern "C" int svb_gen_update_weights(svb_gen_t *g) {
     SVB_CHECK(g && g->finalized, SVB_ERR_STATE, "update_weights: generator not finalized");
     SVB_TRY(gen_build_layers(g));
-    if (g->training) SVB_TRY(gen_build_bwd_layers(g));
-    g->dirty = false;
+    if (g->training) {
+        SVB_TRY(gen_build_bwd_layers(g));
+        SVB_TRY(build_jobs(g));
+    }
+    // the device copies of the folded tensors (if any) are stale now: drop them, they are re-created on demand
+    for (auto &kv : g->nat_dev) cudaFree(kv.second.p);
+    g->nat_dev.clear();
+    g->dirty = false, g->dev_dirty = false;
+    return SVB_OK;
+}
+
+extern "C" int svb_gen_set_weight_dev(svb_gen_t *g, const char *name, const float *src_dev, int64_t n, void *stream) {
+    SVB_CHECK(g && name && src_dev, SVB_ERR_INVALID, "set_weight_dev: null argument");
+    SVB_CHECK(g->finalized && g->training, SVB_ERR_STATE, "set_weight_dev('%s'): only a training handle takes new weights", name);
+    SVB_CUDA(cudaSetDevice(g->device));
+    GradBuf *b;
+    SVB_TRY(nat_buffer(g, name, &b));
+    SVB_CHECK((int64_t)b->n == n, SVB_ERR_INVALID, "set_weight_dev('%s'): tensor has %lld elements, caller passed %lld", name,
+              (long long)b->n, (long long)n);
+    SVB_CUDA(cudaMemcpyAsync(b->p, src_dev, (size_t)n * 4, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    g->dev_dirty = true;
+    return SVB_OK;
+}
+
+extern "C" int svb_gen_update_weights_dev(svb_gen_t *g, void *stream) {
+    SVB_CHECK(g && g->finalized && g->training, SVB_ERR_STATE, "update_weights_dev: not a training handle");
+    SVB_CHECK(!g->dirty, SVB_ERR_STATE, "update_weights_dev: host weights were set too; call svb_gen_update_weights");
+    SVB_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = as_stream(stream);
+    for (const PackJob &j : g->jobs) {
+        GradBuf *b;
+        SVB_TRY(nat_buffer(g, j.src, &b));
+        const int blocks = (int)std::min<size_t>((j.n + 255) / 256, 148 * 8);
+        gather_kernel<<<blocks, 256, 0, st>>>(j.dst, b->p, j.idx, j.n);
+        if (j.tc) SVB_TRY(tc_repack_weights_dev(j.dst, *j.tc, st));
+    }
+    SVB_CUDA(cudaGetLastError());
+    // the two scalars the kernels take by value
+    GradBuf *b;
+    SVB_TRY(nat_buffer(g, "conv_post.bias", &b));
+    SVB_CUDA(cudaMemcpyAsync(&g->post_bias, b->p, 4, cudaMemcpyDeviceToHost, st));
+    if (g->cfg.use_pitch_embed) {
+        SVB_TRY(nat_buffer(g, "m_source.l_linear.bias", &b));
+        SVB_CUDA(cudaMemcpyAsync(&g->lin_b, b->p, 4, cudaMemcpyDeviceToHost, st));
+    }
+    SVB_CUDA(cudaStreamSynchronize(st));
+    g->dev_dirty = false;
     return SVB_OK;
 }
 
@@ -199,6 +379,7 @@ extern "C" int svb_gen_backward(svb_gen_t *g, const float *dwav_dev, void *strea
     auto conv_wgrad = [&](const float *x, const float *gy, int C_in, int C_out, int Tp, int Tq, int K, int dil, float slope,
                           const std::string &prefix) -> int {
         float *dw, *db;
+        if (bwd_skip() & 1) return SVB_OK;
         SVB_TRY(need_grad(prefix + ".weight", &dw));
         SVB_TRY(need_grad(prefix + ".bias", &db));
         WgradArgs a;

@@ -246,10 +246,28 @@ class HifiGanGenerator(nn.Module):
             dev = torch.device('cuda', self._handle_key)
             self._drop_handle()
             return self._ensure_handle(dev)
-        for name, t in self.folded_state().items():
-            shape = (ctypes.c_int64 * t.dim())(*t.shape)
-            _native.check(lib.svb_gen_set_weight(g, name.encode(), _native.ptr(t), shape, t.dim()), f'set_weight({name})')
-        _native.check(lib.svb_gen_update_weights(g), 'update_weights')
+        # device-side: fold weight norm, hand every folded tensor over, rebuild all packings with gather / tile kernels
+        dev = torch.device('cuda', self._handle_key)
+        with torch.cuda.device(dev):
+            st = _native.current_stream_ptr(dev)
+
+            def put(name, t):
+                t = t.detach()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                _native.check(lib.svb_gen_set_weight_dev(g, name.encode(), _native.ptr(t), t.numel(), st), f'set_weight_dev({name})')
+            for prefix, m, ps in self._param_entries():
+                put(prefix + '.bias', ps[0])
+                if len(ps) == 2:
+                    put(prefix + '.weight', ps[1])
+                    continue
+                v, gv = m.weight_v.detach(), m.weight_g.detach()
+                if getattr(m, '_w_scratch', None) is None or m._w_scratch.shape != v.shape or m._w_scratch.device != v.device:
+                    m._w_scratch = torch.empty_like(v, dtype=torch.float32)
+                _native.check(lib.svb_fold_weight_norm_dev(_native.ptr(v), _native.ptr(gv), v.shape[0], v[0].numel(),
+                                                           _native.ptr(m._w_scratch), st), 'fold_weight_norm_dev')
+                put(prefix + '.weight', m._w_scratch)
+            _native.check(lib.svb_gen_update_weights_dev(g, st), 'update_weights_dev')
         self._synced_version = ver
         return g
 

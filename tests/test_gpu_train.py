@@ -14,12 +14,13 @@ from tests import gpu_util as U
 pytestmark = pytest.mark.gpu
 
 # fp32 mode (every kernel on CUDA cores) pins the backward LOGIC: relative L2 per parameter tensor.
-# bf16x3 mode (data gradients on split-bf16 tensor cores) moves the forward by ~1e-6..1e-5, which flips the
-# leaky-relu mask of a handful of near-zero pre-activations; on these tiny test tensors one flip is a ~1e-2 change
-# of that tensor's gradient (the CPU oracle shows the same jump when its own input is perturbed by 1e-4:
-# 8e-6 -> 6.6e-3, not linear).  So bf16x3 is held to: the global gradient, most tensors tight, every tensor loose.
+# The tensor-core modes move the forward by ~5e-6 relative, and the gradient of this leaky-relu network is NOT a
+# continuous function of that: a pre-activation that changes sign flips its mask.  The CPU oracle shows it on itself
+# -- perturbing its mel input by 1e-5 (forward moves 3e-6) moves its own gradients by 1.4e-3 (median over tensors)
+# and 1.5e-2 (worst).  So for those modes the oracle's self-sensitivity at a matched perturbation is measured in the
+# test and the CUDA gradients must stay within 3x of it (median, worst tensor and global).
 REL_TOL = {'fp32': 2e-4}
-BF_GLOBAL_TOL, BF_MEDIAN_TOL, BF_TENSOR_TOL = 3e-3, 2e-4, 8e-2
+SENS_EPS, SENS_FACTOR, SENS_FLOOR = 3e-5, 3.0, 2e-4
 
 
 def _cfg(name, nsf):
@@ -29,6 +30,13 @@ def _cfg(name, nsf):
         h['resblock_dilation_sizes'] = [[1, 3], [1, 3], [1, 3]]
         return h
     return U.config(name, nsf)
+
+
+def _stats(g, g_ref):
+    errs = {k: float((g[k].double() - g_ref[k].double()).norm() / g_ref[k].double().norm().clamp_min(1e-30)) for k in g_ref}
+    num = sum(float((g[k].double() - g_ref[k].double()).pow(2).sum()) for k in g_ref)
+    den = sum(float(g_ref[k].double().pow(2).sum()) for k in g_ref)
+    return errs, (num / den) ** 0.5, float(np.median(list(errs.values()))), max(errs.values())
 
 
 def _oracle_grads(h, sd, mel, f0, ri, nz, cot):
@@ -68,23 +76,21 @@ def test_generator_backward_matches_oracle_autograd(cfg, nsf, B, T, prec):
     (y * cot.cuda()).sum().backward()
     names = dict(m.named_parameters())
     assert set(names) == set(g_ref)
-    errs = {}
-    for k, p in names.items():
-        assert p.grad is not None, k
-        ref = g_ref[k].double()
-        errs[k] = float((p.grad.cpu().double() - ref).norm() / ref.norm().clamp_min(1e-30))
-    top = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
-    num = sum(float((names[k].grad.cpu().double() - g_ref[k].double()).pow(2).sum()) for k in names)
-    den = sum(float(g_ref[k].double().pow(2).sum()) for k in names)
-    glob, med = (num / den) ** 0.5, float(np.median(list(errs.values())))
+    errs, glob, med, worst = _stats({k: p.grad.cpu() for k, p in names.items()}, g_ref)
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
     print(f'{cfg} nsf={nsf} {prec}: global {glob:.1e} median {med:.1e} worst {[(k, f"{e:.1e}") for k, e in top]}')
     if prec == 'fp32':
         for k, e in errs.items():
             assert e < REL_TOL[prec], (k, e)
-    else:
-        assert glob < BF_GLOBAL_TOL and med < BF_MEDIAN_TOL, (glob, med)
-        for k, e in errs.items():
-            assert e < BF_TENSOR_TOL, (k, e)
+        return
+    ref = [0.0, 0.0, 0.0]
+    for s_ in range(3):
+        noise = torch.randn(mel.shape, generator=torch.Generator().manual_seed(100 + s_))
+        _, g_pert = _oracle_grads(h, sd, mel + SENS_EPS * noise, f0, ri, nz, cot)
+        ref = [max(a, b) for a, b in zip(ref, _stats(g_pert, g_ref)[1:])]
+    print(f'   oracle self-sensitivity at eps {SENS_EPS}: global {ref[0]:.1e} median {ref[1]:.1e} worst {ref[2]:.1e}')
+    for got, lim, what in zip((glob, med, worst), ref, ('global', 'median', 'worst')):
+        assert got < SENS_FACTOR * lim + SENS_FLOOR, (what, got, lim)
 
 
 def test_training_step_updates_native_weights():
