@@ -133,6 +133,25 @@ float svb_gen_last_ms(svb_gen_t *g);
 int32_t svb_gen_profile_count(svb_gen_t *g);
 int svb_gen_profile_get(svb_gen_t *g, int32_t i, char *name, int32_t name_cap, float *ms, double *bytes, double *flops);
 
+/* ---- training: backward of the discriminator-side operators ------------------------------------------------
+ * Replaces torch autograd through the Conv1d / Conv2d((k,1)) + leaky_relu stacks of DiscriminatorP / DiscriminatorS
+ * (modules/hifigan/hifigan.py:193-221, :262-286), AvgPool1d(4,2,1) (:304-306), the reflect pad (:209-212) and the
+ * element-wise loss gradients of feature_loss / discriminator_loss / generator_loss (:328-365) and of
+ * SpectralConvergengeLoss / LogSTFTMagnitudeLoss (modules/parallel_wavegan/losses/stft_loss.py:34-73).
+ *   svb_conv_nct_backward: tensors as svb_conv_nct_forward; y = the forward's post-activation output (mask source,
+ *     may be null when out_slope == 1), dy = gradient w.r.t. y.  dz_scratch [B,Cout,Tout,W] receives the masked
+ *     gradient; dx (written), dw / db (ACCUMULATED with atomics; the caller zeroes them) may each be null.
+ *   svb_loss_grad: da = (accumulate ? da : 0) + scale * f(a, b); kind 0 sign(a-b), 1 (a-1), 2 a, 3 (a-b),
+ *     4 sign(ln a - ln b) / a. */
+int svb_conv_nct_backward(const float *x_dev, const float *w_dev, const float *y_dev, const float *dy_dev, int32_t B,
+                          int32_t Cin, int32_t Cout, int32_t Tin, int32_t W, int32_t K, int32_t stride, int32_t dil,
+                          int32_t pad, int32_t groups, float out_slope, float *dz_scratch_dev, float *dx_dev,
+                          float *dw_dev, float *db_dev, void *stream);
+int svb_avgpool1d_4_2_1_backward(const float *dy_dev, float *dx_dev, int64_t rows, int32_t Tin, void *stream);
+int svb_pad_reflect_right_backward(const float *dy_dev, float *dx_dev, int64_t rows, int32_t T, int32_t Tpad, void *stream);
+int svb_loss_grad(const float *a_dev, const float *b_dev, int32_t kind, float scale, float *da_dev, int64_t n,
+                  int32_t accumulate, void *stream);
+
 /* ---- training: backward of the generator -------------------------------------------------------------
  * Replaces torch autograd through HifiGanGenerator.forward (modules/hifigan/hifigan.py:144-169; ResBlock1/2
  * :54-61 / :81-86; weight_norm :35-50,118,124; SourceModuleHnNSF.l_linear source.py:393-394) for the

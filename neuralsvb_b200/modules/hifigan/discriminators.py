@@ -3,8 +3,11 @@ operators of csrc/disc_ops.cu (reference: modules/hifigan/hifigan.py:181-365).
 
 Same constructors, ``forward(y, y_hat, mel=None) -> (y_d_rs, y_d_gs, fmap_rs, fmap_gs)`` and
 state_dict names (weight-norm ``weight_g/weight_v``; spectral-norm ``weight_orig/weight_u/weight_v``
-for MSD[0]) as the reference.  Forward only this round (no autograd): used for evaluation and as
-the parity-checked building block of the vocoder training step.
+for MSD[0]) as the reference.  With grad enabled every operator is a ``torch.autograd.Function`` whose
+backward is a CUDA kernel of csrc/disc_bwd.cu (conv data / weight / bias gradients with the leaky-relu mask,
+AvgPool1d, reflect pad, weight norm, loss gradients): torch only chains the nodes.  The one exception is the
+spectral-norm re-parametrisation of MSD[0] (power iteration and sigma on the [Cout, Cin*K] weight matrix --
+parameter-side arithmetic, a few small matrix-vector products in torch).
 ``use_cond=True`` (mel-conditioned discriminators, off in the shipped config) is not implemented.
 """
 import ctypes
@@ -25,7 +28,41 @@ def _cuda(t):
 
 
 def conv_nct(x, w, b, K, stride=1, dil=1, pad=0, groups=1, slope=1.0, W=1):
-    """x [B, Cin, T(, W)] -> [B, Cout, Tout(, W)] through svb_conv_nct_forward."""
+    """x [B, Cin, T(, W)] -> [B, Cout, Tout(, W)]: svb_conv_nct_forward, differentiable through svb_conv_nct_backward."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
+        return _ConvNctFn.apply(x, w, b, K, stride, dil, pad, groups, slope, W)
+    return _conv_nct_raw(x, w, b, K, stride, dil, pad, groups, slope, W)
+
+
+class _ConvNctFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, K, stride, dil, pad, groups, slope, W):
+        x, w, b = _cuda(x), _cuda(w), _cuda(b)
+        y = _conv_nct_raw(x, w, b, K, stride, dil, pad, groups, slope, W)
+        ctx.save_for_backward(x, w, y)
+        ctx.cfg = (K, stride, dil, pad, groups, slope, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        K, stride, dil, pad, groups, slope, W = ctx.cfg
+        lib = _native.lib()
+        dy = _cuda(dy)
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        dz = torch.empty_like(y)
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.zeros_like(w) if need_w else None
+        db = torch.zeros(w.shape[0], device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _native.check(lib.svb_conv_nct_backward(_native.ptr(x), _native.ptr(w), _native.ptr(y), _native.ptr(dy), x.shape[0],
+                                                    x.shape[1], w.shape[0], x.shape[2], W, K, stride, dil, pad, groups,
+                                                    ctypes.c_float(slope), _native.ptr(dz), _native.ptr(dx), _native.ptr(dw),
+                                                    _native.ptr(db), _native.current_stream_ptr(x.device)), 'conv_nct_backward')
+        return dx, dw, (db if need_b else None), None, None, None, None, None, None, None
+
+
+def _conv_nct_raw(x, w, b, K, stride=1, dil=1, pad=0, groups=1, slope=1.0, W=1):
     lib = _native.lib()
     x = _cuda(x)
     B, Cin, Tin = x.shape[0], x.shape[1], x.shape[2]
@@ -61,7 +98,15 @@ class _NormConv(nn.Module):
         self._cache = None
 
     def effective(self, device):
-        """[Cout, Cin/groups, K] effective weight + bias on `device` (cached until parameters change)."""
+        """[Cout, Cin/groups, K] effective weight + bias on `device` (cached until parameters change).  With grad
+        enabled the result is differentiable w.r.t. the parameters (weight norm: svb_weight_norm_backward)."""
+        wp = self.weight_orig if self.spectral else self.weight_v
+        if torch.is_grad_enabled() and (wp.requires_grad or self.bias.requires_grad):
+            if self.spectral:
+                eff = self._spectral_weight()
+            else:
+                eff = _WeightNormFn.apply(self.weight_v, self.weight_g)
+            return eff.reshape(eff.shape[0], eff.shape[1], -1), self.bias
         key = (str(device), self.bias._version, (self.weight_orig if self.spectral else self.weight_v)._version)
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1], self._cache[2]
@@ -86,6 +131,82 @@ class _NormConv(nn.Module):
         return eff, b
 
 
+    def _spectral_weight(self):
+        """torch.nn.utils.spectral_norm semantics (hifigan.py:261 norm_f): in training mode one power iteration updates
+        the u / v buffers in place, sigma = u . (W v) carries the gradient to weight_orig, u and v are constants."""
+        wm = self.weight_orig.flatten(1)
+        with torch.no_grad():
+            if self.training:
+                v = nn.functional.normalize(torch.mv(wm.t(), self.weight_u), dim=0, eps=1e-12)
+                u = nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+                self.weight_v.copy_(v), self.weight_u.copy_(u)
+            u, v = self.weight_u.clone(), self.weight_v.clone()
+        sigma = torch.dot(u, torch.mv(wm, v))
+        return self.weight_orig / sigma
+
+
+class _WeightNormFn(torch.autograd.Function):
+    """w = g * v / ||v|| (norm over all dims but 0) on the device; backward = svb_weight_norm_backward."""
+
+    @staticmethod
+    def forward(ctx, v, g):
+        lib = _native.lib()
+        v, g = _cuda(v), _cuda(g)
+        w = torch.empty_like(v)
+        with torch.cuda.device(v.device):
+            _native.check(lib.svb_fold_weight_norm_dev(_native.ptr(v), _native.ptr(g), v.shape[0], v[0].numel(), _native.ptr(w),
+                                                       _native.current_stream_ptr(v.device)), 'fold_weight_norm_dev')
+        ctx.save_for_backward(v, g)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g = ctx.saved_tensors
+        lib = _native.lib()
+        dw = _cuda(dw)
+        dv, dg = torch.empty_like(v), torch.empty_like(g)
+        with torch.cuda.device(v.device):
+            _native.check(lib.svb_weight_norm_backward(_native.ptr(v), _native.ptr(g), _native.ptr(dw), v.shape[0], v[0].numel(),
+                                                       _native.ptr(dv), _native.ptr(dg), _native.current_stream_ptr(v.device)),
+                          'weight_norm_backward')
+        return dv, dg
+
+
+class _RowOpFn(torch.autograd.Function):
+    """AvgPool1d(4,2,1) (kind 'pool') and the right reflect pad (kind 'pad') with their adjoint kernels."""
+
+    @staticmethod
+    def forward(ctx, x, kind, tpad):
+        lib = _native.lib()
+        x = _cuda(x)
+        b, c, t = x.shape
+        ctx.kind, ctx.shape, ctx.tpad = kind, (b, c, t), tpad
+        with torch.cuda.device(x.device):
+            st = _native.current_stream_ptr(x.device)
+            if kind == 'pool':
+                y = torch.empty(b, c, (t + 2 - 4) // 2 + 1, device=x.device)
+                _native.check(lib.svb_avgpool1d_4_2_1(_native.ptr(x), _native.ptr(y), b * c, t, st), 'avgpool')
+            else:
+                y = torch.empty(b, c, tpad, device=x.device)
+                _native.check(lib.svb_pad_reflect_right(_native.ptr(x), _native.ptr(y), b * c, t, tpad, st), 'pad_reflect_right')
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _native.lib()
+        dy = _cuda(dy)
+        b, c, t = ctx.shape
+        dx = torch.empty(b, c, t, device=dy.device)
+        with torch.cuda.device(dy.device):
+            st = _native.current_stream_ptr(dy.device)
+            if ctx.kind == 'pool':
+                _native.check(lib.svb_avgpool1d_4_2_1_backward(_native.ptr(dy), _native.ptr(dx), b * c, t, st), 'avgpool_backward')
+            else:
+                _native.check(lib.svb_pad_reflect_right_backward(_native.ptr(dy), _native.ptr(dx), b * c, t, ctx.tpad, st),
+                              'pad_reflect_backward')
+        return dx, None, None
+
+
 class DiscriminatorP(nn.Module):
     def __init__(self, period, kernel_size=5, stride=3, use_spectral_norm=False, use_cond=False, c_in=1):
         super().__init__()
@@ -103,11 +224,7 @@ class DiscriminatorP(nn.Module):
         p = self.period
         if t % p != 0:                                   # reflect pad to a multiple of the period (:209-212)
             tp = t + (p - t % p)
-            xp = torch.empty(b, c, tp, device=x.device)
-            with torch.cuda.device(x.device):
-                _native.check(lib.svb_pad_reflect_right(_native.ptr(x), _native.ptr(xp), b * c, t, tp,
-                                                        _native.current_stream_ptr(x.device)), 'pad_reflect_right')
-            x, t = xp, tp
+            x, t = _RowOpFn.apply(x, 'pad', tp), tp
         x = x.view(b, c, t // p, p)
         fmap = []
         for i, l in enumerate(self.convs):
@@ -156,14 +273,7 @@ class DiscriminatorS(nn.Module):
 
 
 def avg_pool_4_2_1(x):
-    lib = _native.lib()
-    x = _cuda(x)
-    b, c, t = x.shape
-    y = torch.empty(b, c, (t + 2 - 4) // 2 + 1, device=x.device)
-    with torch.cuda.device(x.device):
-        _native.check(lib.svb_avgpool1d_4_2_1(_native.ptr(x), _native.ptr(y), b * c, t, _native.current_stream_ptr(x.device)),
-                      'avgpool')
-    return y
+    return _RowOpFn.apply(x, 'pool', 0)
 
 
 class MultiScaleDiscriminator(nn.Module):
@@ -196,12 +306,57 @@ def pair_stats(a, b=None, want_log=False):
     return out.cpu()
 
 
+class _PairLossFn(torch.autograd.Function):
+    """One reduction of the GAN losses as a differentiable scalar (float64 sum on the device, svb_pair_stats;
+    gradient by svb_loss_grad).  kind: 'l1' mean |a - b|, 'one' mean (1 - a)^2, 'zero' mean a^2."""
+
+    @staticmethod
+    def forward(ctx, a, b, kind):
+        a = _cuda(a)
+        b = None if b is None else _cuda(b)
+        s = pair_stats(a, b)
+        ctx.kind = kind
+        ctx.save_for_backward(a, b) if b is not None else ctx.save_for_backward(a)
+        val = {'l1': s[3], 'one': s[4], 'zero': s[1]}[kind] / a.numel()
+        return torch.tensor(float(val), device=a.device, dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _native.lib()
+        saved = ctx.saved_tensors
+        a, b = saved[0], (saved[1] if len(saved) > 1 else None)
+        n = a.numel()
+        go = float(gout)
+        da = torch.empty_like(a)
+        db = None
+        with torch.cuda.device(a.device):
+            st = _native.current_stream_ptr(a.device)
+            if ctx.kind == 'l1':
+                _native.check(lib.svb_loss_grad(_native.ptr(a), _native.ptr(b), 0, ctypes.c_float(go / n), _native.ptr(da), n, 0, st),
+                              'loss_grad')
+                if ctx.needs_input_grad[1]:
+                    db = torch.empty_like(b)
+                    _native.check(lib.svb_loss_grad(_native.ptr(b), _native.ptr(a), 0, ctypes.c_float(go / n), _native.ptr(db), n, 0,
+                                                    st), 'loss_grad')
+            else:
+                _native.check(lib.svb_loss_grad(_native.ptr(a), None, 1 if ctx.kind == 'one' else 2, ctypes.c_float(2.0 * go / n),
+                                                _native.ptr(da), n, 0, st), 'loss_grad')
+        return (da if ctx.needs_input_grad[0] else None), db, None
+
+
+def _diff(*ts):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
 def feature_loss(fmap_r, fmap_g):
     """2 * sum over discriminators and layers of mean |r - g|  (hifigan.py:328-334)."""
     loss = 0.0
     for dr, dg in zip(fmap_r, fmap_g):
         for rl, gl in zip(dr, dg):
-            loss += float(pair_stats(rl, gl)[3]) / rl.numel()
+            if _diff(rl, gl):
+                loss = loss + _PairLossFn.apply(gl, rl, 'l1')
+            else:
+                loss += float(pair_stats(rl, gl)[3]) / rl.numel()
     return loss * 2
 
 
@@ -209,6 +364,10 @@ def discriminator_loss(disc_real_outputs, disc_generated_outputs):
     """(mean over discriminators of mean (1 - dr)^2, of mean dg^2)  (hifigan.py:337-347)."""
     r, g = 0.0, 0.0
     for dr, dg in zip(disc_real_outputs, disc_generated_outputs):
+        if _diff(dr, dg):
+            r = r + _PairLossFn.apply(dr, None, 'one')
+            g = g + _PairLossFn.apply(dg, None, 'zero')
+            continue
         s = pair_stats(dr, dg)
         r += float(s[4]) / dr.numel()
         g += float(s[5]) / dg.numel()
@@ -218,4 +377,6 @@ def discriminator_loss(disc_real_outputs, disc_generated_outputs):
 
 def generator_loss(disc_outputs):
     """mean over discriminators of mean (1 - dg)^2  (hifigan.py:359-365)."""
+    if _diff(*disc_outputs):
+        return sum(_PairLossFn.apply(dg, None, 'one') for dg in disc_outputs) / len(disc_outputs)
     return sum(float(pair_stats(dg)[4]) / dg.numel() for dg in disc_outputs) / len(disc_outputs)

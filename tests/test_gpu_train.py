@@ -115,3 +115,46 @@ def test_training_step_updates_native_weights():
     with torch.no_grad():
         y2 = m(mel.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda())
     assert U.rms(y2.cpu().numpy(), y_ref.numpy()) < 1e-4
+
+
+# ------------------------------------------------------------------ discriminators + GAN losses
+def _d_signals():
+    y = S.make_wave_batch(2, 8192, seed=U.SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=U.SEED + 5)[:, None]).clamp(-1, 1)
+    return y, y_hat
+
+
+@pytest.mark.parametrize('name', ['mpd', 'msd'])
+def test_discriminator_backward_matches_oracle_autograd(name):
+    """feature + generator + discriminator losses through MPD / MSD: gradients w.r.t. every discriminator parameter
+    (weight-norm g / v, spectral-norm weight_orig, biases) and w.r.t. the generated waveform."""
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    if name == 'mpd':
+        m, sd, fwd = D.MultiPeriodDiscriminator(), S.make_mpd_state_dict(U.SEED), O.mpd_forward
+    else:
+        m, sd, fwd = D.MultiScaleDiscriminator(), S.make_msd_state_dict(U.SEED), O.msd_forward
+    y, y_hat = _d_signals()
+    # oracle (eval-mode spectral norm: no power iteration)
+    is_buf = lambda k: k.endswith('weight_u') or (k.endswith('weight_v') and k[:-1] + 'orig' in sd)
+    p = {k: (v.clone() if is_buf(k) else v.clone().requires_grad_(True)) for k, v in sd.items()}
+    yh = y_hat.clone().requires_grad_(True)
+    rs, gs, fr, fg = fwd(y, yh, O.fold_discriminator_weights(p))
+    dr, dg = O.discriminator_loss(rs, gs)
+    (O.feature_loss(fr, fg) + O.generator_loss(gs) + dr + dg).backward()
+    g_ref = {k: v.grad for k, v in p.items() if not is_buf(k)}
+    g_ref['y_hat'] = yh.grad
+
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().cuda()                                   # eval: spectral norm without power iteration, as the oracle
+    yh2 = y_hat.cuda().requires_grad_(True)
+    rs, gs, fr, fg = m(y.cuda(), yh2)
+    dr, dg = D.discriminator_loss(rs, gs)
+    loss = D.feature_loss(fr, fg) + D.generator_loss(gs) + dr + dg
+    loss.backward()
+    got = {k: q.grad.cpu() for k, q in m.named_parameters()}
+    got['y_hat'] = yh2.grad.cpu()
+    assert set(got) == set(g_ref)
+    errs, glob, med, worst = _stats(got, g_ref)
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    print(f'{name}: global {glob:.1e} median {med:.1e} worst {[(k, f"{e:.1e}") for k, e in top]}')
+    assert glob < 3e-3 and med < 2e-4 and worst < 2e-2, (glob, med, worst)      # a flipped leaky-relu mask moves one small tensor by ~5e-3
