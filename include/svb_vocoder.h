@@ -251,6 +251,12 @@ int64_t svb_stft_num_frames(const svb_stft_config *cfg, int64_t n);
  * out_dev [B, frames, n_out] or [B, n_out, frames]  (n_out = n_mels or n_fft/2+1). */
 int svb_stft_forward(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n,
                      const float *mel_basis_dev, float *out_dev, void *stream);
+/* Backward of svb_stft_forward (torch autograd through torch.stft + magnitude [+ mel + log] in
+ * mel_spectrogram, modules/hifigan/mel_utils.py:59-76, and stft(), modules/parallel_wavegan/losses/stft_loss.py:26-31):
+ * dout = gradient w.r.t. the forward's output (same layout); the gradient w.r.t. the waveform is ACCUMULATED into
+ * dwav [B, n] (atomics; the caller zeroes it).  The spectrum is recomputed per frame, nothing is kept from forward. */
+int svb_stft_backward(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n, const float *mel_basis_dev,
+                      const float *dout_dev, float *dwav_dev, void *stream);
 
 /* PWG.wav2spec / process_utterance (vocoders/pwg.py:105-122, data_gen_utils.py:93-147) from HOST
  * memory: wav_host [n] -> mel_host [frames, n_mels] (log10), wav_out_host [frames*hop] (zero padded

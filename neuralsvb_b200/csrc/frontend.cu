@@ -33,21 +33,37 @@ __device__ __forceinline__ long long reflect_index(long long i, long long n) {
     return i;
 }
 
-__global__ void __launch_bounds__(256) stft_mel_kernel(StftArgs a) {
-    extern __shared__ float smem[];
-    float *re = smem;                 // [n_fft]
-    float *im = re + a.n_fft;         // [n_fft]
-    float *twc = im + a.n_fft;        // [n_fft/2] cos
-    float *tws = twc + a.n_fft / 2;   // [n_fft/2] -sin
-    float *mag = tws + a.n_fft / 2;   // [n_bins]
-    const int tid = threadIdx.x, N = a.n_fft;
-    const int frame = blockIdx.x, b = blockIdx.y;
-    const float *w = a.wav + (size_t)b * a.n;
+// radix-2 decimation-in-time on bit-reversed input, natural-order output; sign = +1: forward (e^{-i..}), -1: inverse
+__device__ __forceinline__ void fft_radix2(float *re, float *im, const float *twc, const float *tws, int N, int log2n,
+                                           float sign) {
+    const int tid = threadIdx.x;
+    for (int s = 1; s <= log2n; ++s) {
+        const int half = 1 << (s - 1);
+        const int tw_stride = N >> s;
+        for (int i = tid; i < N / 2; i += 256) {
+            const int grp = i / half, k = i - grp * half;
+            const int i0 = grp * 2 * half + k, i1 = i0 + half;
+            const float c = twc[k * tw_stride], sn = sign * tws[k * tw_stride];
+            const float xr = re[i1], xi = im[i1];
+            const float tr = xr * c - xi * sn, ti = xr * sn + xi * c;
+            const float ur = re[i0], ui = im[i0];
+            re[i0] = ur + tr, im[i0] = ui + ti;
+            re[i1] = ur - tr, im[i1] = ui - ti;
+        }
+        __syncthreads();
+    }
+}
 
-    // start of the frame in waveform coordinates
-    long long start;
-    if (a.pad_mode == SVB_PAD_HALF_REFLECT) start = (long long)frame * a.hop - (N - a.hop) / 2;
-    else start = (long long)frame * a.hop - N / 2;
+__device__ __forceinline__ long long frame_start(const StftArgs &a, int frame) {
+    if (a.pad_mode == SVB_PAD_HALF_REFLECT) return (long long)frame * a.hop - (a.n_fft - a.hop) / 2;
+    return (long long)frame * a.hop - a.n_fft / 2;
+}
+
+// windowed frame (bit-reversed) + twiddles into shared memory, then the forward FFT
+__device__ __forceinline__ void load_frame_fft(const StftArgs &a, float *re, float *im, float *twc, float *tws, int frame, int b) {
+    const int tid = threadIdx.x, N = a.n_fft;
+    const float *w = a.wav + (size_t)b * a.n;
+    const long long start = frame_start(a, frame);
     const int wl = (N - a.win) / 2;   // window is centred in the n_fft frame (librosa pad_center / torch.stft)
 
     for (int i = tid; i < N; i += 256) {
@@ -78,23 +94,19 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(StftArgs a) {
         tws[i] = -s;
     }
     __syncthreads();
+    fft_radix2(re, im, twc, tws, N, a.log2n, 1.f);
+}
 
-    // radix-2 decimation-in-time, natural-order output
-    for (int s = 1; s <= a.log2n; ++s) {
-        const int half = 1 << (s - 1);
-        const int tw_stride = N >> s;
-        for (int i = tid; i < N / 2; i += 256) {
-            const int grp = i / half, k = i - grp * half;
-            const int i0 = grp * 2 * half + k, i1 = i0 + half;
-            const float c = twc[k * tw_stride], sn = tws[k * tw_stride];
-            const float xr = re[i1], xi = im[i1];
-            const float tr = xr * c - xi * sn, ti = xr * sn + xi * c;
-            const float ur = re[i0], ui = im[i0];
-            re[i0] = ur + tr, im[i0] = ui + ti;
-            re[i1] = ur - tr, im[i1] = ui - ti;
-        }
-        __syncthreads();
-    }
+__global__ void __launch_bounds__(256) stft_mel_kernel(StftArgs a) {
+    extern __shared__ float smem[];
+    float *re = smem;                 // [n_fft]
+    float *im = re + a.n_fft;         // [n_fft]
+    float *twc = im + a.n_fft;        // [n_fft/2] cos
+    float *tws = twc + a.n_fft / 2;   // [n_fft/2] -sin
+    float *mag = tws + a.n_fft / 2;   // [n_bins]
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.x, b = blockIdx.y;
+    load_frame_fft(a, re, im, twc, tws, frame, b);
 
     const bool want_mel = a.out_kind == SVB_OUT_LOG10_MEL || a.out_kind == SVB_OUT_LN_MEL;
     for (int i = tid; i < a.n_bins; i += 256) {
@@ -128,6 +140,111 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(StftArgs a) {
                                             : ((size_t)b * a.n_mels + m) * a.frames + frame;
             a.out[o] = v;
         }
+    }
+}
+
+// Backward of stft_mel_kernel: one CTA per frame recomputes the frame's spectrum, pulls the output gradient back to
+// (d re, d im) of the one-sided bins, runs the inverse (adjoint) FFT  g_n = Re sum_k (d re_k + i d im_k) e^{+2 pi i k n / N}
+// and scatters window * g through the padding's adjoint into d wav (atomics: frames overlap).
+struct StftBwdArgs {
+    const float *dout;
+    float *dwav;
+};
+
+__global__ void __launch_bounds__(256) stft_mel_bwd_kernel(StftArgs a, StftBwdArgs g) {
+    extern __shared__ float smem[];
+    float *re = smem;
+    float *im = re + a.n_fft;
+    float *twc = im + a.n_fft;
+    float *tws = twc + a.n_fft / 2;
+    float *mag = tws + a.n_fft / 2;   // [n_bins]: magnitudes, then d magnitude
+    float *dmel = mag + a.n_bins;     // [n_mels]
+    const int tid = threadIdx.x, N = a.n_fft;
+    const int frame = blockIdx.x, b = blockIdx.y;
+    load_frame_fft(a, re, im, twc, tws, frame, b);
+
+    const bool want_mel = a.out_kind == SVB_OUT_LOG10_MEL || a.out_kind == SVB_OUT_LN_MEL;
+    constexpr int kMaxPer = 9;        // bins per thread for n_fft <= 4096
+    float zr[kMaxPer], zi[kMaxPer];
+    if (want_mel) {
+        for (int i = tid; i < a.n_bins; i += 256) {
+            const float p = re[i] * re[i] + im[i] * im[i];
+            mag[i] = a.out_kind == SVB_OUT_LN_MEL ? sqrtf(p + 1e-9f) : sqrtf(p);
+        }
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int m = warp; m < a.n_mels; m += 8) {
+            const float *row = a.mel_basis + (size_t)m * a.n_bins;
+            float acc = 0.f;
+            for (int i = lane; i < a.n_bins; i += 32) acc = fmaf(__ldg(row + i), mag[i], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                const size_t o = a.frames_major ? ((size_t)b * a.frames + frame) * a.n_mels + m
+                                                : ((size_t)b * a.n_mels + m) * a.frames + frame;
+                float d = acc >= a.eps ? __ldg(g.dout + o) / acc : 0.f;          // d log(max(mel, eps))
+                if (a.out_kind == SVB_OUT_LOG10_MEL) d *= 0.4342944819032518f;
+                dmel[m] = d;
+            }
+        }
+        __syncthreads();
+    }
+    {
+        int j = 0;
+        for (int i = tid; i < a.n_bins; i += 256, ++j) {
+            const float r = re[i], q = im[i];
+            const float p = r * r + q * q;
+            float dm, m;
+            if (want_mel) {
+                dm = 0.f;
+                for (int k = 0; k < a.n_mels; ++k) dm = fmaf(__ldg(a.mel_basis + (size_t)k * a.n_bins + i), dmel[k], dm);
+                m = mag[i];
+            } else {
+                const size_t o = a.frames_major ? ((size_t)b * a.frames + frame) * a.n_bins + i
+                                                : ((size_t)b * a.n_bins + i) * a.frames + frame;
+                dm = __ldg(g.dout + o);
+                if (a.out_kind == SVB_OUT_MAG) {
+                    m = sqrtf(fmaxf(p, a.eps));
+                    if (p < a.eps) dm = 0.f;                                     // clamp(min): no gradient below the floor
+                } else {
+                    m = sqrtf(p);
+                }
+            }
+            const float s = m > 0.f ? dm / m : 0.f;
+            zr[j] = s * r, zi[j] = s * q;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += 256) re[i] = 0.f, im[i] = 0.f;
+    __syncthreads();
+    {
+        int j = 0;
+        for (int i = tid; i < a.n_bins; i += 256, ++j) {
+            const int br = __brev((unsigned)i) >> (32 - a.log2n);
+            re[br] = zr[j], im[br] = zi[j];
+        }
+    }
+    __syncthreads();
+    fft_radix2(re, im, twc, tws, N, a.log2n, -1.f);
+
+    const long long start = frame_start(a, frame);
+    const int wl = (N - a.win) / 2;
+    const float *w = a.wav + (size_t)b * a.n;
+    float *dw = g.dwav + (size_t)b * a.n;
+    for (int i = tid; i < N; i += 256) {
+        const int wi = i - wl;
+        if (wi < 0 || wi >= a.win) continue;
+        long long s = start + i;
+        if (s < 0 || s >= a.n) {
+            if (a.pad_mode == SVB_PAD_CENTER_ZERO) continue;
+            s = reflect_index(s, a.n);
+        }
+        if (a.clamp_input) {
+            const float x = __ldg(w + s);
+            if (x < -1.f || x > 1.f) continue;
+        }
+        const float hann = 0.5f - 0.5f * cospif(2.0f * (float)wi / (float)a.win);
+        atomicAdd(dw + s, hann * re[i]);
     }
 }
 
@@ -226,4 +343,31 @@ extern "C" int64_t svb_wav2spec_host(const svb_stft_config *cfg, const float *wa
         for (int64_t i = 0; i < out_len; ++i) wav_out_host[i] = i < n ? wav_host[i] : 0.f;
     }
     return frames;
+}
+
+extern "C" int svb_stft_backward(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n,
+                                 const float *mel_basis_dev, const float *dout_dev, float *dwav_dev, void *stream) {
+    const bool want_mel = cfg && (cfg->out_kind == SVB_OUT_LOG10_MEL || cfg->out_kind == SVB_OUT_LN_MEL);
+    SVB_TRY(validate_stft(cfg, n, want_mel));
+    SVB_CHECK(wav_dev && dout_dev && dwav_dev && B > 0, SVB_ERR_INVALID, "stft_backward: null buffer or empty batch");
+    SVB_CHECK(!want_mel || mel_basis_dev, SVB_ERR_INVALID, "stft_backward: mel output needs mel_basis_dev");
+    StftArgs a;
+    a.wav = wav_dev, a.mel_basis = mel_basis_dev, a.out = nullptr, a.n = n;
+    a.n_fft = cfg->n_fft, a.log2n = ilog2(cfg->n_fft), a.hop = cfg->hop, a.win = cfg->win;
+    a.n_bins = cfg->n_fft / 2 + 1, a.n_mels = cfg->n_mels;
+    a.frames = (int)svb_stft_num_frames(cfg, n);
+    a.pad_mode = cfg->pad_mode, a.out_kind = cfg->out_kind, a.clamp_input = cfg->clamp_input;
+    a.frames_major = cfg->frames_major, a.eps = cfg->eps;
+    if (a.frames <= 0) return SVB_OK;
+    StftBwdArgs g;
+    g.dout = dout_dev, g.dwav = dwav_dev;
+    const size_t smem = (size_t)(3 * a.n_fft + a.n_bins + (want_mel ? a.n_mels : 0)) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        SVB_CUDA(cudaFuncSetAttribute(stft_mel_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    stft_mel_bwd_kernel<<<dim3(a.frames, B), 256, smem, as_stream(stream)>>>(a, g);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
 }

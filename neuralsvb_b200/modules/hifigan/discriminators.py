@@ -29,7 +29,7 @@ def _cuda(t):
 
 def conv_nct(x, w, b, K, stride=1, dil=1, pad=0, groups=1, slope=1.0, W=1):
     """x [B, Cin, T(, W)] -> [B, Cout, Tout(, W)]: svb_conv_nct_forward, differentiable through svb_conv_nct_backward."""
-    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
+    if torch.is_grad_enabled() and b is not None and (x.requires_grad or w.requires_grad or b.requires_grad):
         return _ConvNctFn.apply(x, w, b, K, stride, dil, pad, groups, slope, W)
     return _conv_nct_raw(x, w, b, K, stride, dil, pad, groups, slope, W)
 
@@ -346,6 +346,13 @@ class _PairLossFn(torch.autograd.Function):
 
 def _diff(*ts):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+def l1_loss(a, b):
+    """mean |a - b| (F.l1_loss, the mel-spectrogram reconstruction loss of the vocoder G step); differentiable w.r.t. a."""
+    if _diff(a, b):
+        return _PairLossFn.apply(a, b, 'l1')
+    return float(pair_stats(a, b)[3]) / a.numel()
 
 
 def feature_loss(fmap_r, fmap_g):

@@ -17,6 +17,37 @@ def _basis(hp, device):
     return _basis_cache[key]
 
 
+class StftFn(torch.autograd.Function):
+    """svb_stft_forward as an autograd node; backward = svb_stft_backward (the spectrum is recomputed per frame).
+    ``cfg`` = (n_fft, hop, win, pad_mode, out_kind, clamp_input, n_mels, frames_major, eps)."""
+
+    @staticmethod
+    def forward(ctx, y, cfg, basis, out_shape):
+        lib = _native.lib()
+        y = y.contiguous().float()
+        c = _native.StftConfig(*cfg)
+        out = torch.empty(out_shape, device=y.device, dtype=torch.float32)
+        with torch.cuda.device(y.device):
+            _native.check(lib.svb_stft_forward(ctypes.byref(c), _native.ptr(y), y.shape[0], y.shape[1], _native.ptr(basis),
+                                               _native.ptr(out), _native.current_stream_ptr(y.device)), 'stft_forward')
+        ctx.cfg, ctx.basis = cfg, basis
+        ctx.save_for_backward(y)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _native.lib()
+        (y,) = ctx.saved_tensors
+        c = _native.StftConfig(*ctx.cfg)
+        dout = dout.contiguous().float()
+        dy = torch.zeros_like(y)
+        with torch.cuda.device(y.device):
+            _native.check(lib.svb_stft_backward(ctypes.byref(c), _native.ptr(y), y.shape[0], y.shape[1], _native.ptr(ctx.basis),
+                                                _native.ptr(dout), _native.ptr(dy), _native.current_stream_ptr(y.device)),
+                          'stft_backward')
+        return dy, None, None, None
+
+
 def mel_spectrogram(y, hparams, center=False, complex=False):
     """y [B, T_wav] on a CUDA device -> ln-mel [B, n_mels, T_wav / hop]:
     clamp(-1, 1), reflect-pad (n_fft-hop)/2, STFT (hann(win), center=False),
@@ -26,13 +57,8 @@ def mel_spectrogram(y, hparams, center=False, complex=False):
     if not y.is_cuda:
         raise RuntimeError('mel_spectrogram needs a CUDA tensor: there is no CPU fallback')
     lib = _native.lib()
-    y = y.contiguous().float()
     B, n = y.shape
-    c = _native.StftConfig(int(hparams['fft_size']), int(hparams['hop_size']), int(hparams['win_size']),
-                           _native.PAD_HALF_REFLECT, _native.OUT_LN_MEL, 1, int(hparams['audio_num_mel_bins']), 0, 1e-5)
-    frames = int(lib.svb_stft_num_frames(ctypes.byref(c), n))
-    out = torch.empty(B, c.n_mels, frames, device=y.device, dtype=torch.float32)
-    with torch.cuda.device(y.device):
-        _native.check(lib.svb_stft_forward(ctypes.byref(c), _native.ptr(y), B, n, _native.ptr(_basis(hparams, y.device)),
-                                           _native.ptr(out), _native.current_stream_ptr(y.device)), 'stft_forward')
-    return out
+    cfg = (int(hparams['fft_size']), int(hparams['hop_size']), int(hparams['win_size']), _native.PAD_HALF_REFLECT,
+           _native.OUT_LN_MEL, 1, int(hparams['audio_num_mel_bins']), 0, 1e-5)
+    frames = int(lib.svb_stft_num_frames(ctypes.byref(_native.StftConfig(*cfg)), n))
+    return StftFn.apply(y, cfg, _basis(hparams, y.device), (B, cfg[6], frames))

@@ -13,27 +13,57 @@ def stft(x, fft_size, hop_size, win_length, window=None):
     accepted for signature compatibility; the kernel generates the hann window itself."""
     if not x.is_cuda:
         raise RuntimeError('stft needs a CUDA tensor: there is no CPU fallback')
+    from neuralsvb_b200.modules.hifigan.mel_utils import StftFn
     lib = _native.lib()
-    x = x.contiguous().float()
     B, n = x.shape
-    c = _native.StftConfig(int(fft_size), int(hop_size), int(win_length), _native.PAD_CENTER_REFLECT,
-                           _native.OUT_MAG, 0, 0, 1, 1e-7)
-    frames = int(lib.svb_stft_num_frames(ctypes.byref(c), n))
-    out = torch.empty(B, frames, fft_size // 2 + 1, device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
-        _native.check(lib.svb_stft_forward(ctypes.byref(c), _native.ptr(x), B, n, None, _native.ptr(out),
-                                           _native.current_stream_ptr(x.device)), 'stft_forward')
-    return out
+    cfg = (int(fft_size), int(hop_size), int(win_length), _native.PAD_CENTER_REFLECT, _native.OUT_MAG, 0, 0, 1, 1e-7)
+    frames = int(lib.svb_stft_num_frames(ctypes.byref(_native.StftConfig(*cfg)), n))
+    return StftFn.apply(x, cfg, None, (B, frames, fft_size // 2 + 1))
 
 
 MR_STFT = ((1024, 120, 600), (2048, 240, 1200), (512, 50, 240))       # losses/stft_loss.py:113-115
 
 
+class _StftLossFn(torch.autograd.Function):
+    """(spectral convergence, log-magnitude L1) of predicted magnitudes x against target magnitudes y
+    (SpectralConvergengeLoss / LogSTFTMagnitudeLoss, losses/stft_loss.py:34-73): float64 reductions by svb_pair_stats,
+    gradient w.r.t. x by svb_loss_grad (the target carries none)."""
+
+    @staticmethod
+    def forward(ctx, x_mag, y_mag):
+        from neuralsvb_b200.modules.hifigan.discriminators import pair_stats
+        s = pair_stats(y_mag, x_mag, want_log=True)
+        ctx.norms = (float(s[0]) ** 0.5, float(s[1]) ** 0.5)
+        ctx.save_for_backward(x_mag, y_mag)
+        dev = x_mag.device
+        return (torch.tensor(ctx.norms[0] / ctx.norms[1], device=dev, dtype=torch.float32),
+                torch.tensor(float(s[2]) / y_mag.numel(), device=dev, dtype=torch.float32))
+
+    @staticmethod
+    def backward(ctx, g_sc, g_mag):
+        lib = _native.lib()
+        x, y = ctx.saved_tensors
+        n = x.numel()
+        dx = torch.empty_like(x)
+        dnorm, ynorm = ctx.norms
+        with torch.cuda.device(x.device):
+            st = _native.current_stream_ptr(x.device)
+            # d/dx ||y - x|| / ||y|| = (x - y) / (||y - x|| ||y||) ;  d/dx mean |ln y - ln x| = sign(ln x - ln y) / (n x)
+            _native.check(lib.svb_loss_grad(_native.ptr(x), _native.ptr(y), 3, ctypes.c_float(float(g_sc) / max(dnorm * ynorm, 1e-30)),
+                                            _native.ptr(dx), n, 0, st), 'loss_grad')
+            _native.check(lib.svb_loss_grad(_native.ptr(x), _native.ptr(y), 4, ctypes.c_float(float(g_mag) / n), _native.ptr(dx), n, 1,
+                                            st), 'loss_grad')
+        return dx, None
+
+
 def stft_loss(x, y, fft_size, shift_size, win_length):
     """(spectral convergence ||Y - X||_F / ||Y||_F, log-magnitude L1 mean |ln Y - ln X|) of one resolution
-    (STFTLoss.forward, losses/stft_loss.py:89-106); magnitudes from the fused STFT kernel, reductions on the device."""
+    (STFTLoss.forward, losses/stft_loss.py:89-106); magnitudes from the fused STFT kernel, reductions on the device.
+    Python floats without grad; differentiable scalars w.r.t. the predicted signal ``x`` when it requires grad."""
     from neuralsvb_b200.modules.hifigan.discriminators import pair_stats
-    x_mag, y_mag = stft(x, fft_size, shift_size, win_length), stft(y, fft_size, shift_size, win_length)
+    x_mag, y_mag = stft(x, fft_size, shift_size, win_length), stft(y.detach(), fft_size, shift_size, win_length)
+    if torch.is_grad_enabled() and x_mag.requires_grad:
+        return _StftLossFn.apply(x_mag, y_mag)
     s = pair_stats(y_mag, x_mag, want_log=True)
     return float(s[0]) ** 0.5 / float(s[1]) ** 0.5, float(s[2]) / y_mag.numel()
 

@@ -67,9 +67,115 @@ class HifiGanInferTask(BaseTask):
         return {'audio_s': a, 'wall_s': w}
 
 
+def vocoder_losses(model_gen, mpd, msd, y, mel, f0, hp, optimizer_idx, y_hat=None, gen_kwargs=None):
+    """The two halves of one HiFi-GAN-NSF training step (SURVEY 3.4 / 8(d) cfg 3; wiring written new, the reference
+    ships only the components -- D1).  y [B,1,T_wav], mel [B,80,T], f0 [B,T] or None.
+      optimizer_idx 0 (generator): lambda_mel * L1(mel(y_hat), mel(y)) + lambda_adv * (generator_loss(MPD) +
+        generator_loss(MSD)) [+ feature_loss if use_fm_loss] [+ sc + mag of the multi-resolution STFT loss if use_ms_stft]
+      optimizer_idx 1 (discriminators): discriminator_loss of MPD and MSD on (y, y_hat.detach())
+    Returns (total loss, {name: scalar}, y_hat)."""
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    from neuralsvb_b200.modules.hifigan.mel_utils import mel_spectrogram
+    from neuralsvb_b200.modules.parallel_wavegan.losses.stft_loss import multi_resolution_stft_loss
+    logs = {}
+    if optimizer_idx == 0:
+        y_hat = model_gen(mel, f0, **(gen_kwargs or {}))
+        loss = hp.get('lambda_mel', 5.0) * D.l1_loss(mel_spectrogram(y_hat.squeeze(1), hp), mel_spectrogram(y.squeeze(1), hp))
+        logs['mel'] = loss
+        if hp.get('lambda_adv', 1.0) > 0 and mpd is not None:
+            _, gs_p, fr_p, fg_p = mpd(y, y_hat)
+            _, gs_s, fr_s, fg_s = msd(y, y_hat)
+            adv = (D.generator_loss(gs_p) + D.generator_loss(gs_s)) * hp.get('lambda_adv', 1.0)
+            logs['a'] = adv
+            loss = loss + adv
+            if hp.get('use_fm_loss', False):
+                fm = D.feature_loss(fr_p, fg_p) + D.feature_loss(fr_s, fg_s)
+                logs['fm'] = fm
+                loss = loss + fm
+        if hp.get('use_ms_stft', False):
+            sc, mag = multi_resolution_stft_loss(y_hat.squeeze(1), y.squeeze(1))
+            logs['sc'], logs['mag'] = sc, mag
+            loss = loss + sc + mag
+        return loss, logs, y_hat
+    y_hat = y_hat.detach()
+    rs_p, gs_p, _, _ = mpd(y, y_hat)
+    rs_s, gs_s, _, _ = msd(y, y_hat)
+    r_p, g_p = D.discriminator_loss(rs_p, gs_p)
+    r_s, g_s = D.discriminator_loss(rs_s, gs_s)
+    logs['r'], logs['f'] = r_p + r_s, g_p + g_s
+    return r_p + g_p + r_s + g_s, logs, y_hat
+
+
 class HifiGanTask(HifiGanInferTask):
-    """The name the reference config points at.  Inference works; training is not implemented yet."""
+    """The task ``egs/egs_bases/tts/vocoder/hifigan.yaml:2`` names (``tasks.vocoder.hifigan.HifiGanTask``, absent from
+    the reference -- D1): HiFi-GAN-NSF generator + MPD + MSD under the trainer's two-optimizer contract
+    (``utils/trainer.py:275-337``; pattern of ``tasks/tts/fs2_adv.py:37-128``).  Every forward and backward operator is a
+    CUDA kernel of this package; torch supplies autograd's graph walk, AdamW and gradient clipping.
+    Without a binarized dataset the loader yields synthetic harmonic+noise clips (SURVEY 8(d) cfg 3)."""
+
+    def build_model(self):
+        import torch
+        from neuralsvb_b200.modules.hifigan.discriminators import MultiPeriodDiscriminator, MultiScaleDiscriminator
+        from neuralsvb_b200.modules.hifigan.hifigan import HifiGanGenerator
+        if hparams.get('infer', False):
+            return super().build_model()
+        self.model_gen = HifiGanGenerator(hparams, precision=hparams.get('vocoder_precision', 'bf16x3'))
+        self.model_disc = torch.nn.ModuleDict({'mpd': MultiPeriodDiscriminator(), 'msd': MultiScaleDiscriminator()})
+        self._y_hat = None
+        return self.model_gen
+
+    def configure_optimizers(self):
+        import torch
+        if hparams.get('infer', False):
+            return []
+        kw = dict(lr=hparams.get('lr', 2e-4), betas=(hparams.get('adam_b1', 0.8), hparams.get('adam_b2', 0.99)),
+                  weight_decay=hparams.get('weight_decay', 0.0))
+        self.opt_g = torch.optim.AdamW(self.model_gen.parameters(), **kw)
+        self.opt_d = torch.optim.AdamW(self.model_disc.parameters(), **kw)
+        return [self.opt_g, self.opt_d]
+
+    def train_dataloader(self):
+        """Synthetic clips of ``max_samples`` samples (hifigan.yaml:23-24), ``max_sentences`` per batch, sharded by rank."""
+        import torch
+        from neuralsvb_b200.modules.hifigan.mel_utils import mel_spectrogram
+        from neuralsvb_b200.utils import synthetic as S
+        hop = hparams['hop_size']
+        n = int(hparams.get('max_samples', 8192)) // hop * hop
+        B = int(hparams.get('max_sentences', 24))
+        rank, world, _ = ddp_utils.dist_env()
+        batches = []
+        for i in range(int(hparams.get('num_train_batches', 8))):
+            seed = hparams['seed'] + 1000 * rank + i
+            y = S.make_wave_batch(B, n, seed=seed)[:, None]
+            _, f0 = make_mel_f0(B, n // hop, seed=seed)
+            batches.append({'wavs': y, 'f0': f0})
+        return batches
 
     def training_step(self, sample, batch_idx, optimizer_idx=-1):
-        raise NotImplementedError('HiFi-GAN G + MPD + MSD training needs the backward kernels (DESIGN.md section 7); '
-                                  'run with --infer')
+        import torch
+        from neuralsvb_b200.modules.hifigan.mel_utils import mel_spectrogram
+        y = sample['wavs'].cuda().float()
+        f0 = sample['f0'].cuda().float() if hparams.get('use_pitch_embed', True) else None
+        if 'mels' in sample:
+            mel = sample['mels'].cuda().float()
+        else:
+            with torch.no_grad():
+                mel = mel_spectrogram(y.squeeze(1), hparams)
+        disc_on = self.global_step >= hparams.get('disc_start_steps', 0)
+        if optimizer_idx == 0:
+            loss, logs, self._y_hat = vocoder_losses(self.model_gen, self.model_disc['mpd'] if disc_on else None,
+                                                     self.model_disc['msd'] if disc_on else None, y, mel, f0, hparams, 0)
+        else:
+            if not disc_on or self._y_hat is None:
+                return {'loss': None}
+            loss, logs, _ = vocoder_losses(None, self.model_disc['mpd'], self.model_disc['msd'], y, mel, f0, hparams, 1,
+                                           y_hat=self._y_hat)
+        logs = {k: float(v) for k, v in logs.items()}
+        return {'loss': loss, 'progress_bar': logs, 'tb_log': logs}
+
+    def on_before_optimization(self, opt_idx):
+        import torch
+        if opt_idx == 0:
+            torch.nn.utils.clip_grad_norm_(self.model_gen.parameters(), hparams.get('generator_grad_norm', 10.0))
+        else:
+            torch.nn.utils.clip_grad_norm_(self.model_disc.parameters(), hparams.get('discriminator_grad_norm', 1.0))

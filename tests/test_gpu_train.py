@@ -158,3 +158,97 @@ def test_discriminator_backward_matches_oracle_autograd(name):
     top = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
     print(f'{name}: global {glob:.1e} median {med:.1e} worst {[(k, f"{e:.1e}") for k, e in top]}')
     assert glob < 3e-3 and med < 2e-4 and worst < 2e-2, (glob, med, worst)      # a flipped leaky-relu mask moves one small tensor by ~5e-3
+
+
+# ------------------------------------------------------------------ spectral losses
+def test_mel_and_mr_stft_loss_backward_match_oracle_autograd():
+    """d/dx of  L1(mel_spectrogram(x), mel_spectrogram(y)) + sc + mag  (multi-resolution STFT loss): the fused STFT
+    kernel's adjoint (svb_stft_backward) against torch autograd through torch.stft in the oracle."""
+    import torch.nn.functional as F
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    from neuralsvb_b200.modules.hifigan.mel_utils import mel_spectrogram
+    from neuralsvb_b200.modules.parallel_wavegan.losses.stft_loss import multi_resolution_stft_loss
+    hp = S.hifigan_config()
+    y = S.make_wave_batch(2, 8192, seed=U.SEED)
+    x0 = (y + 0.05 * S.make_wave_batch(2, 8192, seed=U.SEED + 1)).clamp(-1, 1)
+    for which in ('mel', 'stft'):
+        xr = x0.clone().requires_grad_(True)
+        if which == 'mel':
+            ref = F.l1_loss(O.mel_spectrogram(xr, hp), O.mel_spectrogram(y, hp))
+        else:
+            sc, mag = O.mr_stft_loss(xr, y)
+            ref = sc + mag
+        ref.backward()
+        xc = x0.cuda().requires_grad_(True)
+        if which == 'mel':
+            got = D.l1_loss(mel_spectrogram(xc, hp), mel_spectrogram(y.cuda(), hp))
+        else:
+            sc, mag = multi_resolution_stft_loss(xc, y.cuda())
+            got = sc + mag
+        got.backward()
+        assert abs(float(got) - float(ref)) <= 1e-3 * abs(float(ref))
+        err = float((xc.grad.cpu().double() - xr.grad.double()).norm() / xr.grad.double().norm())
+        print(f'{which} loss {float(got):.5f} (oracle {float(ref):.5f}), d/dx relative L2 error {err:.1e}')
+        assert err < 2e-3, (which, err)
+
+
+# ------------------------------------------------------------------ the composed G / D step
+def test_vocoder_train_step_matches_oracle_wiring():
+    """One generator step and one discriminator step of tasks/vocoder/hifigan.vocoder_losses (all loss terms on) against
+    the same wiring written in eager PyTorch from the oracle's components (SURVEY 8(d) cfg 3: the reference ships no
+    wiring, so results are pinned per component and the composition is checked here)."""
+    import torch.nn.functional as F
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    from neuralsvb_b200.tasks.vocoder.hifigan import vocoder_losses
+    h = S.small_config(True)
+    hp = dict(S.hifigan_config(), lambda_mel=5.0, lambda_adv=1.0, use_fm_loss=True, use_ms_stft=True)
+    B, T, hop = 2, 512, 16
+    sd_g, sd_p, sd_s = S.make_generator_state_dict(h, U.SEED), S.make_mpd_state_dict(U.SEED), S.make_msd_state_dict(U.SEED)
+    mel, f0 = S.make_mel_f0(B, T, U.SEED)
+    ri, nz = S.make_nsf_noise(B, T * hop, U.SEED)
+    y = S.make_wave_batch(B, T * hop, seed=U.SEED)[:, None]
+
+    # ---- oracle wiring
+    is_buf = lambda sd, k: k.endswith('weight_u') or (k.endswith('weight_v') and k[:-1] + 'orig' in sd)
+    pg = {k: v.clone().requires_grad_(True) for k, v in sd_g.items()}
+    pp = {k: v.clone().requires_grad_(True) for k, v in sd_p.items()}
+    ps = {k: (v.clone() if is_buf(sd_s, k) else v.clone().requires_grad_(True)) for k, v in sd_s.items()}
+    wp, ws = O.fold_discriminator_weights(pp), O.fold_discriminator_weights(ps)
+    y_hat = O.generator_forward(O.fold_weight_norm(pg), h, mel, f0, ri, nz)
+    _, gp, frp, fgp = O.mpd_forward(y, y_hat, wp)
+    _, gs, frs, fgs = O.msd_forward(y, y_hat, ws)
+    sc, mag = O.mr_stft_loss(y_hat.squeeze(1), y.squeeze(1))
+    loss_g = (5.0 * F.l1_loss(O.mel_spectrogram(y_hat.squeeze(1), hp), O.mel_spectrogram(y.squeeze(1), hp))
+              + O.generator_loss(gp) + O.generator_loss(gs) + O.feature_loss(frp, fgp) + O.feature_loss(frs, fgs) + sc + mag)
+    gg_ref = dict(zip(pg, torch.autograd.grad(loss_g, list(pg.values()))))
+    rp, gp2, _, _ = O.mpd_forward(y, y_hat.detach(), wp)
+    rs, gs2, _, _ = O.msd_forward(y, y_hat.detach(), ws)
+    loss_d = sum(O.discriminator_loss(rp, gp2)) + sum(O.discriminator_loss(rs, gs2))
+    d_params = {**{'mpd.' + k: v for k, v in pp.items()}, **{'msd.' + k: v for k, v in ps.items() if not is_buf(sd_s, k)}}
+    gd_ref = dict(zip(d_params, torch.autograd.grad(loss_d, list(d_params.values()))))
+
+    # ---- CUDA path
+    gen = HifiGanGenerator(h, precision='fp32')
+    gen.load_state_dict(sd_g, strict=True)
+    gen = gen.cuda().train()
+    mpd, msd = D.MultiPeriodDiscriminator(), D.MultiScaleDiscriminator()
+    mpd.load_state_dict(sd_p, strict=True), msd.load_state_dict(sd_s, strict=True)
+    mpd, msd = mpd.cuda().eval(), msd.cuda().eval()          # eval: spectral norm without power iteration, as the oracle
+    for q in list(mpd.parameters()) + list(msd.parameters()):
+        q.requires_grad_(False)                              # what the trainer does for the other optimizer's parameters
+    lg, logs, yh = vocoder_losses(gen, mpd, msd, y.cuda(), mel.cuda(), f0.cuda(), hp, 0,
+                                  gen_kwargs=dict(rand_ini=ri.cuda(), noise=nz.cuda()))
+    lg.backward()
+    assert abs(float(lg) - float(loss_g)) < 2e-3 * abs(float(loss_g)), (float(lg), float(loss_g))
+    errs, glob, med, worst = _stats({k: q.grad.cpu() for k, q in gen.named_parameters()}, gg_ref)
+    print(f'G step: loss {float(lg):.4f} (oracle {float(loss_g):.4f}) grads global {glob:.1e} median {med:.1e} worst {worst:.1e}')
+    assert glob < 1e-2 and med < 5e-3, (glob, med, worst)
+    for q in list(mpd.parameters()) + list(msd.parameters()):
+        q.requires_grad_(True)
+    ld, _, _ = vocoder_losses(None, mpd, msd, y.cuda(), mel.cuda(), f0.cuda(), hp, 1, y_hat=yh)
+    ld.backward()
+    assert abs(float(ld) - float(loss_d)) < 2e-3 * abs(float(loss_d)), (float(ld), float(loss_d))
+    got = {**{'mpd.' + k: q.grad.cpu() for k, q in mpd.named_parameters()}, **{'msd.' + k: q.grad.cpu() for k, q in msd.named_parameters()}}
+    errs, glob, med, worst = _stats(got, gd_ref)
+    print(f'D step: loss {float(ld):.4f} (oracle {float(loss_d):.4f}) grads global {glob:.1e} median {med:.1e} worst {worst:.1e}')
+    assert glob < 1e-2 and med < 1e-3, (glob, med, worst)
