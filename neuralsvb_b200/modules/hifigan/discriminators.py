@@ -101,7 +101,15 @@ class _NormConv(nn.Module):
         """[Cout, Cin/groups, K] effective weight + bias on `device` (cached until parameters change).  With grad
         enabled the result is differentiable w.r.t. the parameters (weight norm: svb_weight_norm_backward)."""
         wp = self.weight_orig if self.spectral else self.weight_v
-        if torch.is_grad_enabled() and (wp.requires_grad or self.bias.requires_grad):
+        diff = torch.is_grad_enabled() and (wp.requires_grad or self.bias.requires_grad)
+        if self.spectral and self.training and wp.is_cuda:
+            # torch.nn.utils.spectral_norm runs its power iteration on EVERY training-mode forward, also when this
+            # discriminator's parameters are frozen (the generator step)
+            eff = self._spectral_weight()
+            if not diff:
+                eff = eff.detach()
+            return eff.reshape(eff.shape[0], eff.shape[1], -1), (self.bias if diff else self.bias.detach())
+        if diff:
             if self.spectral:
                 eff = self._spectral_weight()
             else:

@@ -122,7 +122,7 @@ class HifiGanTask(HifiGanInferTask):
         self.model_gen = HifiGanGenerator(hparams, precision=hparams.get('vocoder_precision', 'bf16x3'))
         self.model_disc = torch.nn.ModuleDict({'mpd': MultiPeriodDiscriminator(), 'msd': MultiScaleDiscriminator()})
         self._y_hat = None
-        return self.model_gen
+        return None
 
     def configure_optimizers(self):
         import torch
@@ -172,6 +172,22 @@ class HifiGanTask(HifiGanInferTask):
                                            y_hat=self._y_hat)
         logs = {k: float(v) for k, v in logs.items()}
         return {'loss': loss, 'progress_bar': logs, 'tb_log': logs}
+
+    def val_dataloader(self):
+        return self.train_dataloader()[:1]
+
+    def validation_step(self, sample, batch_idx):
+        from neuralsvb_b200.modules.hifigan import discriminators as D
+        from neuralsvb_b200.modules.hifigan.mel_utils import mel_spectrogram
+        y = sample['wavs'].cuda().float()
+        f0 = sample['f0'].cuda().float() if hparams.get('use_pitch_embed', True) else None
+        mel = mel_spectrogram(y.squeeze(1), hparams)
+        y_hat = self.model_gen(mel, f0)
+        return {'val_loss': float(D.l1_loss(mel_spectrogram(y_hat.squeeze(1), hparams), mel))}
+
+    def validation_end(self, outputs):
+        v = sum(o['val_loss'] for o in outputs) / max(len(outputs), 1)
+        return {'val_loss': v, 'tb_log': {'val_loss': v}}
 
     def on_before_optimization(self, opt_idx):
         import torch

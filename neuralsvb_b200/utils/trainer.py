@@ -208,6 +208,8 @@ class Trainer:
                 self.first_epoch = False
                 if (self.global_step + 1) % self.tb_log_interval == 0:
                     self.log_metrics_to_tb(tb_metrics)
+                    if self.proc_rank == 0 and pbar_metrics:
+                        print(f'| step {self.global_step}: {pbar_metrics}', flush=True)
                 self.global_step += 1
                 task.global_step = self.global_step
                 if self.global_step > self.max_updates:

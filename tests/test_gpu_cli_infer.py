@@ -37,3 +37,22 @@ def test_run_py_infer_with_reference_layout_checkpoint(tmp_path):
     assert len(wavs) == 2
     sr, data = wavfile.read(wavs[0])
     assert sr == 22050 and data.dtype == np.int16 and len(data) == 64 * 256 and np.abs(data).max() > 100
+
+
+def test_run_py_trains_the_vocoder_for_a_few_steps(tmp_path):
+    """tasks/run.py -> HifiGanTask.start -> Trainer.fit: generator + MPD + MSD, two optimizers, synthetic clips.
+    The mel loss must go down over the steps and the run must leave a checkpoint the vocoder plugin can load."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, '-m', 'neuralsvb_b200.tasks.run', '--config', os.path.join(ROOT, 'egs/vocoder_train_synthetic.yaml'),
+                        '--exp_name', 'cli_train', '--reset', '--hparams',
+                        'max_updates=6,max_sentences=2,max_samples=8192,num_train_batches=1,val_check_interval=4,tb_log_interval=1,lr=0.001'],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert 'Training end' in r.stdout
+    import re
+    mels = [float(m) for m in re.findall(r"'mel': ([0-9.eE+-]+)", r.stdout)]
+    assert len(mels) >= 4 and mels[-1] < mels[0], mels
+    ckpts = list((tmp_path / 'checkpoints' / 'cli_train').glob('model_ckpt_steps_*.ckpt'))
+    assert ckpts, r.stdout[-2000:]
+    sd = torch.load(ckpts[0], map_location='cpu')['state_dict']
+    assert 'model_gen' in sd and 'conv_pre.weight_v' in sd['model_gen']
