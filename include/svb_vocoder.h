@@ -152,6 +152,24 @@ int svb_pad_reflect_right_backward(const float *dy_dev, float *dx_dev, int64_t r
 int svb_loss_grad(const float *a_dev, const float *b_dev, int32_t kind, float scale, float *da_dev, int64_t n,
                   int32_t accumulate, void *stream);
 
+/* ---- dense discriminator convolutions on the tensor-core kernel -------------------------------------------------
+ * One handle per Conv1d / Conv2d((k,1)) layer with groups == 1 (modules/hifigan/hifigan.py:193-199, :262-271):
+ * tensors are PyTorch-layout device buffers [B, C, T, W] (W = period columns, 1 for DiscriminatorS); weights
+ * [Cout, Cin, K] and bias are device buffers re-packed by svb_tc_layer_set_weight_dev (cheap: call it whenever
+ * they change).  forward: y = leaky_relu(conv(x) + bias, out_slope).  backward: dy is the gradient w.r.t. y;
+ * dx is written, dw [Cout, Cin, K] / db [Cout] are ACCUMULATED (caller zeroes them); each may be null.
+ * Shapes: stride 1 needs padding (K-1)/2; Cin*K (stride > 1) or Cin (stride 1) and Cout multiples of 32, Cout <= 1024. */
+typedef struct svb_tc_layer svb_tc_layer_t;
+int svb_tc_layer_create(int32_t Cin, int32_t Cout, int32_t K, int32_t stride, int32_t pad, int32_t precision, int device,
+                        svb_tc_layer_t **out);
+void svb_tc_layer_destroy(svb_tc_layer_t *layer);
+int svb_tc_layer_set_weight_dev(svb_tc_layer_t *layer, const float *w_dev, const float *bias_dev, void *stream);
+int64_t svb_tc_layer_out_len(const svb_tc_layer_t *layer, int64_t T);
+int svb_tc_layer_forward(svb_tc_layer_t *layer, const float *x_dev, int32_t B, int32_t T, int32_t W, float out_slope,
+                         float *y_dev, void *stream);
+int svb_tc_layer_backward(svb_tc_layer_t *layer, const float *x_dev, const float *y_dev, const float *dy_dev, int32_t B,
+                          int32_t T, int32_t W, float out_slope, float *dx_dev, float *dw_dev, float *db_dev, void *stream);
+
 /* ---- training: backward of the generator -------------------------------------------------------------
  * Replaces torch autograd through HifiGanGenerator.forward (modules/hifigan/hifigan.py:144-169; ResBlock1/2
  * :54-61 / :81-86; weight_norm :35-50,118,124; SourceModuleHnNSF.l_linear source.py:393-394) for the

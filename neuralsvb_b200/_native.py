@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libsvb_vocoder.so')
 HEADER = os.path.join(_ROOT, 'include', 'svb_vocoder.h')
 SOURCES = ['api.cu', 'conv_ffma.cu', 'conv_tc.cu', 'nsf_source.cu', 'frontend.cu', 'generator.cu', 'layer_api.cu', 'disc_ops.cu',
-           'train_ops.cu', 'generator_bwd.cu', 'disc_bwd.cu']
+           'train_ops.cu', 'generator_bwd.cu', 'disc_bwd.cu', 'tc_layer.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -110,6 +110,12 @@ _PROTOS = {
     'svb_avgpool1d_4_2_1_backward': (ctypes.c_int, [_P, _P, _I64, _I32, _P]),
     'svb_pad_reflect_right_backward': (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P]),
     'svb_loss_grad': (ctypes.c_int, [_P, _P, _I32, ctypes.c_float, _P, _I64, _I32, _P]),
+    'svb_tc_layer_create': (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, ctypes.c_int, ctypes.POINTER(_P)]),
+    'svb_tc_layer_destroy': (None, [_P]),
+    'svb_tc_layer_set_weight_dev': (ctypes.c_int, [_P, _P, _P, _P]),
+    'svb_tc_layer_out_len': (_I64, [_P, _I64]),
+    'svb_tc_layer_forward': (ctypes.c_int, [_P, _P, _I32, _I32, _I32, ctypes.c_float, _P, _P]),
+    'svb_tc_layer_backward': (ctypes.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, ctypes.c_float, _P, _P, _P, _P]),
     'svb_gen_set_training': (ctypes.c_int, [_P, _I32]),
     'svb_gen_update_weights': (ctypes.c_int, [_P]),
     'svb_gen_zero_grad': (ctypes.c_int, [_P, _P]),

@@ -214,7 +214,7 @@ constexpr int kMaxW = 8;
 constexpr int kTcThreadsP = 576;
 constexpr int kWarpProducer = 16, kWarpMma = 17, kWarpTransform0 = 8;
 constexpr int kStageBytes = 8 * 4096;   // epilogue transpose tiles: 32 rows x 128 B per epilogue warp
-constexpr int kBiasBytes = 4096;        // bias of the layer (Cout <= 1024 floats)
+constexpr int kBiasBytes = 4096;        // bias of the layer (Cout <= 1024 floats; wider layers take 12 KB)
 
 // Persistent kernel: one CTA per SM walks "groups" (MT consecutive 128-row tiles of one clip for
 // one column block).  Every stage is decoupled by mbarriers, so the TMA producer runs ahead into
@@ -728,7 +728,7 @@ int tc_repack_weights_dev(const float *packed_dev, const TcWeights &w, cudaStrea
 
 bool tc_supported(const TcWeights &w, const ConvArgs &a) {
     return w.ok && a.Cin % 4 == 0 && a.bias != nullptr && (a.KS - 1) / 2 * a.dil <= kPad &&
-           (a.ups_u == 0 || a.Cout % 32 == 0) && a.Cout <= 1024;
+           (a.ups_u == 0 || a.Cout % 32 == 0) && a.Cout <= 3072;
 }
 
 template <int MODE>
@@ -785,7 +785,8 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     // ---- M tiles per group: each weight tile fetched from L2 feeds MT accumulators.  Two accumulator
     // sets live in TMEM (2 * MT * N <= 512 columns); slabs and the weight ring must fit shared memory.
     size_t smem = 0;
-    const size_t budget = 226 * 1024 - kStageBytes - kBiasBytes;
+    const size_t bias_bytes = a.Cout <= 1024 ? kBiasBytes : 3 * kBiasBytes;
+    const size_t budget = 226 * 1024 - kStageBytes - bias_bytes;
     int force_sets = 0;
     if (const char *e = getenv("SVB_TC_SETS")) force_sets = atoi(e);
     const long long tile_units = (long long)tiles * p.col_blocks * a.B;
@@ -837,7 +838,7 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         p.nW = nW;
         p.off_stage = p.off_w + (uint32_t)nW * p.wstage_bytes;
         p.off_bias = p.off_stage + kStageBytes;
-        smem = (size_t)p.off_bias + kBiasBytes;
+        smem = (size_t)p.off_bias + bias_bytes;
         break;
     }
     if (getenv("SVB_TC_VERBOSE"))

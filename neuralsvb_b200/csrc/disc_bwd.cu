@@ -46,23 +46,29 @@ __global__ void __launch_bounds__(256) mask_bias_kernel(const float *__restrict_
     }
 }
 
-constexpr int kDT = 64, kDC = 64, kDCo = 4;     // data-gradient tile: 64 inputs x 64 cins, 4 couts per smem chunk
+constexpr int kDCo = 4;     // couts per shared-memory chunk of the data-gradient kernel
 
-template <int STRIDE>
+// Data gradient of the strided / grouped conv.  Block = CIQ input-channel quads (4*CIQ = the group's channels, up to 64)
+// x 4*TX input positions, TX = 256 / CIQ.  dx[t] only receives taps k with (t + pad - k*dil) divisible by the stride;
+// a thread's 4 positions are TX apart, so when TX is a multiple of the stride (and dil == 1) they share that tap set
+// and the loop walks ONLY the valid taps (k = k0, k0 + STRIDE, ...): no wasted iterations for the stride-2/4 layers.
+template <int STRIDE, int CIQ>
 __global__ void __launch_bounds__(256) gconv_dgrad_kernel(GBwdArgs a) {
+    constexpr int TX = 256 / CIQ, TT = 4 * TX, CI = 4 * CIQ;
     extern __shared__ float sm[];
-    const int span = (kDT - 1 + (a.K - 1) * a.dil) / STRIDE + 2;
+    const int span = (TT - 1 + (a.K - 1) * a.dil) / STRIDE + 2;
     float *zs = sm;                               // [kDCo][span]
-    float *ws = sm + kDCo * span;                 // [kDCo][K][kDC]
+    float *ws = sm + kDCo * span;                 // [kDCo][K][CI]
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
-    const int ci_tiles = (cin_g + kDC - 1) / kDC;
+    const int ci_tiles = (cin_g + CI - 1) / CI;
     const int g = blockIdx.y / ci_tiles, ci_t = blockIdx.y % ci_tiles;
     const int bw = blockIdx.z, b = bw / a.W, wcol = bw % a.W;
-    const int t0 = blockIdx.x * kDT;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int t0 = blockIdx.x * TT;
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
     // smallest numerator t + pad - k*dil of the tile; floor division (the numerator may be negative)
     const int num_lo = t0 + a.pad - (a.K - 1) * a.dil;
     const int base = num_lo >= 0 ? num_lo / STRIDE : -((-num_lo + STRIDE - 1) / STRIDE);
+    const bool shared_taps = (TX % STRIDE == 0) && a.dil == 1;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -78,36 +84,55 @@ __global__ void __launch_bounds__(256) gconv_dgrad_kernel(GBwdArgs a) {
                 v = __ldg(a.dz + (((size_t)b * a.Cout + g * cout_g + c0 + c) * a.Tout + to) * a.W + wcol);
             zs[idx] = v;
         }
-        for (int idx = tid; idx < kDCo * a.K * kDC; idx += 256) {
-            const int ci = idx % kDC, k = (idx / kDC) % a.K, c = idx / (kDC * a.K);
+        for (int idx = tid; idx < kDCo * a.K * CI; idx += 256) {
+            const int ci = idx % CI, k = (idx / CI) % a.K, c = idx / (CI * a.K);
             float v = 0.f;
-            const int cig = ci_t * kDC + ci;
+            const int cig = ci_t * CI + ci;
             if (c0 + c < cout_g && cig < cin_g) v = __ldg(a.w + ((size_t)(g * cout_g + c0 + c) * cin_g + cig) * a.K + k);
             ws[idx] = v;
         }
         __syncthreads();
-        for (int c = 0; c < kDCo; ++c)
-            for (int k = 0; k < a.K; ++k) {
-                const float4 w4 = *reinterpret_cast<const float4 *>(ws + (c * a.K + k) * kDC + 4 * ty);
+        if (shared_taps) {
+            const int n0 = t0 + tx + a.pad;                       // numerator of position j = 0 at k = 0
+            const int k0 = n0 % STRIDE;                           // taps k = k0 (mod STRIDE) land on an output
+            for (int c = 0; c < kDCo; ++c) {
+                const float *zr = zs + c * span - base;
+                for (int k = k0; k < a.K; k += STRIDE) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(ws + (c * a.K + k) * CI + 4 * ty);
+                    const int q = (n0 - k) / STRIDE;              // exact; may be negative at the left edge (zs is zero there)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int num = t0 + tx + 16 * j + a.pad - k * a.dil;
-                    if (num < 0) continue;
-                    const int q = num / STRIDE;
-                    if (q * STRIDE != num) continue;
-                    const float zv = zs[c * span + q - base];
-                    acc[0][j] = fmaf(w4.x, zv, acc[0][j]), acc[1][j] = fmaf(w4.y, zv, acc[1][j]);
-                    acc[2][j] = fmaf(w4.z, zv, acc[2][j]), acc[3][j] = fmaf(w4.w, zv, acc[3][j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const int qq = q + j * (TX / STRIDE);
+                        const float zv = (n0 + j * TX - k >= 0) ? zr[qq] : 0.f;
+                        acc[0][j] = fmaf(w4.x, zv, acc[0][j]), acc[1][j] = fmaf(w4.y, zv, acc[1][j]);
+                        acc[2][j] = fmaf(w4.z, zv, acc[2][j]), acc[3][j] = fmaf(w4.w, zv, acc[3][j]);
+                    }
                 }
             }
+        } else {
+            for (int c = 0; c < kDCo; ++c)
+                for (int k = 0; k < a.K; ++k) {
+                    const float4 w4 = *reinterpret_cast<const float4 *>(ws + (c * a.K + k) * CI + 4 * ty);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int num = t0 + tx + TX * j + a.pad - k * a.dil;
+                        if (num < 0) continue;
+                        const int q = num / STRIDE;
+                        if (q * STRIDE != num) continue;
+                        const float zv = zs[c * span + q - base];
+                        acc[0][j] = fmaf(w4.x, zv, acc[0][j]), acc[1][j] = fmaf(w4.y, zv, acc[1][j]);
+                        acc[2][j] = fmaf(w4.z, zv, acc[2][j]), acc[3][j] = fmaf(w4.w, zv, acc[3][j]);
+                    }
+                }
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int cig = ci_t * kDC + 4 * ty + i;
+        const int cig = ci_t * CI + 4 * ty + i;
         if (cig >= cin_g) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int t = t0 + tx + 16 * j;
+            const int t = t0 + tx + TX * j;
             if (t < a.Tin) a.dx[(((size_t)b * a.Cin + g * cin_g + cig) * a.Tin + t) * a.W + wcol] = acc[i][j];
         }
     }
@@ -236,6 +261,37 @@ static int launch_wgrad_k(const GBwdArgs &a, cudaStream_t st) {
     return SVB_OK;
 }
 
+template <int STRIDE, int CIQ>
+static int launch_dgrad_t(const GBwdArgs &a, cudaStream_t st) {
+    constexpr int TX = 256 / CIQ, TT = 4 * TX, CI = 4 * CIQ;
+    const int cin_g = a.Cin / a.groups;
+    const int span = (TT - 1 + (a.K - 1) * a.dil) / STRIDE + 2;
+    const size_t smem = ((size_t)kDCo * span + (size_t)kDCo * a.K * CI) * 4;
+    SVB_CHECK(smem <= 48 * 1024, SVB_ERR_INVALID, "conv_nct_backward: kernel %d too large", a.K);
+    dim3 grid((a.Tin + TT - 1) / TT, ((cin_g + CI - 1) / CI) * a.groups, a.B * a.W);
+    gconv_dgrad_kernel<STRIDE, CIQ><<<grid, 256, smem, st>>>(a);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
+template <int STRIDE>
+static int launch_dgrad_s(const GBwdArgs &a, cudaStream_t st) {
+    const int cin_g = a.Cin / a.groups;
+    if (cin_g <= 8) return launch_dgrad_t<STRIDE, 2>(a, st);
+    if (cin_g <= 16) return launch_dgrad_t<STRIDE, 4>(a, st);
+    if (cin_g <= 32) return launch_dgrad_t<STRIDE, 8>(a, st);
+    return launch_dgrad_t<STRIDE, 16>(a, st);
+}
+
+static int launch_dgrad(const GBwdArgs &a, cudaStream_t st) {
+    switch (a.stride) {
+        case 1: return launch_dgrad_s<1>(a, st);
+        case 2: return launch_dgrad_s<2>(a, st);
+        case 3: return launch_dgrad_s<3>(a, st);
+        default: return launch_dgrad_s<4>(a, st);
+    }
+}
+
 extern "C" int svb_conv_nct_backward(const float *x_dev, const float *w_dev, const float *y_dev, const float *dy_dev, int32_t B,
                                      int32_t Cin, int32_t Cout, int32_t Tin, int32_t W, int32_t K, int32_t stride, int32_t dil,
                                      int32_t pad, int32_t groups, float out_slope, float *dz_scratch_dev, float *dx_dev,
@@ -254,15 +310,7 @@ extern "C" int svb_conv_nct_backward(const float *x_dev, const float *w_dev, con
                                                      (long long)a.Tout * W, dz_scratch_dev, db_dev);
     if (dx_dev) {
         SVB_CHECK(stride <= 4, SVB_ERR_INVALID, "conv_nct_backward: stride %d unsupported", stride);
-        const int cin_g = Cin / groups;
-        const int span = (kDT - 1 + (K - 1) * dil) / stride + 2;
-        const size_t smem = ((size_t)kDCo * span + (size_t)kDCo * K * kDC) * 4;
-        SVB_CHECK(smem <= 48 * 1024, SVB_ERR_INVALID, "conv_nct_backward: kernel %d too large", K);
-        dim3 grid((Tin + kDT - 1) / kDT, ((cin_g + kDC - 1) / kDC) * groups, B * W);
-        if (stride == 1) gconv_dgrad_kernel<1><<<grid, 256, smem, st>>>(a);
-        else if (stride == 2) gconv_dgrad_kernel<2><<<grid, 256, smem, st>>>(a);
-        else if (stride == 3) gconv_dgrad_kernel<3><<<grid, 256, smem, st>>>(a);
-        else gconv_dgrad_kernel<4><<<grid, 256, smem, st>>>(a);
+        SVB_TRY(launch_dgrad(a, st));
     }
     if (dw_dev) {
         switch (K) {

@@ -24,9 +24,13 @@ struct GConvArgs {
     float out_slope;                      // leaky-relu slope applied to the output (1 = none)
 };
 
-constexpr int kGT = 64, kGC = 64, kGCI = 4;   // tile: 64 outputs x 64 couts, 4 input channels per smem chunk
+constexpr int kGCI = 4;   // input channels per shared-memory chunk
 
+// Block = COQ output-channel quads (4*COQ = the group's output channels, up to 64) x 4*TX outputs, TX = 256 / COQ:
+// the narrow groups of the MSD (8-32 channels per group) keep every thread busy.
+template <int COQ>
 __global__ void __launch_bounds__(256) gconv_kernel(GConvArgs a) {
+    constexpr int TX = 256 / COQ, kGT = 4 * TX, kGC = 4 * COQ;
     extern __shared__ float sm[];
     const int span = (kGT - 1) * a.stride + (a.K - 1) * a.dil + 1;
     float *xs = sm;                               // [kGCI][span]
@@ -36,7 +40,7 @@ __global__ void __launch_bounds__(256) gconv_kernel(GConvArgs a) {
     const int g = blockIdx.y / co_tiles, co_t = blockIdx.y % co_tiles;
     const int bw = blockIdx.z, b = bw / a.W, wcol = bw % a.W;
     const int to0 = blockIdx.x * kGT;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;       // tx: outputs tx + 16 j ; ty: couts 4 ty ..
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;       // tx: outputs tx + TX j ; ty: couts 4 ty ..
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(256) gconv_kernel(GConvArgs a) {
                 const float *xr = xs + ci * span + k * a.dil;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float xv = xr[(tx + 16 * j) * a.stride];
+                    const float xv = xr[(tx + TX * j) * a.stride];
                     acc[0][j] = fmaf(w4.x, xv, acc[0][j]), acc[1][j] = fmaf(w4.y, xv, acc[1][j]);
                     acc[2][j] = fmaf(w4.z, xv, acc[2][j]), acc[3][j] = fmaf(w4.w, xv, acc[3][j]);
                 }
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(256) gconv_kernel(GConvArgs a) {
         const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int to = to0 + tx + 16 * j;
+            const int to = to0 + tx + TX * j;
             if (to >= a.Tout) continue;
             const float v = acc[i][j] + bv;
             a.y[(((size_t)b * a.Cout + co) * a.Tout + to) * a.W + wcol] = lrelu(v, a.out_slope);
@@ -160,6 +164,23 @@ __global__ void matvec_rows_kernel(const float *__restrict__ Wm, const float *__
 
 using namespace svb;
 
+template <int COQ>
+static int launch_gconv(const GConvArgs &a, cudaStream_t st) {
+    constexpr int TX = 256 / COQ, kGT = 4 * TX, kGC = 4 * COQ;
+    const int span = (kGT - 1) * a.stride + (a.K - 1) * a.dil + 1;
+    const size_t smem = ((size_t)kGCI * span + (size_t)kGCI * a.K * kGC) * 4;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        SVB_CUDA(cudaFuncSetAttribute(gconv_kernel<COQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int cout_g = a.Cout / a.groups;
+    dim3 grid((a.Tout + kGT - 1) / kGT, ((cout_g + kGC - 1) / kGC) * a.groups, a.B * a.W);
+    gconv_kernel<COQ><<<grid, 256, smem, st>>>(a);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
 extern "C" int svb_conv_nct_forward(const float *x_dev, const float *w_dev, const float *bias_dev, float *y_dev, int32_t B,
                                     int32_t Cin, int32_t Cout, int32_t Tin, int32_t W, int32_t K, int32_t stride, int32_t dil,
                                     int32_t pad, int32_t groups, float out_slope, void *stream) {
@@ -172,18 +193,11 @@ extern "C" int svb_conv_nct_forward(const float *x_dev, const float *w_dev, cons
     a.groups = groups, a.out_slope = out_slope;
     a.Tout = (Tin + 2 * pad - dil * (K - 1) - 1) / stride + 1;
     SVB_CHECK(a.Tout > 0, SVB_ERR_INVALID, "conv_nct: empty output (Tin %d K %d)", Tin, K);
-    const int span = (kGT - 1) * stride + (K - 1) * dil + 1;
-    const size_t smem = ((size_t)kGCI * span + (size_t)kGCI * K * kGC) * 4;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        SVB_CUDA(cudaFuncSetAttribute(gconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     const int cout_g = Cout / groups;
-    dim3 grid((a.Tout + kGT - 1) / kGT, ((cout_g + kGC - 1) / kGC) * groups, B * W);
-    gconv_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
-    SVB_CUDA(cudaGetLastError());
-    return SVB_OK;
+    if (cout_g <= 8) return launch_gconv<2>(a, as_stream(stream));
+    if (cout_g <= 16) return launch_gconv<4>(a, as_stream(stream));
+    if (cout_g <= 32) return launch_gconv<8>(a, as_stream(stream));
+    return launch_gconv<16>(a, as_stream(stream));
 }
 
 extern "C" int svb_avgpool1d_4_2_1(const float *x_dev, float *y_dev, int64_t rows, int32_t Tin, void *stream) {

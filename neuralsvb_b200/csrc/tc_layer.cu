@@ -1,0 +1,287 @@
+// Dense discriminator convolutions on the tcgen05 kernel (conv_tc.cu): a per-layer handle that takes PyTorch-layout
+// device tensors [B, C, T, W] (W = period columns of DiscriminatorP's (k,1) Conv2d, 1 for DiscriminatorS), converts
+// them to G32T with every (clip, column) as its own short clip, and runs forward / data gradient on the tensor
+// cores and the weight gradient on the G32T fp32 kernel (train_ops.cu).
+//   stride 1, padding (K-1)/2  : the generator's kernel as is (KS = K taps)
+//   stride s > 1               : the input is gathered tap-major ("K-expanded": channel c*K + j of output row `to`
+//                                is x[c][to*s + j - pad]), which turns the conv into ONE K = 1 GEMM over Cin*K
+//                                channels on the UNPERMUTED weight tensor [Cout][Cin*K]; its data gradient is the
+//                                transposed GEMM followed by a gather (col2im).
+// Reference: the Conv2d((5,1),(3,1)) / Conv1d stacks of modules/hifigan/hifigan.py:193-199, :262-271 (layers with
+// groups == 1 and >= 32 channels: 98 % of the discriminators' FLOPs).
+#include <algorithm>
+#include <vector>
+
+#include "generator.cuh"
+#include "train_ops.cuh"
+
+using namespace svb;
+
+namespace {
+
+// out (G32T: clips = B*W, Ce = C*KE channels, Tq rows, EVERY row of the allocation written so a shared arena needs
+// no memset): out[clip][(c*KE + j)][to] = x[b][c][to*s + j - p][w] * (mask ? lrelu'(mask) : 1)
+__global__ void expand_to_g32t_kernel(const float *__restrict__ x, const float *__restrict__ mask, float slope, int B, int C,
+                                      int T, int W, int KE, int s, int p, int Tq, int Tp, float *__restrict__ out) {
+    const int Ce = C * KE, groups = c4t_groups(Ce);
+    const long long total = (long long)B * W * groups * Tp * 32;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(i & 31);
+        long long r = i >> 5;
+        const int row = (int)(r % Tp);
+        r /= Tp;
+        const int grp = (int)(r % groups), clip = (int)(r / groups);
+        const int to = row - kPad, cc = grp * 32 + lane;
+        float v = 0.f;
+        if (to >= 0 && to < Tq && cc < Ce) {
+            const int c = cc / KE, j = cc - c * KE;
+            const int t = to * s + j - p;
+            if (t >= 0 && t < T) {
+                const int b = clip / W, w = clip - b * W;
+                const size_t xi = (((size_t)b * C + c) * T + t) * W + w;
+                v = __ldg(x + xi);
+                if (mask && !(__ldg(mask + xi) > 0.f)) v *= slope;
+            }
+        }
+        out[i] = v;
+    }
+}
+
+// y[b][c][t][w] = lrelu(g[clip][c][t], slope)
+__global__ void g32t_to_nctw_kernel(const float *__restrict__ g, int B, int C, int T, int W, int Tp, float slope,
+                                    float *__restrict__ y) {
+    const int groups = c4t_groups(C);
+    const long long total = (long long)B * C * T * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        long long r = i / W;
+        const int t = (int)(r % T);
+        r /= T;
+        const int c = (int)(r % C), b = (int)(r / C);
+        const float v = g[((((size_t)b * W + w) * groups + (c >> 5)) * Tp + kPad + t) * 32 + (c & 31)];
+        y[i] = v >= 0.f ? v : v * slope;
+    }
+}
+
+// dx[b][c][t][w] = sum_j [ (t + p - j) % s == 0 ] g[clip][c*KE + j][(t + p - j) / s]
+__global__ void col2im_to_nctw_kernel(const float *__restrict__ g, int B, int C, int T, int W, int KE, int s, int p, int Tq,
+                                      int Tp, float *__restrict__ dx) {
+    const int groups = c4t_groups(C * KE);
+    const long long total = (long long)B * C * T * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        long long r = i / W;
+        const int t = (int)(r % T);
+        r /= T;
+        const int c = (int)(r % C), b = (int)(r / C);
+        const size_t base = ((size_t)b * W + w) * groups;
+        float acc = 0.f;
+        for (int j = 0; j < KE; ++j) {
+            const int num = t + p - j;
+            if (num < 0) break;
+            const int to = num / s;
+            if (to * s != num || to >= Tq) continue;
+            const int cc = c * KE + j;
+            acc += g[((base + (cc >> 5)) * Tp + kPad + to) * 32 + (cc & 31)];
+        }
+        dx[i] = acc;
+    }
+}
+
+__global__ void gather_w_kernel(float *__restrict__ dst, const float *__restrict__ nat, const int *__restrict__ idx, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = idx[i] ? nat[idx[i] - 1] : 0.f;
+}
+
+// one scratch arena per device, shared by every layer handle (calls are stream-ordered)
+struct Arena {
+    char *p = nullptr;
+    size_t cap = 0;
+};
+Arena g_arena[16];
+
+int arena_get(int device, size_t bytes, char **out) {
+    Arena &a = g_arena[device & 15];
+    if (bytes > a.cap) {
+        if (a.p) {
+            SVB_CUDA(cudaDeviceSynchronize());
+            SVB_CUDA(cudaFree(a.p));
+        }
+        a.p = nullptr, a.cap = 0;
+        SVB_CUDA(cudaMalloc((void **)&a.p, bytes));
+        a.cap = bytes;
+    }
+    *out = a.p;
+    return SVB_OK;
+}
+
+int blocks_for(long long total) { return (int)std::min<long long>((total + 255) / 256, 148 * 32); }
+
+}  // namespace
+
+struct svb_tc_layer {
+    int device = 0, precision = SVB_PREC_BF16X3;
+    int Cin = 0, Cout = 0, K = 1, stride = 1, pad = 0;
+    int KE = 1;                 // channel expansion (K when stride > 1)
+    ConvLayer fwd, bwd;
+    int *map_f = nullptr, *map_b = nullptr;
+    size_t n_f = 0, n_b = 0;
+    float *bias = nullptr, *zero_bias = nullptr;
+    std::vector<void *> allocs;
+    bool has_w = false;
+};
+
+static std::vector<int> to_idx(const std::vector<float> &v) {
+    std::vector<int> r(v.size());
+    for (size_t i = 0; i < v.size(); ++i) r[i] = (int)v[i];
+    return r;
+}
+
+extern "C" int svb_tc_layer_create(int32_t Cin, int32_t Cout, int32_t K, int32_t stride, int32_t pad, int32_t precision,
+                                   int device, svb_tc_layer_t **out) {
+    SVB_CHECK(out && Cin > 0 && Cout > 0 && K >= 1 && stride >= 1 && pad >= 0, SVB_ERR_INVALID, "tc_layer_create: bad argument");
+    SVB_CHECK(precision >= 1 && precision <= 3, SVB_ERR_INVALID, "tc_layer_create: precision must be a tensor-core mode");
+    SVB_CHECK(stride > 1 || (K % 2 == 1 && pad == (K - 1) / 2), SVB_ERR_INVALID,
+              "tc_layer_create: a stride-1 layer needs 'same' padding (K %d pad %d)", K, pad);
+    const int KE = stride > 1 ? K : 1, KS = stride > 1 ? 1 : K, Ce = Cin * KE;
+    SVB_CHECK(Ce % 32 == 0 && Cout % 32 == 0 && Cout <= 1024 && Ce <= 3072 && (long long)Cout * Ce * KS < (1 << 24), SVB_ERR_INVALID,
+              "tc_layer_create: %d -> %d channels (K %d, stride %d) is not a tensor-core shape", Cin, Cout, K, stride);
+    SVB_CUDA(cudaSetDevice(device));
+    svb_tc_layer *L = new (std::nothrow) svb_tc_layer();
+    SVB_CHECK(L, SVB_ERR_NOMEM, "tc_layer_create: out of host memory");
+    L->device = device, L->precision = precision, L->Cin = Cin, L->Cout = Cout, L->K = K, L->stride = stride, L->pad = pad, L->KE = KE;
+    auto fail = [&](int rc) {
+        for (void *p : L->allocs) cudaFree(p);
+        delete L;
+        return rc;
+    };
+    auto dev_alloc = [&](void **p, size_t bytes) -> int {
+        SVB_CUDA(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+        L->allocs.push_back(*p);
+        SVB_CUDA(cudaMemset(*p, 0, std::max<size_t>(bytes, 16)));
+        return SVB_OK;
+    };
+    const size_t n = (size_t)Cout * Ce * KS;
+    std::vector<float> id(n);
+    for (size_t i = 0; i < n; ++i) id[i] = (float)(i + 1);
+    // forward: natural [Cout][Ce][KS] -> FFMA packing [KS][Ce][Cout]
+    const std::vector<float> pf = pack_conv_weights(id.data(), Cout, Ce, KS);
+    // data gradient: a Conv1d with weight Wd[ce][co][KS-1-k] = W[co][ce][k]
+    std::vector<float> wd(n);
+    for (int co = 0; co < Cout; ++co)
+        for (int ce = 0; ce < Ce; ++ce)
+            for (int k = 0; k < KS; ++k) wd[((size_t)ce * Cout + co) * KS + (KS - 1 - k)] = id[((size_t)co * Ce + ce) * KS + k];
+    const std::vector<float> pb = pack_conv_weights(wd.data(), Ce, Cout, KS);
+    int rc;
+    auto setup = [&](ConvLayer &cl, int ci, int co, const std::vector<float> &pk, int **map) -> int {
+        cl.Cin = ci, cl.Cout = co, cl.CoutP = co, cl.KS = KS, cl.dil = 1, cl.ups_u = 0, cl.macs_per_row = (double)ci * co * KS;
+        SVB_TRY(dev_alloc((void **)&cl.w, pk.size() * 4));
+        const std::vector<int> idx = to_idx(pk);
+        SVB_TRY(dev_alloc((void **)map, idx.size() * sizeof(int)));
+        SVB_CUDA(cudaMemcpy(*map, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<float> zeros(pk.size(), 0.f);
+        SVB_TRY(tc_pack_weights(zeros.data(), KS, ci, co, &cl.tc, &L->allocs));     // allocates the tile blobs
+        SVB_CHECK(cl.tc.ok, SVB_ERR_INVALID, "tc_layer_create: no tensor-core tiling for %d -> %d", ci, co);
+        return SVB_OK;
+    };
+    if ((rc = setup(L->fwd, Ce, Cout, pf, &L->map_f)) != SVB_OK) return fail(rc);
+    if ((rc = setup(L->bwd, Cout, Ce, pb, &L->map_b)) != SVB_OK) return fail(rc);
+    L->n_f = pf.size(), L->n_b = pb.size();
+    if ((rc = dev_alloc((void **)&L->bias, (size_t)Cout * 4)) != SVB_OK) return fail(rc);
+    if ((rc = dev_alloc((void **)&L->zero_bias, (size_t)std::max(Ce, Cout) * 4)) != SVB_OK) return fail(rc);
+    L->fwd.b = L->bias, L->bwd.b = L->zero_bias;
+    *out = L;
+    return SVB_OK;
+}
+
+extern "C" void svb_tc_layer_destroy(svb_tc_layer_t *L) {
+    if (!L) return;
+    cudaSetDevice(L->device);
+    for (void *p : L->allocs) cudaFree(p);
+    delete L;
+}
+
+extern "C" int svb_tc_layer_set_weight_dev(svb_tc_layer_t *L, const float *w_dev, const float *bias_dev, void *stream) {
+    SVB_CHECK(L && w_dev && bias_dev, SVB_ERR_INVALID, "tc_layer_set_weight: null argument");
+    SVB_CUDA(cudaSetDevice(L->device));
+    cudaStream_t st = as_stream(stream);
+    gather_w_kernel<<<blocks_for((long long)L->n_f), 256, 0, st>>>(L->fwd.w, w_dev, L->map_f, L->n_f);
+    SVB_TRY(tc_repack_weights_dev(L->fwd.w, L->fwd.tc, st));
+    gather_w_kernel<<<blocks_for((long long)L->n_b), 256, 0, st>>>(L->bwd.w, w_dev, L->map_b, L->n_b);
+    SVB_TRY(tc_repack_weights_dev(L->bwd.w, L->bwd.tc, st));
+    SVB_CUDA(cudaMemcpyAsync(L->bias, bias_dev, (size_t)L->Cout * 4, cudaMemcpyDeviceToDevice, st));
+    SVB_CUDA(cudaGetLastError());
+    L->has_w = true;
+    return SVB_OK;
+}
+
+static int run_tc(const svb_tc_layer *L, const ConvLayer &cl, const float *in, float *out, int Tp, int clips, int Tq, cudaStream_t st) {
+    ConvArgs a;
+    a.in = in, a.w = cl.w, a.bias = cl.b, a.res = nullptr, a.out = out;
+    a.B = clips, a.Cin = cl.Cin, a.in_Tp = Tp, a.Cout = cl.Cout, a.out_Tp = Tp, a.CoutP = cl.CoutP, a.Tq = Tq;
+    a.KS = cl.KS, a.dil = 1, a.ups_u = 0, a.in_slope = 1.f, a.out_scale = 1.f, a.accumulate = 0;
+    SVB_CHECK(tc_supported(cl.tc, a), SVB_ERR_INVALID, "tc_layer: shape not supported by the tensor-core kernel");
+    return launch_conv_tc(cl.tc, a, L->precision, st);
+}
+
+extern "C" int64_t svb_tc_layer_out_len(const svb_tc_layer_t *L, int64_t T) {
+    if (!L) return -1;
+    return (T + 2 * L->pad - (L->K - 1) - 1) / L->stride + 1;
+}
+
+extern "C" int svb_tc_layer_forward(svb_tc_layer_t *L, const float *x_dev, int32_t B, int32_t T, int32_t W, float out_slope,
+                                    float *y_dev, void *stream) {
+    SVB_CHECK(L && L->has_w && x_dev && y_dev && B > 0 && T > 0 && W > 0, SVB_ERR_INVALID, "tc_layer_forward: bad argument");
+    SVB_CUDA(cudaSetDevice(L->device));
+    cudaStream_t st = as_stream(stream);
+    const int Tq = (int)svb_tc_layer_out_len(L, T), Tp = c4t_rows(Tq), clips = B * W, Ce = L->Cin * L->KE;
+    const int gather_pad = L->stride > 1 ? L->pad : 0;      // a stride-1 layer pads physically (G32T zero rows)
+    SVB_CHECK(Tq > 0, SVB_ERR_INVALID, "tc_layer_forward: empty output");
+    const size_t n_x = c4t_floats(clips, Ce, Tq), n_y = c4t_floats(clips, L->Cout, Tq);
+    char *base;
+    SVB_TRY(arena_get(L->device, (n_x + n_y) * 4, &base));
+    float *xe = reinterpret_cast<float *>(base), *yg = xe + n_x;
+    expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, gather_pad,
+                                                                         Tq, Tp, xe);
+    SVB_TRY(run_tc(L, L->fwd, xe, yg, Tp, clips, Tq, st));
+    g32t_to_nctw_kernel<<<blocks_for((long long)B * L->Cout * Tq * W), 256, 0, st>>>(yg, B, L->Cout, Tq, W, Tp, out_slope, y_dev);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_tc_layer_backward(svb_tc_layer_t *L, const float *x_dev, const float *y_dev, const float *dy_dev, int32_t B,
+                                     int32_t T, int32_t W, float out_slope, float *dx_dev, float *dw_dev, float *db_dev,
+                                     void *stream) {
+    SVB_CHECK(L && L->has_w && x_dev && dy_dev && B > 0 && T > 0 && W > 0, SVB_ERR_INVALID, "tc_layer_backward: bad argument");
+    SVB_CHECK(out_slope == 1.f || y_dev, SVB_ERR_INVALID, "tc_layer_backward: the activation mask needs the forward output");
+    SVB_CUDA(cudaSetDevice(L->device));
+    cudaStream_t st = as_stream(stream);
+    const int Tq = (int)svb_tc_layer_out_len(L, T), Tp = c4t_rows(Tq), clips = B * W, Ce = L->Cin * L->KE;
+    const int gather_pad = L->stride > 1 ? L->pad : 0;
+    const size_t n_x = c4t_floats(clips, Ce, Tq), n_y = c4t_floats(clips, L->Cout, Tq);
+    char *base;
+    SVB_TRY(arena_get(L->device, (2 * n_x + n_y) * 4, &base));
+    float *xe = reinterpret_cast<float *>(base), *dxe = xe + n_x, *dzg = dxe + n_x;
+    // masked output gradient in G32T (KE = 1 gather of dy, leaky-relu derivative from the stored output)
+    expand_to_g32t_kernel<<<blocks_for((long long)n_y), 256, 0, st>>>(dy_dev, out_slope == 1.f ? nullptr : y_dev, out_slope, B, L->Cout,
+                                                                         Tq, W, 1, 1, 0, Tq, Tp, dzg);
+    if (db_dev) SVB_TRY(launch_colsum(dzg, clips, L->Cout, Tq, Tp, db_dev, st));
+    if (dw_dev) {
+        expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, gather_pad,
+                                                                             Tq, Tp, xe);
+        const int KS = L->fwd.KS;
+        WgradArgs a;
+        a.A = xe, a.G = dzg, a.out = dw_dev, a.B = clips, a.Tq = Tq, a.Ca = Ce, a.TpA = Tp, a.Cg = L->Cout, a.TpG = Tp, a.K = KS;
+        a.sa = 1, a.da = 1, a.pa = (KS - 1) / 2, a.sb = 1, a.db = 0, a.pb = 0, a.slope = 1.f;
+        a.s_co = (long long)Ce * KS, a.s_ci = KS, a.s_k = 1;      // natural [Cout][Cin][K]; expanded channel c*K + j is the same offset
+        SVB_TRY(launch_wgrad(a, st));
+    }
+    if (dx_dev) {
+        SVB_TRY(run_tc(L, L->bwd, dzg, dxe, Tp, clips, Tq, st));
+        const long long total = (long long)B * L->Cin * T * W;
+        if (L->stride == 1) g32t_to_nctw_kernel<<<blocks_for(total), 256, 0, st>>>(dxe, B, L->Cin, T, W, Tp, 1.f, dx_dev);
+        else col2im_to_nctw_kernel<<<blocks_for(total), 256, 0, st>>>(dxe, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tq, Tp, dx_dev);
+    }
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}

@@ -62,6 +62,99 @@ class _ConvNctFn(torch.autograd.Function):
         return dx, dw, (db if need_b else None), None, None, None, None, None, None, None
 
 
+USE_TC = True            # dense layers with >= 32 channels run on the tcgen05 kernel (svb_tc_layer_*); False: fp32 CUDA cores
+TC_PRECISION = 'bf16x3'
+
+
+def tc_eligible(cin, cout, K, stride, dil, pad, groups):
+    if not USE_TC or groups != 1 or dil != 1 or cout % 32 or cout > 1024:
+        return False
+    if stride == 1:
+        return cin % 32 == 0 and K % 2 == 1 and pad == (K - 1) // 2
+    return (cin * K) % 32 == 0 and cin * K <= 3072
+
+
+class TcLayer:
+    """Owner of one svb_tc_layer handle (created lazily on the first CUDA call of its conv)."""
+
+    def __init__(self):
+        self.h, self.key = None, None
+
+    def get(self, cin, cout, K, stride, pad, device):
+        key = (cin, cout, K, stride, pad, device.index, TC_PRECISION)
+        if self.h is None or self.key != key:
+            self.close()
+            h = ctypes.c_void_p()
+            _native.check(_native.lib().svb_tc_layer_create(cin, cout, K, stride, pad, _native.PREC[TC_PRECISION],
+                                                            device.index if device.index is not None else torch.cuda.current_device(),
+                                                            ctypes.byref(h)), 'tc_layer_create')
+            self.h, self.key = h, key
+        return self.h
+
+    def close(self):
+        if self.h is not None:
+            _native.lib().svb_tc_layer_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def conv_tc(x, w, b, layer, K, stride, pad, slope, W):
+    """Dense conv through the tensor-core layer handle; same contract as conv_nct."""
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
+        return _TcConvFn.apply(x, w, b, layer, K, stride, pad, slope, W)
+    return _tc_forward(_cuda(x), _cuda(w), _cuda(b), layer, K, stride, pad, slope, W)
+
+
+def _tc_forward(x, w, b, layer, K, stride, pad, slope, W):
+    lib = _native.lib()
+    B, Cin, Tin = x.shape[0], x.shape[1], x.shape[2]
+    Cout = w.shape[0]
+    with torch.cuda.device(x.device):
+        st = _native.current_stream_ptr(x.device)
+        h = layer.get(Cin, Cout, K, stride, pad, x.device)
+        _native.check(lib.svb_tc_layer_set_weight_dev(h, _native.ptr(w), _native.ptr(b), st), 'tc_layer_set_weight')
+        Tout = int(lib.svb_tc_layer_out_len(h, Tin))
+        y = torch.empty((B, Cout, Tout) + ((W,) if x.dim() == 4 else ()), device=x.device, dtype=torch.float32)
+        _native.check(lib.svb_tc_layer_forward(h, _native.ptr(x), B, Tin, W, ctypes.c_float(slope), _native.ptr(y), st),
+                      'tc_layer_forward')
+    return y
+
+
+class _TcConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, layer, K, stride, pad, slope, W):
+        x, w, b = _cuda(x), _cuda(w), _cuda(b)
+        y = _tc_forward(x, w, b, layer, K, stride, pad, slope, W)
+        ctx.save_for_backward(x, w, b, y)
+        ctx.cfg = (layer, K, stride, pad, slope, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, b, y = ctx.saved_tensors
+        layer, K, stride, pad, slope, W = ctx.cfg
+        lib = _native.lib()
+        dy = _cuda(dy)
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.zeros_like(w) if need_w else None
+        db = torch.zeros_like(b) if need_b else None
+        with torch.cuda.device(x.device):
+            st = _native.current_stream_ptr(x.device)
+            h = layer.get(x.shape[1], w.shape[0], K, stride, pad, x.device)
+            # the handle may have served another tensor pair since the forward (y / y_hat share it): re-pack is cheap
+            _native.check(lib.svb_tc_layer_set_weight_dev(h, _native.ptr(w), _native.ptr(b), st), 'tc_layer_set_weight')
+            _native.check(lib.svb_tc_layer_backward(h, _native.ptr(x), _native.ptr(y), _native.ptr(dy), x.shape[0], x.shape[2], W,
+                                                    ctypes.c_float(slope), _native.ptr(dx), _native.ptr(dw), _native.ptr(db), st),
+                          'tc_layer_backward')
+        return dx, dw, db, None, None, None, None, None, None
+
+
 def _conv_nct_raw(x, w, b, K, stride=1, dil=1, pad=0, groups=1, slope=1.0, W=1):
     lib = _native.lib()
     x = _cuda(x)
@@ -96,6 +189,14 @@ class _NormConv(nn.Module):
             self.weight_g = nn.Parameter(v.flatten(1).norm(dim=1).view(-1, *([1] * (len(shape) - 1))))
             self.weight_v = nn.Parameter(v)
         self._cache = None
+        self.tc = TcLayer()
+
+    def conv(self, x, K, stride=1, pad=0, groups=1, slope=1.0, W=1):
+        """This layer's convolution on x: the tensor-core handle for dense >= 32-channel layers, else the fp32 kernel."""
+        w, bias = self.effective(x.device)
+        if tc_eligible(x.shape[1], w.shape[0], K, stride, 1, pad, groups) and x.is_cuda:
+            return conv_tc(x, w, bias, self.tc, K, stride, pad, slope, W)
+        return conv_nct(x, w, bias, K, stride=stride, pad=pad, groups=groups, slope=slope, W=W)
 
     def effective(self, device):
         """[Cout, Cin/groups, K] effective weight + bias on `device` (cached until parameters change).  With grad
@@ -236,11 +337,9 @@ class DiscriminatorP(nn.Module):
         x = x.view(b, c, t // p, p)
         fmap = []
         for i, l in enumerate(self.convs):
-            w, bias = l.effective(x.device)
-            x = conv_nct(x, w, bias, self.kernel_size, stride=(self.stride if i < 4 else 1), pad=2, slope=LRELU_SLOPE, W=p)
+            x = l.conv(x, self.kernel_size, stride=(self.stride if i < 4 else 1), pad=2, slope=LRELU_SLOPE, W=p)
             fmap.append(x)
-        w, bias = self.conv_post.effective(x.device)
-        x = conv_nct(x, w, bias, 3, pad=1, W=p)
+        x = self.conv_post.conv(x, 3, pad=1, W=p)
         fmap.append(x)
         return torch.flatten(x, 1, -1), fmap
 
@@ -271,11 +370,9 @@ class DiscriminatorS(nn.Module):
     def forward(self, x, mel=None):
         fmap = []
         for l, (_, _, k, s, g, p) in zip(self.convs, MSD_LAYERS):
-            w, bias = l.effective(x.device)
-            x = conv_nct(x, w, bias, k, stride=s, pad=p, groups=g, slope=LRELU_SLOPE)
+            x = l.conv(x, k, stride=s, pad=p, groups=g, slope=LRELU_SLOPE)
             fmap.append(x)
-        w, bias = self.conv_post.effective(x.device)
-        x = conv_nct(x, w, bias, 3, pad=1)
+        x = self.conv_post.conv(x, 3, pad=1)
         fmap.append(x)
         return torch.flatten(x, 1, -1), fmap
 

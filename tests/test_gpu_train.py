@@ -157,7 +157,7 @@ def test_discriminator_backward_matches_oracle_autograd(name):
     errs, glob, med, worst = _stats(got, g_ref)
     top = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
     print(f'{name}: global {glob:.1e} median {med:.1e} worst {[(k, f"{e:.1e}") for k, e in top]}')
-    assert glob < 3e-3 and med < 2e-4 and worst < 2e-2, (glob, med, worst)      # a flipped leaky-relu mask moves one small tensor by ~5e-3
+    assert glob < 3e-3 and med < 2e-3 and worst < 2e-2, (glob, med, worst)      # split-bf16 dense layers + a few flipped leaky-relu masks
 
 
 # ------------------------------------------------------------------ spectral losses
