@@ -151,6 +151,9 @@ int svb_avgpool1d_4_2_1_backward(const float *dy_dev, float *dx_dev, int64_t row
 int svb_pad_reflect_right_backward(const float *dy_dev, float *dx_dev, int64_t rows, int32_t T, int32_t Tpad, void *stream);
 int svb_loss_grad(const float *a_dev, const float *b_dev, int32_t kind, float scale, float *da_dev, int64_t n,
                   int32_t accumulate, void *stream);
+/* same, with the factor scale * (*scale_dev) read on the device (the upstream gradient of an autograd node) */
+int svb_loss_grad_dev(const float *a_dev, const float *b_dev, int32_t kind, float scale, const float *scale_dev,
+                      float *da_dev, int64_t n, int32_t accumulate, void *stream);
 
 /* ---- dense discriminator convolutions on the tensor-core kernel -------------------------------------------------
  * One handle per Conv1d / Conv2d((k,1)) layer with groups == 1 (modules/hifigan/hifigan.py:193-199, :262-271):

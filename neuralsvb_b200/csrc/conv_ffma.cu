@@ -248,7 +248,7 @@ int launch_noise_conv_add(float *x, int B, int C, int T, int Tp, const float *ha
 
 // ------------------------------------------------------------------------------ conv_post + tanh
 __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const float4 *__restrict__ x, int C, int T, int Tp,
-                                                             const float4 *__restrict__ wq, float bias, int K,
+                                                             const float4 *__restrict__ wq, const float *__restrict__ bias, int K,
                                                              float slope, float *__restrict__ wav) {
     extern __shared__ float4 sm4[];
     const int cq_n = C >> 2, halo = (K - 1) / 2, rows = 256 + 2 * halo;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const float4 *__res
     __syncthreads();
     const int t = t0 + tid;
     if (t >= T) return;
-    float acc = bias;
+    float acc = __ldg(bias);
     for (int cq = 0; cq < cq_n; ++cq)
         for (int k = 0; k < K; ++k) {
             const float4 xv = xs[cq * rows + tid + k], wv = ws[cq * K + k];
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const float4 *__res
     wav[(size_t)b * T + t] = tanhf(acc);
 }
 
-int launch_conv_post_tanh(const float *x, int B, int C, int T, int Tp, const float *wq, float bias, int K, float slope,
+int launch_conv_post_tanh(const float *x, int B, int C, int T, int Tp, const float *wq, const float *bias, int K, float slope,
                           float *wav, cudaStream_t st) {
     const int rows = 256 + (K - 1);
     const size_t smem = (size_t)(C / 4) * (rows + K) * 16;

@@ -43,7 +43,7 @@ int launch_noise_conv_add(float *x, int B, int C, int T, int Tp, const float *ha
                           const float *nb, int K, int stride, int pad, cudaStream_t st);
 
 // wav[b][t] = tanh(bias + sum_{ci,k} w[ci][k] * lrelu(x[b][t+k-3][ci], slope))   (hifigan.py:165-167)
-int launch_conv_post_tanh(const float *x, int B, int C, int T, int Tp, const float *wq, float bias, int K,
+int launch_conv_post_tanh(const float *x, int B, int C, int T, int Tp, const float *wq, const float *bias_dev, int K,
                           float slope, float *wav, cudaStream_t st);
 
 // host-side weight packing (layer_api.cu)

@@ -222,7 +222,8 @@ __global__ void pad_reflect_right_bwd_kernel(const float *__restrict__ dy, float
 
 // element-wise loss gradients; kind: 0 L1 (sign(a-b)), 1 (a - 1), 2 a, 3 (a - b), 4 sign(ln a - ln b) / a
 __global__ void loss_grad_kernel(const float *__restrict__ a, const float *__restrict__ b, int kind, float scale,
-                                 float *__restrict__ da, long long n, int accumulate) {
+                                 const float *__restrict__ scale_dev, float *__restrict__ da, long long n, int accumulate) {
+    if (scale_dev) scale *= __ldg(scale_dev);          // upstream gradient / norms stay on the device: no host sync
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float av = a[i], bv = b ? b[i] : 0.f;
         float g;
@@ -350,7 +351,17 @@ extern "C" int svb_loss_grad(const float *a_dev, const float *b_dev, int32_t kin
     SVB_CHECK(a_dev && da_dev && n > 0 && kind >= 0 && kind <= 4 && (b_dev || kind == 1 || kind == 2), SVB_ERR_INVALID,
               "loss_grad: bad argument");
     const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-    loss_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a_dev, b_dev, kind, scale, da_dev, n, accumulate);
+    loss_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a_dev, b_dev, kind, scale, nullptr, da_dev, n, accumulate);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_loss_grad_dev(const float *a_dev, const float *b_dev, int32_t kind, float scale, const float *scale_dev,
+                                 float *da_dev, int64_t n, int32_t accumulate, void *stream) {
+    SVB_CHECK(a_dev && da_dev && scale_dev && n > 0 && kind >= 0 && kind <= 4 && (b_dev || kind == 1 || kind == 2), SVB_ERR_INVALID,
+              "loss_grad_dev: bad argument");
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    loss_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a_dev, b_dev, kind, scale, scale_dev, da_dev, n, accumulate);
     SVB_CUDA(cudaGetLastError());
     return SVB_OK;
 }

@@ -204,7 +204,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         {
             ProfScope ps(g, ns, "nsf source (4 kernels)", 4.0 * B * (T + (double)Tw * (noise ? 10 : 1)), 60.0 * B * Tw * 9);
             SVB_TRY(launch_nsf_source(f0, rand_ini, noise, seed, B, T, g->hop, (float)g->cfg.audio_sample_rate, g->lin_w,
-                                      g->lin_b, g->ws + bf.nsf, har, g->training ? F(bf.sines) : nullptr, ns, &l));
+                                      g->lin_b_dev, g->ws + bf.nsf, har, g->training ? F(bf.sines) : nullptr, ns, &l));
         }
         if (har_on_side) SVB_CUDA(cudaEventRecord(g->ev_chain[0], ns));
         g->last_launches += l;
@@ -280,7 +280,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
     // x = tanh(conv_post(leaky_relu(x)))   default slope 0.01   :165-167
     {
         ProfScope ps(g, st, "conv_post_tanh", 4.0 * B * Tin * (g->post_C + 1.0), 2.0 * B * (double)Tin * g->post_C * g->post_K);
-        SVB_TRY(launch_conv_post_tanh(x_in, B, g->post_C, Tin, Tin_p, g->post_wq, g->post_bias, g->post_K, 0.01f, wav, st));
+        SVB_TRY(launch_conv_post_tanh(x_in, B, g->post_C, Tin, Tin_p, g->post_wq, g->post_b_dev, g->post_K, 0.01f, wav, st));
     }
     g->last_launches += 1;
     g->last_flops += 2.0 * B * (double)Tin * g->post_C * g->post_K;
@@ -435,14 +435,15 @@ int svb::gen_build_layers(svb_gen *g) {
             for (int k = 0; k < 7; ++k)
                 for (int e = 0; e < 4; ++e) p[((size_t)cq * 7 + k) * 4 + e] = w->data[(size_t)(cq * 4 + e) * 7 + k];
         SVB_TRY(gen_upload(g, p, &g->post_wq));
-        g->post_bias = b->data[0], g->post_K = 7, g->post_C = cin;
+        SVB_TRY(gen_upload(g, b->data, &g->post_b_dev));
+        g->post_K = 7, g->post_C = cin;
     }
     if (c.use_pitch_embed) {   // m_source.l_linear: Linear(9, 1)   source.py:378
         const HostTensor *w, *b;
         SVB_TRY(gen_get_w(g, "m_source.l_linear.weight", {1, 9}, &w));
         SVB_TRY(gen_get_w(g, "m_source.l_linear.bias", {1}, &b));
         SVB_TRY(gen_upload(g, w->data, &g->lin_w));
-        g->lin_b = b->data[0];
+        SVB_TRY(gen_upload(g, b->data, &g->lin_b_dev));
     }
     return SVB_OK;
 }

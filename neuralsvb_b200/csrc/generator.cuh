@@ -82,10 +82,9 @@ struct svb_gen {
     svb::ConvLayer conv_pre;
     std::vector<svb::Stage> stages;
     float *post_wq = nullptr;
-    float post_bias = 0.f;
     int post_K = 7, post_C = 0;
     float *lin_w = nullptr;
-    float lin_b = 0.f;
+    float *lin_b_dev = nullptr;     // m_source.l_linear.bias [1]
     int hop = 1;
 
     // workspace

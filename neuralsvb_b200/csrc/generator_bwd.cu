@@ -160,7 +160,11 @@ int build_jobs(svb_gen *g) {
         SVB_TRY(add_job(g, "conv_post.weight", g->post_wq, m, nullptr));
         SVB_TRY(add_copy_job(g, "conv_post.weight", g->post_w_nat, (size_t)C * K));
     }
-    if (c.use_pitch_embed) SVB_TRY(add_copy_job(g, "m_source.l_linear.weight", g->lin_w, 9));
+    SVB_TRY(add_copy_job(g, "conv_post.bias", g->post_b_dev, 1));
+    if (c.use_pitch_embed) {
+        SVB_TRY(add_copy_job(g, "m_source.l_linear.weight", g->lin_w, 9));
+        SVB_TRY(add_copy_job(g, "m_source.l_linear.bias", g->lin_b_dev, 1));
+    }
     return SVB_OK;
 }
 
@@ -301,15 +305,6 @@ extern "C" int svb_gen_update_weights_dev(svb_gen_t *g, void *stream) {
         if (j.tc) SVB_TRY(tc_repack_weights_dev(j.dst, *j.tc, st));
     }
     SVB_CUDA(cudaGetLastError());
-    // the two scalars the kernels take by value
-    GradBuf *b;
-    SVB_TRY(nat_buffer(g, "conv_post.bias", &b));
-    SVB_CUDA(cudaMemcpyAsync(&g->post_bias, b->p, 4, cudaMemcpyDeviceToHost, st));
-    if (g->cfg.use_pitch_embed) {
-        SVB_TRY(nat_buffer(g, "m_source.l_linear.bias", &b));
-        SVB_CUDA(cudaMemcpyAsync(&g->lin_b, b->p, 4, cudaMemcpyDeviceToHost, st));
-    }
-    SVB_CUDA(cudaStreamSynchronize(st));
     g->dev_dirty = false;
     return SVB_OK;
 }

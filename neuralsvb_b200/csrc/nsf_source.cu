@@ -145,7 +145,7 @@ __global__ void nsf_chunk_scan_kernel(NsfDims d, double *__restrict__ csum) {
 // ---- kernel 4: synthesis + harmonic merge, one warp per (b, chunk) -----------------------------
 __global__ void nsf_synth_kernel(NsfDims d, const float *__restrict__ f0, const float *__restrict__ rand_ini,
                                  const float *__restrict__ noise, uint64_t seed, const double *__restrict__ base1,
-                                 const double *__restrict__ cbase, const float *__restrict__ lin_w, float lin_b,
+                                 const double *__restrict__ cbase, const float *__restrict__ lin_w, const float *__restrict__ lin_b,
                                  float *__restrict__ har, float *__restrict__ sines) {
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -174,7 +174,7 @@ __global__ void nsf_synth_kernel(NsfDims d, const float *__restrict__ f0, const 
         }
     }
 
-    float merged = lin_b;
+    float merged = __ldg(lin_b);
 #pragma unroll 1
     for (int k = 0; k < kH; ++k) {
         const int bk = b * kH + k;
@@ -201,7 +201,7 @@ size_t nsf_workspace_bytes(int B, int F, int U) {
 }
 
 int launch_nsf_source(const float *f0, const float *rand_ini, const float *noise, uint64_t seed, int B, int F, int U,
-                      float sr, const float *lin_w_dev, float lin_b, void *workspace, float *har, float *sines,
+                      float sr, const float *lin_w_dev, const float *lin_b_dev, void *workspace, float *har, float *sines,
                       cudaStream_t st, int *launches) {
     NsfDims d;
     d.B = B, d.F = F, d.U = U, d.T = F * U, d.nchunk = (d.T + 31) / 32, d.sr = sr;
@@ -223,7 +223,7 @@ int launch_nsf_source(const float *f0, const float *rand_ini, const float *noise
     {
         const long long threads = (long long)B * d.nchunk * 32;
         nsf_synth_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(d, f0, rand_ini, noise, seed, base1, csum,
-                                                                               lin_w_dev, lin_b, har, sines);
+                                                                               lin_w_dev, lin_b_dev, har, sines);
     }
     SVB_CUDA(cudaGetLastError());
     if (launches) *launches += 4;

@@ -219,6 +219,13 @@ class _NormConv(nn.Module):
         key = (str(device), self.bias._version, (self.weight_orig if self.spectral else self.weight_v)._version)
         if self._cache is not None and self._cache[0] == key:
             return self._cache[1], self._cache[2]
+        if wp.is_cuda and wp.device == device:           # parameters already on the device: fold there, no host round trip
+            with torch.no_grad():
+                eff = self._spectral_weight() if self.spectral else _WeightNormFn.apply(self.weight_v, self.weight_g)
+            eff = eff.detach().reshape(eff.shape[0], eff.shape[1], -1).contiguous()
+            b = self.bias.detach().float()
+            self._cache = (key, eff, b)
+            return eff, b
         lib = _native.lib()
         dev_idx = device.index if device.index is not None else torch.cuda.current_device()
         if self.spectral:
@@ -401,6 +408,11 @@ class MultiScaleDiscriminator(nn.Module):
 # ------------------------------------------------------------------ losses (device reductions)
 def pair_stats(a, b=None, want_log=False):
     """float64 [6] on the host: sum (a-b)^2, sum a^2, sum |ln a - ln b|, sum |a-b|, sum (1-a)^2, sum b^2."""
+    return pair_stats_dev(a, b, want_log).cpu()
+
+
+def pair_stats_dev(a, b=None, want_log=False):
+    """The same six sums as a float64 [6] DEVICE tensor (no host synchronisation: the training losses stay on the GPU)."""
     lib = _native.lib()
     a = _cuda(a)
     b = None if b is None else _cuda(b)
@@ -408,7 +420,7 @@ def pair_stats(a, b=None, want_log=False):
     with torch.cuda.device(a.device):
         _native.check(lib.svb_pair_stats(_native.ptr(a), _native.ptr(b), a.numel(), int(want_log), ctypes.c_void_p(out.data_ptr()),
                                          _native.current_stream_ptr(a.device)), 'pair_stats')
-    return out.cpu()
+    return out
 
 
 class _PairLossFn(torch.autograd.Function):
@@ -419,11 +431,10 @@ class _PairLossFn(torch.autograd.Function):
     def forward(ctx, a, b, kind):
         a = _cuda(a)
         b = None if b is None else _cuda(b)
-        s = pair_stats(a, b)
+        s = pair_stats_dev(a, b)
         ctx.kind = kind
         ctx.save_for_backward(a, b) if b is not None else ctx.save_for_backward(a)
-        val = {'l1': s[3], 'one': s[4], 'zero': s[1]}[kind] / a.numel()
-        return torch.tensor(float(val), device=a.device, dtype=torch.float32)
+        return (s[{'l1': 3, 'one': 4, 'zero': 1}[kind]] / a.numel()).float()
 
     @staticmethod
     def backward(ctx, gout):
@@ -431,21 +442,21 @@ class _PairLossFn(torch.autograd.Function):
         saved = ctx.saved_tensors
         a, b = saved[0], (saved[1] if len(saved) > 1 else None)
         n = a.numel()
-        go = float(gout)
+        go = gout.detach().float().contiguous()          # upstream gradient: read by the kernel, never brought to the host
         da = torch.empty_like(a)
         db = None
         with torch.cuda.device(a.device):
             st = _native.current_stream_ptr(a.device)
             if ctx.kind == 'l1':
-                _native.check(lib.svb_loss_grad(_native.ptr(a), _native.ptr(b), 0, ctypes.c_float(go / n), _native.ptr(da), n, 0, st),
-                              'loss_grad')
+                _native.check(lib.svb_loss_grad_dev(_native.ptr(a), _native.ptr(b), 0, ctypes.c_float(1.0 / n), _native.ptr(go),
+                                                    _native.ptr(da), n, 0, st), 'loss_grad')
                 if ctx.needs_input_grad[1]:
                     db = torch.empty_like(b)
-                    _native.check(lib.svb_loss_grad(_native.ptr(b), _native.ptr(a), 0, ctypes.c_float(go / n), _native.ptr(db), n, 0,
-                                                    st), 'loss_grad')
+                    _native.check(lib.svb_loss_grad_dev(_native.ptr(b), _native.ptr(a), 0, ctypes.c_float(1.0 / n), _native.ptr(go),
+                                                        _native.ptr(db), n, 0, st), 'loss_grad')
             else:
-                _native.check(lib.svb_loss_grad(_native.ptr(a), None, 1 if ctx.kind == 'one' else 2, ctypes.c_float(2.0 * go / n),
-                                                _native.ptr(da), n, 0, st), 'loss_grad')
+                _native.check(lib.svb_loss_grad_dev(_native.ptr(a), None, 1 if ctx.kind == 'one' else 2, ctypes.c_float(2.0 / n),
+                                                    _native.ptr(go), _native.ptr(da), n, 0, st), 'loss_grad')
         return (da if ctx.needs_input_grad[0] else None), db, None
 
 

@@ -31,28 +31,27 @@ class _StftLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_mag, y_mag):
-        from neuralsvb_b200.modules.hifigan.discriminators import pair_stats
-        s = pair_stats(y_mag, x_mag, want_log=True)
-        ctx.norms = (float(s[0]) ** 0.5, float(s[1]) ** 0.5)
-        ctx.save_for_backward(x_mag, y_mag)
-        dev = x_mag.device
-        return (torch.tensor(ctx.norms[0] / ctx.norms[1], device=dev, dtype=torch.float32),
-                torch.tensor(float(s[2]) / y_mag.numel(), device=dev, dtype=torch.float32))
+        from neuralsvb_b200.modules.hifigan.discriminators import pair_stats_dev
+        s = pair_stats_dev(y_mag, x_mag, want_log=True)           # stays on the device: no host synchronisation
+        dnorm, ynorm = s[0].sqrt(), s[1].sqrt()
+        ctx.save_for_backward(x_mag, y_mag, (dnorm * ynorm).clamp_min(1e-30))
+        return (dnorm / ynorm).float(), (s[2] / y_mag.numel()).float()
 
     @staticmethod
     def backward(ctx, g_sc, g_mag):
         lib = _native.lib()
-        x, y = ctx.saved_tensors
+        x, y, norms = ctx.saved_tensors
         n = x.numel()
         dx = torch.empty_like(x)
-        dnorm, ynorm = ctx.norms
+        s_sc = (g_sc.double() / norms).float().contiguous()      # device scalars: the kernels read them in place
+        s_mag = g_mag.detach().float().contiguous()
         with torch.cuda.device(x.device):
             st = _native.current_stream_ptr(x.device)
             # d/dx ||y - x|| / ||y|| = (x - y) / (||y - x|| ||y||) ;  d/dx mean |ln y - ln x| = sign(ln x - ln y) / (n x)
-            _native.check(lib.svb_loss_grad(_native.ptr(x), _native.ptr(y), 3, ctypes.c_float(float(g_sc) / max(dnorm * ynorm, 1e-30)),
-                                            _native.ptr(dx), n, 0, st), 'loss_grad')
-            _native.check(lib.svb_loss_grad(_native.ptr(x), _native.ptr(y), 4, ctypes.c_float(float(g_mag) / n), _native.ptr(dx), n, 1,
-                                            st), 'loss_grad')
+            _native.check(lib.svb_loss_grad_dev(_native.ptr(x), _native.ptr(y), 3, ctypes.c_float(1.0), _native.ptr(s_sc),
+                                                _native.ptr(dx), n, 0, st), 'loss_grad')
+            _native.check(lib.svb_loss_grad_dev(_native.ptr(x), _native.ptr(y), 4, ctypes.c_float(1.0 / n), _native.ptr(s_mag),
+                                                _native.ptr(dx), n, 1, st), 'loss_grad')
         return dx, None
 
 
