@@ -249,7 +249,8 @@ typedef enum svb_spec_out {
     SVB_OUT_LOG10_MEL = 0,      /* log10(max(eps, mel_basis @ |X|))              data_gen_utils.py:125-134   */
     SVB_OUT_LN_MEL = 1,         /* ln(max(eps, mel_basis @ sqrt(|X|^2 + 1e-9)))  mel_utils.py:74-76,23-24     */
     SVB_OUT_MAG = 2,            /* sqrt(max(|X|^2, floor))                       losses/stft_loss.py:31       */
-    SVB_OUT_MAG_RAW = 3         /* |X|                                           data_gen_utils.py:125        */
+    SVB_OUT_MAG_RAW = 3,        /* |X|                                           data_gen_utils.py:125        */
+    SVB_OUT_MEL_MAG = 4         /* mel_basis @ sqrt(max(|X|^2, floor)), no log   parallel_wavegan/stft_loss.py:40-47 (use_mel_loss) */
 } svb_spec_out;
 
 typedef struct svb_stft_config {

@@ -23,7 +23,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 SVB_MAX_UPS, SVB_MAX_RBK, SVB_MAX_DIL = 8, 4, 4
 PREC = {'fp32': 0, 'tf32': 1, 'tf32x3': 2, 'bf16x3': 3}
 PAD_CENTER_ZERO, PAD_CENTER_REFLECT, PAD_HALF_REFLECT = 0, 1, 2
-OUT_LOG10_MEL, OUT_LN_MEL, OUT_MAG, OUT_MAG_RAW = 0, 1, 2, 3
+OUT_LOG10_MEL, OUT_LN_MEL, OUT_MAG, OUT_MAG_RAW, OUT_MEL_MAG = 0, 1, 2, 3, 4
 
 
 class GenConfig(ctypes.Structure):

@@ -108,12 +108,12 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(StftArgs a) {
     const int frame = blockIdx.x, b = blockIdx.y;
     load_frame_fft(a, re, im, twc, tws, frame, b);
 
-    const bool want_mel = a.out_kind == SVB_OUT_LOG10_MEL || a.out_kind == SVB_OUT_LN_MEL;
+    const bool want_mel = a.out_kind == SVB_OUT_LOG10_MEL || a.out_kind == SVB_OUT_LN_MEL || a.out_kind == SVB_OUT_MEL_MAG;
     for (int i = tid; i < a.n_bins; i += 256) {
         const float p = re[i] * re[i] + im[i] * im[i];
         float m;
         if (a.out_kind == SVB_OUT_LN_MEL) m = sqrtf(p + 1e-9f);           // mel_utils.py:74
-        else if (a.out_kind == SVB_OUT_MAG) m = sqrtf(fmaxf(p, a.eps));   // stft_loss.py:31
+        else if (a.out_kind == SVB_OUT_MAG || a.out_kind == SVB_OUT_MEL_MAG) m = sqrtf(fmaxf(p, a.eps));   // stft_loss.py:31
         else m = sqrtf(p);                                                // np.abs, data_gen_utils.py:125
         if (want_mel) mag[i] = m;
         else {
@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(StftArgs a) {
         if (lane == 0) {
             float v;
             if (a.out_kind == SVB_OUT_LOG10_MEL) v = log10f(fmaxf(a.eps, acc));   // data_gen_utils.py:134
+            else if (a.out_kind == SVB_OUT_MEL_MAG) v = acc;                      // parallel_wavegan/stft_loss.py:46 (no log)
             else v = logf(fmaxf(acc, a.eps));                                     // mel_utils.py:23-24
             const size_t o = a.frames_major ? ((size_t)b * a.frames + frame) * a.n_mels + m
                                             : ((size_t)b * a.n_mels + m) * a.frames + frame;
@@ -163,13 +164,13 @@ __global__ void __launch_bounds__(256) stft_mel_bwd_kernel(StftArgs a, StftBwdAr
     const int frame = blockIdx.x, b = blockIdx.y;
     load_frame_fft(a, re, im, twc, tws, frame, b);
 
-    const bool want_mel = a.out_kind == SVB_OUT_LOG10_MEL || a.out_kind == SVB_OUT_LN_MEL;
+    const bool want_mel = a.out_kind == SVB_OUT_LOG10_MEL || a.out_kind == SVB_OUT_LN_MEL || a.out_kind == SVB_OUT_MEL_MAG;
     constexpr int kMaxPer = 9;        // bins per thread for n_fft <= 4096
     float zr[kMaxPer], zi[kMaxPer];
     if (want_mel) {
         for (int i = tid; i < a.n_bins; i += 256) {
             const float p = re[i] * re[i] + im[i] * im[i];
-            mag[i] = a.out_kind == SVB_OUT_LN_MEL ? sqrtf(p + 1e-9f) : sqrtf(p);
+            mag[i] = a.out_kind == SVB_OUT_LN_MEL ? sqrtf(p + 1e-9f) : (a.out_kind == SVB_OUT_MEL_MAG ? sqrtf(fmaxf(p, a.eps)) : sqrtf(p));
         }
         __syncthreads();
         const int lane = tid & 31, warp = tid >> 5;
@@ -182,7 +183,9 @@ __global__ void __launch_bounds__(256) stft_mel_bwd_kernel(StftArgs a, StftBwdAr
             if (lane == 0) {
                 const size_t o = a.frames_major ? ((size_t)b * a.frames + frame) * a.n_mels + m
                                                 : ((size_t)b * a.n_mels + m) * a.frames + frame;
-                float d = acc >= a.eps ? __ldg(g.dout + o) / acc : 0.f;          // d log(max(mel, eps))
+                float d;
+                if (a.out_kind == SVB_OUT_MEL_MAG) d = __ldg(g.dout + o);
+                else d = acc >= a.eps ? __ldg(g.dout + o) / acc : 0.f;           // d log(max(mel, eps))
                 if (a.out_kind == SVB_OUT_LOG10_MEL) d *= 0.4342944819032518f;
                 dmel[m] = d;
             }
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(256) stft_mel_bwd_kernel(StftArgs a, StftBwdAr
                 dm = 0.f;
                 for (int k = 0; k < a.n_mels; ++k) dm = fmaf(__ldg(a.mel_basis + (size_t)k * a.n_bins + i), dmel[k], dm);
                 m = mag[i];
+                if (a.out_kind == SVB_OUT_MEL_MAG && p < a.eps) dm = 0.f;        // clamp(min) floor of the magnitude
             } else {
                 const size_t o = a.frames_major ? ((size_t)b * a.frames + frame) * a.n_bins + i
                                                 : ((size_t)b * a.n_bins + i) * a.frames + frame;
@@ -273,7 +277,7 @@ static int validate_stft(const svb_stft_config *cfg, int64_t n, bool need_mel) {
               "stft: n_fft %d must be a power of two in [64, 4096]", cfg->n_fft);
     SVB_CHECK(cfg->hop > 0 && cfg->win > 0 && cfg->win <= cfg->n_fft, SVB_ERR_INVALID,
               "stft: bad hop %d / win %d", cfg->hop, cfg->win);
-    SVB_CHECK(cfg->pad_mode >= 0 && cfg->pad_mode <= 2 && cfg->out_kind >= 0 && cfg->out_kind <= 3, SVB_ERR_INVALID,
+    SVB_CHECK(cfg->pad_mode >= 0 && cfg->pad_mode <= 2 && cfg->out_kind >= 0 && cfg->out_kind <= 4, SVB_ERR_INVALID,
               "stft: bad pad_mode / out_kind");
     SVB_CHECK(n >= 1, SVB_ERR_INVALID, "stft: empty waveform");
     if (cfg->pad_mode != SVB_PAD_CENTER_ZERO) {
@@ -287,7 +291,7 @@ static int validate_stft(const svb_stft_config *cfg, int64_t n, bool need_mel) {
 
 extern "C" int svb_stft_forward(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n,
                                 const float *mel_basis_dev, float *out_dev, void *stream) {
-    const bool want_mel = cfg && (cfg->out_kind == SVB_OUT_LOG10_MEL || cfg->out_kind == SVB_OUT_LN_MEL);
+    const bool want_mel = cfg && (cfg->out_kind == SVB_OUT_LOG10_MEL || cfg->out_kind == SVB_OUT_LN_MEL || cfg->out_kind == SVB_OUT_MEL_MAG);
     SVB_TRY(validate_stft(cfg, n, want_mel));
     SVB_CHECK(wav_dev && out_dev && B > 0, SVB_ERR_INVALID, "stft: null buffer or empty batch");
     SVB_CHECK(!want_mel || mel_basis_dev, SVB_ERR_INVALID, "stft: mel output needs mel_basis_dev");
@@ -347,7 +351,7 @@ extern "C" int64_t svb_wav2spec_host(const svb_stft_config *cfg, const float *wa
 
 extern "C" int svb_stft_backward(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n,
                                  const float *mel_basis_dev, const float *dout_dev, float *dwav_dev, void *stream) {
-    const bool want_mel = cfg && (cfg->out_kind == SVB_OUT_LOG10_MEL || cfg->out_kind == SVB_OUT_LN_MEL);
+    const bool want_mel = cfg && (cfg->out_kind == SVB_OUT_LOG10_MEL || cfg->out_kind == SVB_OUT_LN_MEL || cfg->out_kind == SVB_OUT_MEL_MAG);
     SVB_TRY(validate_stft(cfg, n, want_mel));
     SVB_CHECK(wav_dev && dout_dev && dwav_dev && B > 0, SVB_ERR_INVALID, "stft_backward: null buffer or empty batch");
     SVB_CHECK(!want_mel || mel_basis_dev, SVB_ERR_INVALID, "stft_backward: mel output needs mel_basis_dev");

@@ -498,6 +498,13 @@ def discriminator_loss(disc_real_outputs, disc_generated_outputs):
     return r / n, g / n
 
 
+def cond_discriminator_loss(outputs):
+    """mean over discriminators of mean dg^2  (hifigan.py:350-356)."""
+    if _diff(*outputs):
+        return sum(_PairLossFn.apply(dg, None, 'zero') for dg in outputs) / len(outputs)
+    return sum(float(pair_stats(dg)[1]) / dg.numel() for dg in outputs) / len(outputs)
+
+
 def generator_loss(disc_outputs):
     """mean over discriminators of mean (1 - dg)^2  (hifigan.py:359-365)."""
     if _diff(*disc_outputs):

@@ -21,6 +21,28 @@ def stft(x, fft_size, hop_size, win_length, window=None):
     return StftFn.apply(x, cfg, None, (B, frames, fft_size // 2 + 1))
 
 
+_mel_cache = {}
+
+
+def stft_mel(x, fft_size, hop_size, win_length):
+    """Mel-projected STFT magnitudes [B, frames, 80] of the ``use_mel_loss`` variant
+    (modules/parallel_wavegan/stft_loss.py:40-47: ``mag @ librosa.filters.mel(22050, fft_size, 80).T``, no log),
+    fused in the STFT kernel (output kind MEL_MAG)."""
+    from neuralsvb_b200.modules.hifigan.mel_utils import StftFn
+    from neuralsvb_b200.utils import audio
+    if not x.is_cuda:
+        raise RuntimeError('stft needs a CUDA tensor: there is no CPU fallback')
+    lib = _native.lib()
+    key = (int(fft_size), str(x.device))
+    if key not in _mel_cache:
+        hp = {'audio_sample_rate': 22050, 'fft_size': int(fft_size), 'audio_num_mel_bins': 80, 'fmin': 0, 'fmax': 22050 // 2}
+        _mel_cache[key] = torch.from_numpy(audio.build_mel_basis(hp).copy()).float().to(x.device)
+    B, n = x.shape
+    cfg = (int(fft_size), int(hop_size), int(win_length), _native.PAD_CENTER_REFLECT, _native.OUT_MEL_MAG, 0, 80, 1, 1e-7)
+    frames = int(lib.svb_stft_num_frames(ctypes.byref(_native.StftConfig(*cfg)), n))
+    return StftFn.apply(x, cfg, _mel_cache[key], (B, frames, 80))
+
+
 MR_STFT = ((1024, 120, 600), (2048, 240, 1200), (512, 50, 240))       # losses/stft_loss.py:113-115
 
 
@@ -55,22 +77,24 @@ class _StftLossFn(torch.autograd.Function):
         return dx, None
 
 
-def stft_loss(x, y, fft_size, shift_size, win_length):
+def stft_loss(x, y, fft_size, shift_size, win_length, use_mel_loss=False):
     """(spectral convergence ||Y - X||_F / ||Y||_F, log-magnitude L1 mean |ln Y - ln X|) of one resolution
     (STFTLoss.forward, losses/stft_loss.py:89-106); magnitudes from the fused STFT kernel, reductions on the device.
     Python floats without grad; differentiable scalars w.r.t. the predicted signal ``x`` when it requires grad."""
     from neuralsvb_b200.modules.hifigan.discriminators import pair_stats
-    x_mag, y_mag = stft(x, fft_size, shift_size, win_length), stft(y.detach(), fft_size, shift_size, win_length)
+    f = stft_mel if use_mel_loss else stft
+    x_mag, y_mag = f(x, fft_size, shift_size, win_length), f(y.detach(), fft_size, shift_size, win_length)
     if torch.is_grad_enabled() and x_mag.requires_grad:
         return _StftLossFn.apply(x_mag, y_mag)
     s = pair_stats(y_mag, x_mag, want_log=True)
     return float(s[0]) ** 0.5 / float(s[1]) ** 0.5, float(s[2]) / y_mag.numel()
 
 
-def multi_resolution_stft_loss(x, y, resolutions=MR_STFT):
-    """MultiResolutionSTFTLoss.forward (losses/stft_loss.py:130-153): mean over resolutions of (sc, mag)."""
+def multi_resolution_stft_loss(x, y, resolutions=MR_STFT, use_mel_loss=False):
+    """MultiResolutionSTFTLoss.forward (losses/stft_loss.py:130-153; modules/parallel_wavegan/stft_loss.py:55-100 with
+    ``use_mel_loss``): mean over resolutions of (sc, mag)."""
     sc, mag = 0.0, 0.0
     for fs, ss, wl in resolutions:
-        s, m = stft_loss(x, y, fs, ss, wl)
+        s, m = stft_loss(x, y, fs, ss, wl, use_mel_loss)
         sc, mag = sc + s, mag + m
     return sc / len(resolutions), mag / len(resolutions)

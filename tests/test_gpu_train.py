@@ -171,19 +171,19 @@ def test_mel_and_mr_stft_loss_backward_match_oracle_autograd():
     hp = S.hifigan_config()
     y = S.make_wave_batch(2, 8192, seed=U.SEED)
     x0 = (y + 0.05 * S.make_wave_batch(2, 8192, seed=U.SEED + 1)).clamp(-1, 1)
-    for which in ('mel', 'stft'):
+    for which in ('mel', 'stft', 'stft_mel'):
         xr = x0.clone().requires_grad_(True)
         if which == 'mel':
             ref = F.l1_loss(O.mel_spectrogram(xr, hp), O.mel_spectrogram(y, hp))
         else:
-            sc, mag = O.mr_stft_loss(xr, y)
+            sc, mag = O.mr_stft_loss(xr, y, use_mel_loss=which == 'stft_mel')
             ref = sc + mag
         ref.backward()
         xc = x0.cuda().requires_grad_(True)
         if which == 'mel':
             got = D.l1_loss(mel_spectrogram(xc, hp), mel_spectrogram(y.cuda(), hp))
         else:
-            sc, mag = multi_resolution_stft_loss(xc, y.cuda())
+            sc, mag = multi_resolution_stft_loss(xc, y.cuda(), use_mel_loss=which == 'stft_mel')
             got = sc + mag
         got.backward()
         assert abs(float(got) - float(ref)) <= 1e-3 * abs(float(ref))
