@@ -381,6 +381,7 @@ extern "C" int svb_gen_backward(svb_gen_t *g, const float *dwav_dev, void *strea
         a.A = x, a.G = gy, a.out = dw, a.B = B, a.Tq = Tq, a.Ca = C_in, a.TpA = Tp, a.Cg = C_out, a.TpG = Tp, a.K = K;
         a.sa = 1, a.da = dil, a.pa = (K - 1) / 2 * dil, a.sb = 1, a.db = 0, a.pb = 0, a.slope = slope;
         a.s_co = (long long)C_in * K, a.s_ci = K, a.s_k = 1;
+        a.allow_tc = g->cfg.precision != SVB_PREC_FP32;
         SVB_TRY(launch_wgrad(a, st));
         SVB_TRY(launch_colsum(gy, B, C_out, Tq, Tp, db, st));
         g->bwd_launches += 2;

@@ -274,6 +274,7 @@ extern "C" int svb_tc_layer_backward(svb_tc_layer_t *L, const float *x_dev, cons
         a.A = xe, a.G = dzg, a.out = dw_dev, a.B = clips, a.Tq = Tq, a.Ca = Ce, a.TpA = Tp, a.Cg = L->Cout, a.TpG = Tp, a.K = KS;
         a.sa = 1, a.da = 1, a.pa = (KS - 1) / 2, a.sb = 1, a.db = 0, a.pb = 0, a.slope = 1.f;
         a.s_co = (long long)Ce * KS, a.s_ci = KS, a.s_k = 1;      // natural [Cout][Cin][K]; expanded channel c*K + j is the same offset
+        a.allow_tc = 1;
         SVB_TRY(launch_wgrad(a, st));
     }
     if (dx_dev) {

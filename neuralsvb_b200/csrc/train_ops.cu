@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(256) nsf_linear_bwd_kernel(const float *__rest
 int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
     SVB_CHECK(a.A && a.G && a.out && a.B > 0 && a.Tq > 0 && a.K >= 1, SVB_ERR_INVALID, "wgrad: bad argument");
     SVB_CHECK(a.pa <= kPad && a.pb <= kPad, SVB_ERR_INVALID, "wgrad: padding %d / %d exceeds the %d-row halo", a.pa, a.pb, kPad);
+    if (a.allow_tc && wgrad_tc_supported(a)) return launch_wgrad_tc(a, st);
     const int units_per_b = (a.Tq + kWgRows - 1) / kWgRows;
     const int TA = a.Ca > 32 ? 64 : 32, TG = a.Cg > 32 ? 64 : 32;
     const int na = (a.Ca + TA - 1) / TA, ng = (a.Cg + TG - 1) / TG;

@@ -17,8 +17,11 @@ struct WgradArgs {
     int sa, da, pa, sb, db, pb;
     float slope;                // leaky-relu slope applied to A on load (1 = identity)
     long long s_ci, s_co, s_k;
+    int allow_tc = 0;           // 1: stride-1 shapes may run on the tcgen05 kernel (wgrad_tc.cu, split-bf16 operands)
 };
 int launch_wgrad(const WgradArgs &a, cudaStream_t st);
+bool wgrad_tc_supported(const WgradArgs &a);
+int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st);
 
 // db[c] += sum_{b,t<T} G[b][t][c]
 int launch_colsum(const float *G, int B, int C, int T, int Tp, float *db, cudaStream_t st);
