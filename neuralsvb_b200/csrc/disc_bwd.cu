@@ -138,10 +138,12 @@ __global__ void __launch_bounds__(256) gconv_dgrad_kernel(GBwdArgs a) {
     }
 }
 
-constexpr int kWT = 64, kWC = 64, kWCI = 4;      // weight-gradient tile: 64 outputs x 64 couts x 4 cins, all K taps
+constexpr int kWT = 64;      // outputs per shared-memory tile of the weight-gradient kernel
 
-template <int K>
+// Block = kWC output channels (the group's width, up to 64) x kWCI = 256 / kWC input channels, all K taps per thread.
+template <int K, int kWC>
 __global__ void __launch_bounds__(256) gconv_wgrad_kernel(GBwdArgs a, int to_tiles) {
+    constexpr int kWCI = 256 / kWC;
     extern __shared__ float sm[];
     const int span = (kWT - 1) * a.stride + (K - 1) * a.dil + 1;
     float *zs = sm;                               // [kWT][kWC + 1]
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) gconv_wgrad_kernel(GBwdArgs a, int to_til
     const int ci_c = r % ci_chunks;
     r /= ci_chunks;
     const int co_t = r % co_tiles, g = r / co_tiles;
-    const int tid = threadIdx.x, co = tid & 63, cis = tid >> 6;
+    const int tid = threadIdx.x, co = tid % kWC, cis = tid / kWC;
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
@@ -245,8 +247,9 @@ __global__ void loss_grad_kernel(const float *__restrict__ a, const float *__res
 
 using namespace svb;
 
-template <int K>
-static int launch_wgrad_k(const GBwdArgs &a, cudaStream_t st) {
+template <int K, int kWC>
+static int launch_wgrad_kc(const GBwdArgs &a, cudaStream_t st) {
+    constexpr int kWCI = 256 / kWC;
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
     const int co_tiles = (cout_g + kWC - 1) / kWC, ci_chunks = (cin_g + kWCI - 1) / kWCI;
     const int to_tiles = (a.Tout + kWT - 1) / kWT;
@@ -257,9 +260,17 @@ static int launch_wgrad_k(const GBwdArgs &a, cudaStream_t st) {
     const size_t smem = ((size_t)kWT * (kWC + 1) + (size_t)kWCI * span) * 4;
     SVB_CHECK(smem <= 48 * 1024, SVB_ERR_INVALID, "conv_nct_backward: stride %d / kernel %d too large", a.stride, K);
     SVB_CHECK(tiles <= 65535, SVB_ERR_INVALID, "conv_nct_backward: too many weight tiles");
-    gconv_wgrad_kernel<K><<<dim3(ns, (unsigned)tiles), 256, smem, st>>>(a, to_tiles);
+    gconv_wgrad_kernel<K, kWC><<<dim3(ns, (unsigned)tiles), 256, smem, st>>>(a, to_tiles);
     SVB_CUDA(cudaGetLastError());
     return SVB_OK;
+}
+
+template <int K>
+static int launch_wgrad_k(const GBwdArgs &a, cudaStream_t st) {
+    const int cout_g = a.Cout / a.groups;
+    if (cout_g <= 16) return launch_wgrad_kc<K, 16>(a, st);
+    if (cout_g <= 32) return launch_wgrad_kc<K, 32>(a, st);
+    return launch_wgrad_kc<K, 64>(a, st);
 }
 
 template <int STRIDE, int CIQ>
