@@ -280,6 +280,12 @@ int svb_stft_forward(const svb_stft_config *cfg, const float *wav_dev, int32_t B
 int svb_stft_backward(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n, const float *mel_basis_dev,
                       const float *dout_dev, float *dwav_dev, void *stream);
 
+/* Spectral-subtraction post-filter of the vocoder output (vocoders/vocoder_utils.py:7-15, applied by
+ * vocoders/hifigan.py:66-69 when hparams['vocoder_denoise_c'] > 0):  librosa.stft(n_fft, hop, win, pad 'constant') ->
+ * max(|X| - v, 0) with the phase kept -> librosa.istft(hop, win).  wav [B, n] -> out [B, hop * (n / hop)] (device).
+ * Only n_fft / hop / win of cfg are read. */
+int svb_denoise(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n, float v, float *out_dev, void *stream);
+
 /* PWG.wav2spec / process_utterance (vocoders/pwg.py:105-122, data_gen_utils.py:93-147) from HOST
  * memory: wav_host [n] -> mel_host [frames, n_mels] (log10), wav_out_host [frames*hop] (zero padded
  * on the right, audio.librosa_pad_lr, utils/audio.py:67-76).  mel_basis_host [n_mels, n_fft/2+1].

@@ -252,6 +252,79 @@ __global__ void __launch_bounds__(256) stft_mel_bwd_kernel(StftArgs a, StftBwdAr
     }
 }
 
+// Spectral-subtraction post-filter (vocoders/vocoder_utils.py:7-15): per frame STFT -> |X| - v clipped at 0, phase kept
+// -> inverse real FFT -> window -> overlap-add; a second kernel divides by the window sum-square (librosa.istft) and
+// trims the centre padding.
+__global__ void __launch_bounds__(256) denoise_frames_kernel(StftArgs a, float v, float *__restrict__ acc, long long out_len) {
+    extern __shared__ float smem[];
+    float *re = smem;
+    float *im = re + a.n_fft;
+    float *twc = im + a.n_fft;
+    float *tws = twc + a.n_fft / 2;
+    __shared__ float edge[2];         // Re Z_0, Re Z_{N/2}
+    const int tid = threadIdx.x, N = a.n_fft;
+    const int frame = blockIdx.x, b = blockIdx.y;
+    load_frame_fft(a, re, im, twc, tws, frame, b);
+    constexpr int kMaxPer = 9;
+    float zr[kMaxPer], zi[kMaxPer];
+    {
+        int j = 0;
+        for (int i = tid; i < a.n_bins; i += 256, ++j) {
+            const float r = re[i], q = im[i];
+            const float m = sqrtf(r * r + q * q);
+            const float sc = m > 0.f ? fmaxf(m - v, 0.f) / m : 0.f;
+            zr[j] = sc * r, zi[j] = sc * q;
+            if (i == 0) edge[0] = zr[j];
+            if (i == N / 2) edge[1] = zr[j];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += 256) re[i] = 0.f, im[i] = 0.f;
+    __syncthreads();
+    {
+        int j = 0;
+        for (int i = tid; i < a.n_bins; i += 256, ++j) {
+            const int br = __brev((unsigned)i) >> (32 - a.log2n);
+            re[br] = zr[j], im[br] = zi[j];
+        }
+    }
+    __syncthreads();
+    fft_radix2(re, im, twc, tws, N, a.log2n, -1.f);
+    // irfft_n = (2 Re sum_{k<=N/2} Z_k e^{+i..} - Re Z_0 - (-1)^n Re Z_{N/2}) / N
+    const int wl = (N - a.win) / 2;
+    const long long start = (long long)frame * a.hop - N / 2;
+    float *out = acc + (size_t)b * out_len;
+    for (int i = tid; i < N; i += 256) {
+        const int wi = i - wl;
+        if (wi < 0 || wi >= a.win) continue;
+        const long long s = start + i;
+        if (s < 0 || s >= out_len) continue;
+        const float x = (2.f * re[i] - edge[0] - ((i & 1) ? -edge[1] : edge[1])) / (float)N;
+        const float hann = 0.5f - 0.5f * cospif(2.0f * (float)wi / (float)a.win);
+        atomicAdd(out + s, hann * x);
+    }
+}
+
+__global__ void denoise_norm_kernel(float *__restrict__ y, long long out_len, int B, int N, int hop, int win, int frames) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * out_len) return;
+    const long long s = i % out_len;
+    const int wl = (N - win) / 2;
+    // frames f with 0 <= s + N/2 - f*hop < N
+    const long long p = s + N / 2;
+    long long f_hi = p / hop, f_lo = (p - N + hop) / hop;       // ceil((p - N + 1) / hop)
+    if (p - N + 1 <= 0) f_lo = 0;
+    if (f_hi > frames - 1) f_hi = frames - 1;
+    float wss = 0.f;
+    for (long long f = f_lo; f <= f_hi; ++f) {
+        const int wi = (int)(p - f * hop) - wl;
+        if (wi < 0 || wi >= win) continue;
+        const float h = 0.5f - 0.5f * cospif(2.0f * (float)wi / (float)win);
+        wss += h * h;
+    }
+    if (wss > 1.1754944e-38f) y[i] /= wss;
+}
+
 static int ilog2(int n) {
     int l = 0;
     while ((1 << l) < n) ++l;
@@ -372,6 +445,36 @@ extern "C" int svb_stft_backward(const svb_stft_config *cfg, const float *wav_de
         configured = smem;
     }
     stft_mel_bwd_kernel<<<dim3(a.frames, B), 256, smem, as_stream(stream)>>>(a, g);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_denoise(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int64_t n, float v, float *out_dev,
+                           void *stream) {
+    svb_stft_config c;
+    SVB_CHECK(cfg && wav_dev && out_dev && B > 0 && v >= 0.f, SVB_ERR_INVALID, "denoise: bad argument");
+    c = *cfg;
+    c.pad_mode = SVB_PAD_CENTER_ZERO, c.out_kind = SVB_OUT_MAG_RAW, c.clamp_input = 0;
+    SVB_TRY(validate_stft(&c, n, false));
+    StftArgs a;
+    a.wav = wav_dev, a.mel_basis = nullptr, a.out = nullptr, a.n = n;
+    a.n_fft = c.n_fft, a.log2n = ilog2(c.n_fft), a.hop = c.hop, a.win = c.win;
+    a.n_bins = c.n_fft / 2 + 1, a.n_mels = 0;
+    a.frames = (int)svb_stft_num_frames(&c, n);
+    a.pad_mode = c.pad_mode, a.out_kind = c.out_kind, a.clamp_input = 0, a.frames_major = 1, a.eps = 0.f;
+    const long long out_len = (long long)c.hop * (a.frames - 1);      // librosa.istft length (centre padding trimmed)
+    SVB_CHECK(out_len > 0, SVB_ERR_INVALID, "denoise: signal shorter than one hop");
+    cudaStream_t st = as_stream(stream);
+    SVB_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)B * out_len * sizeof(float), st));
+    const size_t smem = (size_t)(3 * a.n_fft) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        SVB_CUDA(cudaFuncSetAttribute(denoise_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    denoise_frames_kernel<<<dim3(a.frames, B), 256, smem, st>>>(a, v, out_dev, out_len);
+    const long long tot = (long long)B * out_len;
+    denoise_norm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(out_dev, out_len, B, c.n_fft, c.hop, c.win, a.frames);
     SVB_CUDA(cudaGetLastError());
     return SVB_OK;
 }

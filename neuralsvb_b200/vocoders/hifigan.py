@@ -131,9 +131,9 @@ class HifiGAN(BaseVocoder):
                     g, mels.ctypes.data_as(ctypes.c_void_p),
                     None if f0s is None else f0s.ctypes.data_as(ctypes.c_void_p),
                     ctypes.c_uint64(seed), B, T, out.ctypes.data_as(ctypes.c_void_p), st), 'spec2wav')
-        if hparams.get('vocoder_denoise_c', 0.0) > 0:
-            raise NotImplementedError('vocoder_denoise_c > 0 (spectral-subtraction post-filter, '
-                                      'vocoders/vocoder_utils.py) is outside the B200 hot path')
+        if hparams.get('vocoder_denoise_c', 0.0) > 0:                  # vocoders/hifigan.py:66-69
+            from neuralsvb_b200.vocoders.vocoder_utils import denoise
+            out = np.stack([denoise(o, v=hparams['vocoder_denoise_c']) for o in out])
         return out
 
     @staticmethod

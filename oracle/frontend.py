@@ -92,6 +92,37 @@ def stft_librosa(y, n_fft, hop_length, win_length=None, pad_mode='constant'):
     return np.fft.rfft(win[:, None] * frames, axis=0).astype(np.complex64)
 
 
+def istft_librosa(stft_matrix, hop_length, win_length=None):
+    """librosa.istft(stft_matrix, hop_length, win_length, window='hann', center=True, length=None) (librosa 0.8.0,
+    core/spectrum.py): per-frame irfft * padded window, overlap-add, division by the window sum-square where it is
+    above float32 tiny, centre padding n_fft//2 trimmed from both ends."""
+    n_fft = 2 * (stft_matrix.shape[0] - 1)
+    if win_length is None:
+        win_length = n_fft
+    win = hann_periodic(win_length)
+    lpad = (n_fft - win_length) // 2
+    win = np.pad(win, (lpad, n_fft - win_length - lpad))
+    n_frames = stft_matrix.shape[1]
+    expected = n_fft + hop_length * (n_frames - 1)
+    y = np.zeros(expected, dtype=np.float32)
+    wss = np.zeros(expected, dtype=np.float32)
+    frames = np.fft.irfft(stft_matrix, n=n_fft, axis=0)
+    for i in range(n_frames):
+        y[i * hop_length:i * hop_length + n_fft] += (win * frames[:, i]).astype(np.float32)
+        wss[i * hop_length:i * hop_length + n_fft] += (win ** 2).astype(np.float32)
+    nz = wss > np.finfo(np.float32).tiny
+    y[nz] /= wss[nz]
+    return y[n_fft // 2:expected - n_fft // 2]
+
+
+def denoise(wav, v, fft_size, hop_size, win_size):
+    """vocoders/vocoder_utils.py:7-15."""
+    spec = stft_librosa(wav, fft_size, hop_size, win_size, pad_mode='constant')
+    spec_m = np.clip(np.abs(spec) - v, a_min=0, a_max=None)
+    spec_a = np.angle(spec)
+    return istft_librosa(spec_m * np.exp(1j * spec_a), hop_size, win_size)
+
+
 # ---------------------------------------------------------------- utils/audio.py helpers
 def librosa_pad_lr(x, fsize, fshift, pad_sides=1):
     """utils/audio.py:67-76."""

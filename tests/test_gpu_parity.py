@@ -194,3 +194,17 @@ def test_tf32_fast_mode_error(gold):
     err = U.rms(y[:, ::stride], gold['generator']['hop256_t16/y_sub'])
     print(f'1xTF32 waveform RMS error {err:.3e}')
     assert err < 5 * WAV_RMS_TOL
+
+
+# ------------------------------------------------------------------ post-filter
+@pytest.mark.parametrize('win', [512, 1024])
+def test_denoise_matches_oracle(win):
+    """vocoder_denoise_c post-filter (vocoders/vocoder_utils.py:7-15) on the fused STFT / inverse-FFT kernels."""
+    from neuralsvb_b200.vocoders.vocoder_utils import denoise
+    wav = S.make_clip(256 * 60, seed=U.SEED)
+    hp = dict(fft_size=1024, hop_size=256, win_size=win)
+    got = denoise(wav, v=0.1, hp=hp)
+    ref = FE.denoise(wav, 0.1, 1024, 256, win)
+    assert got.shape == ref.shape == (256 * 60,)
+    assert np.abs(got - ref).max() < 2e-5, np.abs(got - ref).max()
+    assert U.rms(got, wav) > 1e-3            # the filter did change the signal

@@ -252,3 +252,58 @@ def test_vocoder_train_step_matches_oracle_wiring():
     errs, glob, med, worst = _stats(got, gd_ref)
     print(f'D step: loss {float(ld):.4f} (oracle {float(loss_d):.4f}) grads global {glob:.1e} median {med:.1e} worst {worst:.1e}')
     assert glob < 1e-2 and med < 1e-3, (glob, med, worst)
+
+
+# ------------------------------------------------------------------ call patterns of a training loop
+def _train_model(h, prec='fp32'):
+    m = HifiGanGenerator(h, precision=prec)
+    m.load_state_dict(S.make_generator_state_dict(h, U.SEED), strict=True)
+    return m.cuda().train()
+
+
+@pytest.mark.parametrize('B,T', [(1, 1), (3, 5), (1, 130)])
+def test_backward_ragged_shapes_fp32(B, T):
+    """One frame, odd batch, more than one 256-row tile per clip at the first stage: exact (fp32) gradient parity."""
+    h = S.small_config(True)
+    sd = S.make_generator_state_dict(h, U.SEED)
+    mel, f0 = S.make_mel_f0(B, T, U.SEED)
+    ri, nz = S.make_nsf_noise(B, T * 16, U.SEED)
+    cot = torch.randn(B, 1, T * 16, generator=torch.Generator().manual_seed(3))
+    _, g_ref = _oracle_grads(h, sd, mel, f0, ri, nz, cot)
+    m = _train_model(h)
+    (m(mel.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda()) * cot.cuda()).sum().backward()
+    errs, glob, med, worst = _stats({k: p.grad.cpu() for k, p in m.named_parameters()}, g_ref)
+    assert worst < 2e-4, (worst, sorted(errs.items(), key=lambda kv: -kv[1])[:3])
+
+
+def test_backward_is_repeatable_and_accumulates_like_autograd():
+    """Two forward/backward passes without zero_grad double the gradients (torch semantics); the native buffers are
+    cleared per backward, so a second call does not see the first one's atomics."""
+    h = S.small_config(True)
+    mel, f0 = S.make_mel_f0(2, 24, U.SEED)
+    ri, nz = S.make_nsf_noise(2, 24 * 16, U.SEED)
+    m = _train_model(h)
+    args = (mel.cuda(), f0.cuda())
+    kw = dict(rand_ini=ri.cuda(), noise=nz.cuda())
+    m(*args, **kw).pow(2).mean().backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m(*args, **kw).pow(2).mean().backward()
+    for k, p in m.named_parameters():
+        assert torch.allclose(p.grad, 2 * g1[k], rtol=2e-4, atol=1e-10), k
+    m.zero_grad()
+    m(*args, **kw).pow(2).mean().backward()
+    for k, p in m.named_parameters():
+        assert torch.allclose(p.grad, g1[k], rtol=2e-4, atol=1e-10), k
+
+
+def test_backward_without_training_forward_fails_loudly():
+    import ctypes
+    from neuralsvb_b200 import _native
+    h = S.small_config(True)
+    m = _train_model(h).eval()
+    mel, f0 = S.make_mel_f0(1, 8, U.SEED)
+    with torch.no_grad():
+        m(mel.cuda(), f0.cuda())
+    dy = torch.zeros(1, 1, 8 * 16, device='cuda')
+    rc = _native.lib().svb_gen_backward(m.native_handle(), _native.ptr(dy), None)
+    assert rc != 0 and b'training' in _native.lib().svb_last_error()

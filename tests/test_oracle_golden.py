@@ -104,3 +104,16 @@ def test_discriminators_and_gan_losses_match_reference(golden_dir, name):
         assert np.abs(gg.numpy() - g[f'{name}/logit_g{i}']).max() < 2e-5 * max(1.0, np.abs(g[f'{name}/logit_g{i}']).max())
         for j, f in enumerate(fr[i]):
             assert tuple(f.shape) == tuple(g[f'{name}/fmap_r{i}_{j}_shape'])
+
+
+def test_oracle_istft_round_trip_and_denoise_shape():
+    """oracle/frontend.istft_librosa (librosa 0.8.0 istft restated): STFT -> iSTFT reproduces the signal away from the
+    edges, and the denoise post-filter (vocoders/vocoder_utils.py:7-15) keeps the length hop * (len // hop)."""
+    import numpy as np
+    from neuralsvb_b200.utils import synthetic as S
+    from oracle import frontend as FE
+    w = S.make_clip(256 * 20, seed=1)
+    y = FE.istft_librosa(FE.stft_librosa(w, 1024, 256, 512), 256, 512)
+    assert y.shape == w.shape and np.abs(y[512:-512] - w[512:-512]).max() < 1e-6
+    d = FE.denoise(w, 0.1, 1024, 256, 512)
+    assert d.shape == w.shape and np.abs(d).max() < np.abs(w).max()
