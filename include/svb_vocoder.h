@@ -147,6 +147,13 @@ int svb_conv_nct_backward(const float *x_dev, const float *w_dev, const float *y
                           int32_t Cin, int32_t Cout, int32_t Tin, int32_t W, int32_t K, int32_t stride, int32_t dil,
                           int32_t pad, int32_t groups, float out_slope, float *dz_scratch_dev, float *dx_dev,
                           float *dw_dev, float *db_dev, void *stream);
+/* cond_net of the mel-conditioned ("use_cond") discriminators: ConvTranspose1d(C = 80, 1, K = 2*stride, stride,
+ * padding = stride/2) (modules/hifigan/hifigan.py:185-189, :257-260).  mel [B, C, T] -> y [B, (T-1)*stride - 2*pad + K];
+ * w [C, 1, K], bias [1] on the device.  backward ACCUMULATES dw / db (the mel is an input: no gradient). */
+int svb_cond_net_forward(const float *mel_dev, const float *w_dev, const float *bias_dev, int32_t B, int32_t C, int32_t T,
+                         int32_t K, int32_t stride, int32_t pad, float *y_dev, void *stream);
+int svb_cond_net_backward(const float *mel_dev, const float *dy_dev, int32_t B, int32_t C, int32_t T, int32_t K, int32_t stride,
+                          int32_t pad, float *dw_dev, float *db_dev, void *stream);
 int svb_avgpool1d_4_2_1_backward(const float *dy_dev, float *dx_dev, int64_t rows, int32_t Tin, void *stream);
 int svb_pad_reflect_right_backward(const float *dy_dev, float *dx_dev, int64_t rows, int32_t T, int32_t Tpad, void *stream);
 int svb_loss_grad(const float *a_dev, const float *b_dev, int32_t kind, float scale, float *da_dev, int64_t n,

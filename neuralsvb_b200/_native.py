@@ -108,6 +108,8 @@ _PROTOS = {
     'svb_conv_nct_backward': (ctypes.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
                                              ctypes.c_float, _P, _P, _P, _P, _P]),
     'svb_avgpool1d_4_2_1_backward': (ctypes.c_int, [_P, _P, _I64, _I32, _P]),
+    'svb_cond_net_forward': (ctypes.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    'svb_cond_net_backward': (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     'svb_pad_reflect_right_backward': (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _P]),
     'svb_loss_grad': (ctypes.c_int, [_P, _P, _I32, ctypes.c_float, _P, _I64, _I32, _P]),
     'svb_loss_grad_dev': (ctypes.c_int, [_P, _P, _I32, ctypes.c_float, _P, _P, _I64, _I32, _P]),

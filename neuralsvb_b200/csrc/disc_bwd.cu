@@ -242,10 +242,80 @@ __global__ void loss_grad_kernel(const float *__restrict__ a, const float *__res
     }
 }
 
+// cond_net of the mel-conditioned discriminators: ConvTranspose1d(C, 1, K, stride s, padding p) (hifigan.py:188,260)
+//   y[b][tau] = bias + sum_c sum_{t : 0 <= tau + p - t*s < K} mel[b][c][t] * w[c][tau + p - t*s]
+__global__ void cond_net_fwd_kernel(const float *__restrict__ mel, const float *__restrict__ w, const float *__restrict__ bias,
+                                    int C, int T, int K, int s, int p, long long Tout, float *__restrict__ y) {
+    const long long tau = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (tau >= Tout) return;
+    float acc = __ldg(bias);
+    const long long num = tau + p;
+    for (long long t = num / s; t >= 0; --t) {
+        const long long k = num - t * s;
+        if (k >= K) break;
+        if (t >= T) continue;
+        for (int c = 0; c < C; ++c) acc = fmaf(__ldg(mel + ((size_t)b * C + c) * T + t), __ldg(w + (size_t)c * K + k), acc);
+    }
+    y[(size_t)b * Tout + tau] = acc;
+}
+
+// dw[c][k] += sum_b sum_t mel[b][c][t] * dy[b][t*s - p + k] ; db += sum dy     (block = one channel, threads over k)
+__global__ void __launch_bounds__(256) cond_net_bwd_kernel(const float *__restrict__ mel, const float *__restrict__ dy, int B,
+                                                           int C, int T, int K, int s, int p, long long Tout,
+                                                           float *__restrict__ dw, float *__restrict__ db) {
+    const int c = blockIdx.x;
+    for (int k = threadIdx.x; k < K; k += 256) {
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b)
+            for (int t = 0; t < T; ++t) {
+                const long long tau = (long long)t * s - p + k;
+                if (tau >= 0 && tau < Tout) acc = fmaf(__ldg(mel + ((size_t)b * C + c) * T + t), __ldg(dy + (size_t)b * Tout + tau), acc);
+            }
+        atomicAdd(dw + (size_t)c * K + k, acc);
+    }
+    if (c == 0) {
+        __shared__ float red[8];
+        float v = 0.f;
+        for (long long i = threadIdx.x; i < (long long)B * Tout; i += 256) v += dy[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; ++i) t += red[i];
+            atomicAdd(db, t);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace svb
 
 using namespace svb;
+
+extern "C" int svb_cond_net_forward(const float *mel_dev, const float *w_dev, const float *bias_dev, int32_t B, int32_t C, int32_t T,
+                                    int32_t K, int32_t stride, int32_t pad, float *y_dev, void *stream) {
+    SVB_CHECK(mel_dev && w_dev && bias_dev && y_dev && B > 0 && C > 0 && T > 0 && K > 0 && stride > 0 && pad >= 0, SVB_ERR_INVALID,
+              "cond_net_forward: bad argument");
+    const long long Tout = (long long)(T - 1) * stride - 2 * pad + K;
+    SVB_CHECK(Tout > 0, SVB_ERR_INVALID, "cond_net_forward: empty output");
+    cond_net_fwd_kernel<<<dim3((unsigned)((Tout + 255) / 256), B), 256, 0, as_stream(stream)>>>(mel_dev, w_dev, bias_dev, C, T, K, stride,
+                                                                                               pad, Tout, y_dev);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_cond_net_backward(const float *mel_dev, const float *dy_dev, int32_t B, int32_t C, int32_t T, int32_t K,
+                                     int32_t stride, int32_t pad, float *dw_dev, float *db_dev, void *stream) {
+    SVB_CHECK(mel_dev && dy_dev && dw_dev && db_dev && B > 0 && C > 0 && T > 0 && K > 0 && stride > 0 && pad >= 0, SVB_ERR_INVALID,
+              "cond_net_backward: bad argument");
+    const long long Tout = (long long)(T - 1) * stride - 2 * pad + K;
+    cond_net_bwd_kernel<<<C, 256, 0, as_stream(stream)>>>(mel_dev, dy_dev, B, C, T, K, stride, pad, Tout, dw_dev, db_dev);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
 
 template <int K, int kWC>
 static int launch_wgrad_kc(const GBwdArgs &a, cudaStream_t st) {

@@ -8,7 +8,9 @@ backward is a CUDA kernel of csrc/disc_bwd.cu (conv data / weight / bias gradien
 AvgPool1d, reflect pad, weight norm, loss gradients): torch only chains the nodes.  The one exception is the
 spectral-norm re-parametrisation of MSD[0] (power iteration and sigma on the [Cout, Cin*K] weight matrix --
 parameter-side arithmetic, a few small matrix-vector products in torch).
-``use_cond=True`` (mel-conditioned discriminators, off in the shipped config) is not implemented.
+``use_cond=True`` (mel-conditioned discriminators, off in the shipped config): ``cond_net`` is the ConvTranspose1d
+kernel pair ``svb_cond_net_forward / svb_cond_net_backward``; ``hparams['hop_size']`` is read at construction like the
+reference does (hifigan.py:185-187, :292-301).
 """
 import ctypes
 
@@ -323,19 +325,65 @@ class _RowOpFn(torch.autograd.Function):
         return dx, None, None
 
 
+class _CondNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mel, w, b, t):
+        lib = _native.lib()
+        mel, w, b = _cuda(mel), _cuda(w), _cuda(b)
+        B, C, T = mel.shape
+        y = torch.empty(B, 1, T * t, device=mel.device, dtype=torch.float32)
+        with torch.cuda.device(mel.device):
+            _native.check(lib.svb_cond_net_forward(_native.ptr(mel), _native.ptr(w), _native.ptr(b), B, C, T, 2 * t, t, t // 2,
+                                                   _native.ptr(y), _native.current_stream_ptr(mel.device)), 'cond_net_forward')
+        ctx.save_for_backward(mel, w)
+        ctx.t = t
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _native.lib()
+        mel, w = ctx.saved_tensors
+        dy = _cuda(dy)
+        B, C, T = mel.shape
+        dw, db = torch.zeros_like(w), torch.zeros(1, device=mel.device, dtype=torch.float32)
+        with torch.cuda.device(mel.device):
+            _native.check(lib.svb_cond_net_backward(_native.ptr(mel), _native.ptr(dy), B, C, T, 2 * ctx.t, ctx.t, ctx.t // 2,
+                                                    _native.ptr(dw), _native.ptr(db), _native.current_stream_ptr(mel.device)),
+                          'cond_net_backward')
+        return None, dw, db, None
+
+
+class _CondNet(nn.Module):
+    """Parameters of ``cond_net = ConvTranspose1d(80, 1, 2t, stride=t, padding=t//2)`` (hifigan.py:188, :260)."""
+
+    def __init__(self, t, n_mel=80):
+        super().__init__()
+        self.t = int(t)
+        bound = 1.0 / (2 * self.t) ** 0.5
+        self.weight = nn.Parameter(torch.empty(n_mel, 1, 2 * self.t).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.empty(1).uniform_(-bound, bound))
+
+    def forward(self, mel):
+        return _CondNetFn.apply(mel, self.weight, self.bias, self.t)
+
+
 class DiscriminatorP(nn.Module):
     def __init__(self, period, kernel_size=5, stride=3, use_spectral_norm=False, use_cond=False, c_in=1):
         super().__init__()
+        self.use_cond = use_cond
         if use_cond:
-            raise NotImplementedError('use_cond discriminators are not on the shipped path')
+            from neuralsvb_b200.utils.hparams import hparams
+            self.cond_net = _CondNet(hparams['hop_size'])
+            c_in = 2
         self.period, self.kernel_size, self.stride = period, kernel_size, stride
         ch = [(c_in, 32), (32, 128), (128, 512), (512, 1024), (1024, 1024)]
         self.convs = nn.ModuleList([_NormConv((co, ci, kernel_size, 1), use_spectral_norm) for ci, co in ch])
         self.conv_post = _NormConv((1, 1024, 3, 1), use_spectral_norm)
 
     def forward(self, x, mel=None):
-        lib = _native.lib()
         x = _cuda(x)
+        if self.use_cond:
+            x = torch.cat([self.cond_net(mel), x], 1)                 # hifigan.py:204-206
         b, c, t = x.shape
         p = self.period
         if t % p != 0:                                   # reflect pad to a multiple of the period (:209-212)
@@ -368,14 +416,21 @@ class MultiPeriodDiscriminator(nn.Module):
 class DiscriminatorS(nn.Module):
     def __init__(self, use_spectral_norm=False, use_cond=False, upsample_rates=None, c_in=1):
         super().__init__()
+        self.use_cond = use_cond
         if use_cond:
-            raise NotImplementedError('use_cond discriminators are not on the shipped path')
+            t = 1
+            for u in upsample_rates:
+                t *= int(u)
+            self.cond_net = _CondNet(t)
+            c_in = 2
         self.convs = nn.ModuleList([_NormConv((co, (c_in if i == 0 else ci) // g, k), use_spectral_norm)
                                     for i, (ci, co, k, _, g, _) in enumerate(MSD_LAYERS)])
         self.conv_post = _NormConv((1, 1024, 3), use_spectral_norm)
 
     def forward(self, x, mel=None):
         fmap = []
+        if self.use_cond:
+            x = torch.cat([self.cond_net(mel), _cuda(x)], 1)          # hifigan.py:274-276
         for l, (_, _, k, s, g, p) in zip(self.convs, MSD_LAYERS):
             x = l.conv(x, k, stride=s, pad=p, groups=g, slope=LRELU_SLOPE)
             fmap.append(x)
@@ -391,8 +446,15 @@ def avg_pool_4_2_1(x):
 class MultiScaleDiscriminator(nn.Module):
     def __init__(self, use_cond=False, c_in=1):
         super().__init__()
-        self.discriminators = nn.ModuleList([DiscriminatorS(use_spectral_norm=True, c_in=c_in), DiscriminatorS(c_in=c_in),
-                                             DiscriminatorS(c_in=c_in)])
+        hop = 256
+        if use_cond:
+            from neuralsvb_b200.utils.hparams import hparams
+            hop = hparams['hop_size']
+        rates = [[4, 4, hop // 16], [4, 4, hop // 32], [4, 4, hop // 64]]          # hifigan.py:294-302
+        self.discriminators = nn.ModuleList([
+            DiscriminatorS(use_spectral_norm=True, use_cond=use_cond, upsample_rates=rates[0], c_in=c_in),
+            DiscriminatorS(use_cond=use_cond, upsample_rates=rates[1], c_in=c_in),
+            DiscriminatorS(use_cond=use_cond, upsample_rates=rates[2], c_in=c_in)])
 
     def forward(self, y, y_hat, mel=None):
         y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []

@@ -192,13 +192,22 @@ MSD_LAYERS = [(1, 128, 15, 1, 1, 7), (128, 128, 41, 2, 4, 20), (128, 256, 41, 2,
               (512, 1024, 41, 4, 16, 20), (1024, 1024, 41, 1, 16, 20), (1024, 1024, 5, 1, 1, 2)]
 
 
-def make_mpd_state_dict(seed=1234):
-    """MultiPeriodDiscriminator state_dict (use_cond=False): 5 x DiscriminatorP, weight-normed
-    Conv2d [Cout, Cin, 5, 1] (+ conv_post [1, 1024, 3, 1]) -- modules/hifigan/hifigan.py:181-235."""
-    rs = np.random.RandomState(seed + 101)
+def _cond_net(rs, sd, prefix, t):
+    """cond_net = ConvTranspose1d(80, 1, 2t, stride=t, padding=t//2), plain (hifigan.py:185-189, :257-260)."""
+    sd[prefix + 'cond_net.weight'] = _normal(rs, (80, 1, 2 * t), 0.3 / np.sqrt(80 * 2.0))
+    sd[prefix + 'cond_net.bias'] = _uniform(rs, (1,), 0.05)
+
+
+def make_mpd_state_dict(seed=1234, use_cond=False, hop=256):
+    """MultiPeriodDiscriminator state_dict: 5 x DiscriminatorP, weight-normed Conv2d [Cout, Cin, 5, 1]
+    (+ conv_post [1, 1024, 3, 1]) -- modules/hifigan/hifigan.py:181-235.  ``use_cond``: + cond_net, 2 input channels."""
+    rs = np.random.RandomState(seed + 101 + (1000 if use_cond else 0))
     sd = OrderedDict()
     for d in range(len(MPD_PERIODS)):
-        layers = [(f'convs.{i}', cin, cout, 5) for i, (cin, cout) in enumerate(_MPD_CH)] + [('conv_post', 1024, 1, 3)]
+        if use_cond:
+            _cond_net(rs, sd, f'discriminators.{d}.', hop)
+        layers = [(f'convs.{i}', (2 if use_cond and i == 0 else cin), cout, 5) for i, (cin, cout) in enumerate(_MPD_CH)] + \
+                 [('conv_post', 1024, 1, 3)]
         for name, cin, cout, k in layers:
             sd[f'discriminators.{d}.{name}.bias'] = _uniform(rs, (cout,), 0.05)
             g, v = _wn_pair(rs, (cout, cin, k, 1), 1.3 / np.sqrt(cin * k), (1, 2, 3))
@@ -206,14 +215,17 @@ def make_mpd_state_dict(seed=1234):
     return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v))) for k, v in sd.items())
 
 
-def make_msd_state_dict(seed=1234):
-    """MultiScaleDiscriminator state_dict (use_cond=False): discriminator 0 is spectral-normed
-    (weight_orig / weight_u / weight_v), 1 and 2 weight-normed -- modules/hifigan/hifigan.py:253-302."""
-    rs = np.random.RandomState(seed + 202)
+def make_msd_state_dict(seed=1234, use_cond=False, hop=256):
+    """MultiScaleDiscriminator state_dict: discriminator 0 is spectral-normed (weight_orig / weight_u / weight_v),
+    1 and 2 weight-normed -- modules/hifigan/hifigan.py:253-302.  ``use_cond``: + cond_net with stride
+    hop / 2**d (upsample_rates [4, 4, hop // (16 * 2**d)], :294-302), 2 input channels."""
+    rs = np.random.RandomState(seed + 202 + (1000 if use_cond else 0))
     sd = OrderedDict()
     for d in range(3):
-        layers = [(f'convs.{i}', cin, cout, k, g) for i, (cin, cout, k, _, g, _) in enumerate(MSD_LAYERS)] + \
-                 [('conv_post', 1024, 1, 3, 1)]
+        if use_cond:
+            _cond_net(rs, sd, f'discriminators.{d}.', hop // (2 ** d))
+        layers = [(f'convs.{i}', (2 if use_cond and i == 0 else cin), cout, k, g)
+                  for i, (cin, cout, k, _, g, _) in enumerate(MSD_LAYERS)] + [('conv_post', 1024, 1, 3, 1)]
         for name, cin, cout, k, groups in layers:
             cg = cin // groups
             sd[f'discriminators.{d}.{name}.bias'] = _uniform(rs, (cout,), 0.05)

@@ -137,13 +137,40 @@ def gen_discriminators():
     np.savez_compressed(os.path.join(OUT, 'discriminators.npz'), **out)
 
 
+def gen_discriminators_cond():
+    """use_cond=True variants (mel-conditioned cond_net, hifigan.py:185-189,204-206,257-260,274-276) from the reference
+    modules: logits and the GAN losses."""
+    R.install()
+    from utils.hparams import hparams as ref_hp
+    ref_hp['hop_size'] = 256
+    from modules.hifigan.hifigan import (MultiPeriodDiscriminator, MultiScaleDiscriminator, cond_discriminator_loss,
+                                         discriminator_loss, feature_loss, generator_loss)
+    out = {}
+    y = S.make_wave_batch(2, 8192, seed=SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=SEED + 5)[:, None]).clamp(-1, 1)
+    mel, _ = S.make_mel_f0(2, 32, SEED)
+    for name, cls, sd in (('mpd', MultiPeriodDiscriminator, S.make_mpd_state_dict(SEED, use_cond=True)),
+                          ('msd', MultiScaleDiscriminator, S.make_msd_state_dict(SEED, use_cond=True))):
+        m = cls(use_cond=True)
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        with torch.no_grad():
+            rs, gs, fr, fg = m(y, y_hat, mel)
+            out[f'{name}/losses'] = np.array([float(feature_loss(fr, fg)), *[float(v) for v in discriminator_loss(rs, gs)],
+                                              float(generator_loss(gs)), float(cond_discriminator_loss(gs))], np.float64)
+        for i, (r, g) in enumerate(zip(rs, gs)):
+            out[f'{name}/logit_r{i}'], out[f'{name}/logit_g{i}'] = r.numpy(), g.numpy()
+        print(name, out[f'{name}/losses'])
+    np.savez_compressed(os.path.join(OUT, 'discriminators_cond.npz'), **out)
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
-    which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators']
+    which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond']
     for w in which:
         globals()[f'gen_{w}']()
 

@@ -150,10 +150,20 @@ def generator_forward(w, h, mel, f0=None, rand_ini=None, noise=None, taps=None):
 
 
 # ------------------------------------------------------------------ discriminators
-def disc_p_forward(x, w, prefix, period):
-    """DiscriminatorP.forward (hifigan.py:202-223), use_cond=False.  ``w`` holds
-    folded Conv2d weights [Cout,Cin,k,1]."""
+def _cond(x, w, prefix, mel):
+    """cond_net + concat (hifigan.py:204-206, :274-276): x_mel = ConvTranspose1d(80, 1, 2t, t, t//2)(mel)."""
+    cw = w[f'{prefix}.cond_net.weight']
+    t = cw.shape[2] // 2
+    x_mel = F.conv_transpose1d(mel, cw, w[f'{prefix}.cond_net.bias'], stride=t, padding=t // 2)
+    return torch.cat([x_mel, x], 1)
+
+
+def disc_p_forward(x, w, prefix, period, mel=None):
+    """DiscriminatorP.forward (hifigan.py:202-223).  ``w`` holds folded Conv2d weights [Cout,Cin,k,1];
+    ``mel`` [B,80,T] switches on the use_cond branch."""
     fmap = []
+    if mel is not None:
+        x = _cond(x, w, prefix, mel)
     b, c, t = x.shape
     if t % period != 0:
         n_pad = period - (t % period)
@@ -174,12 +184,12 @@ def disc_p_forward(x, w, prefix, period):
 MPD_PERIODS = (2, 3, 5, 7, 11)                  # hifigan.py:229-235
 
 
-def mpd_forward(y, y_hat, w, prefix=''):
+def mpd_forward(y, y_hat, w, prefix='', mel=None):
     """MultiPeriodDiscriminator.forward (hifigan.py:237-250)."""
     y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
     for i, p in enumerate(MPD_PERIODS):
-        r, fr = disc_p_forward(y, w, f'{prefix}discriminators.{i}', p)
-        g, fg = disc_p_forward(y_hat, w, f'{prefix}discriminators.{i}', p)
+        r, fr = disc_p_forward(y, w, f'{prefix}discriminators.{i}', p, mel)
+        g, fg = disc_p_forward(y_hat, w, f'{prefix}discriminators.{i}', p, mel)
         y_d_rs.append(r), fmap_rs.append(fr), y_d_gs.append(g), fmap_gs.append(fg)
     return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
@@ -189,10 +199,12 @@ MSD_LAYERS = [  # (cin, cout, k, stride, groups, pad)   hifigan.py:262-270
     (512, 1024, 41, 4, 16, 20), (1024, 1024, 41, 1, 16, 20), (1024, 1024, 5, 1, 1, 2)]
 
 
-def disc_s_forward(x, w, prefix):
-    """DiscriminatorS.forward (hifigan.py:273-286), use_cond=False, effective
-    (already normalised) weights."""
+def disc_s_forward(x, w, prefix, mel=None):
+    """DiscriminatorS.forward (hifigan.py:273-286), effective (already normalised) weights; ``mel`` switches on
+    the use_cond branch."""
     fmap = []
+    if mel is not None:
+        x = _cond(x, w, prefix, mel)
     for i, (_, _, _, s, g, p) in enumerate(MSD_LAYERS):
         x = F.conv1d(x, w[f'{prefix}.convs.{i}.weight'], w[f'{prefix}.convs.{i}.bias'],
                      stride=s, padding=p, groups=g)
@@ -203,7 +215,7 @@ def disc_s_forward(x, w, prefix):
     return torch.flatten(x, 1, -1), fmap
 
 
-def msd_forward(y, y_hat, w, prefix=''):
+def msd_forward(y, y_hat, w, prefix='', mel=None):
     """MultiScaleDiscriminator.forward (hifigan.py:309-325): AvgPool1d(4,2,1)
     between scales (count_include_pad default True)."""
     y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
@@ -211,8 +223,8 @@ def msd_forward(y, y_hat, w, prefix=''):
         if i != 0:
             y = F.avg_pool1d(y, 4, 2, padding=1)
             y_hat = F.avg_pool1d(y_hat, 4, 2, padding=1)
-        r, fr = disc_s_forward(y, w, f'{prefix}discriminators.{i}')
-        g, fg = disc_s_forward(y_hat, w, f'{prefix}discriminators.{i}')
+        r, fr = disc_s_forward(y, w, f'{prefix}discriminators.{i}', mel)
+        g, fg = disc_s_forward(y_hat, w, f'{prefix}discriminators.{i}', mel)
         y_d_rs.append(r), fmap_rs.append(fr), y_d_gs.append(g), fmap_gs.append(fg)
     return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 

@@ -80,3 +80,43 @@ def test_generic_conv_edge_cases_against_torch():
     assert got.shape == ref.shape and (got - ref).abs().max() < 1e-4 * ref.abs().max()
     x = torch.randn(2, 1, 33, generator=g)
     assert torch.allclose(avg_pool_4_2_1(x.cuda()).cpu(), F.avg_pool1d(x, 4, 2, padding=1), atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['mpd', 'msd'])
+def test_cond_discriminators_forward_and_backward(golden_dir, name):
+    """use_cond=True: logits / losses against the reference fixture, parameter gradients (incl. cond_net) against
+    torch autograd through the oracle."""
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    from neuralsvb_b200.utils.hparams import hparams
+    hparams['hop_size'] = 256
+    g = np.load(os.path.join(golden_dir, 'discriminators_cond.npz'))
+    if name == 'mpd':
+        m, sd, fwd = D.MultiPeriodDiscriminator(use_cond=True), S.make_mpd_state_dict(SEED, use_cond=True), O.mpd_forward
+    else:
+        m, sd, fwd = D.MultiScaleDiscriminator(use_cond=True), S.make_msd_state_dict(SEED, use_cond=True), O.msd_forward
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().cuda()
+    y, y_hat = _signals()
+    mel, _ = S.make_mel_f0(2, 32, SEED)
+    with torch.no_grad():
+        rs, gs, fr, fg = m(y.cuda(), y_hat.cuda(), mel.cuda())
+        losses = [D.feature_loss(fr, fg), *D.discriminator_loss(rs, gs), D.generator_loss(gs), D.cond_discriminator_loss(gs)]
+    np.testing.assert_allclose(losses, g[f'{name}/losses'], rtol=2e-4)
+    for i, (r, gg) in enumerate(zip(rs, gs)):
+        ref_r, ref_g = g[f'{name}/logit_r{i}'], g[f'{name}/logit_g{i}']
+        assert np.abs(r.cpu().numpy() - ref_r).max() <= 5e-4 * np.abs(ref_r).max() + 1e-6
+        assert np.abs(gg.cpu().numpy() - ref_g).max() <= 5e-4 * np.abs(ref_g).max() + 1e-6
+    # gradients
+    is_buf = lambda k: k.endswith('weight_u') or (k.endswith('weight_v') and k[:-1] + 'orig' in sd)
+    p = {k: (v.clone() if is_buf(k) else v.clone().requires_grad_(True)) for k, v in sd.items()}
+    rs, gs, fr, fg = fwd(y, y_hat, O.fold_discriminator_weights(p), mel=mel)
+    dr, dg = O.discriminator_loss(rs, gs)
+    (dr + dg + O.feature_loss(fr, fg)).backward()
+    rs, gs, fr, fg = m(y.cuda(), y_hat.cuda(), mel.cuda())
+    dr, dg = D.discriminator_loss(rs, gs)
+    (dr + dg + D.feature_loss(fr, fg)).backward()
+    errs = {k: float((q.grad.cpu().double() - p[k].grad.double()).norm() / p[k].grad.double().norm().clamp_min(1e-30))
+            for k, q in m.named_parameters()}
+    cond = {k: e for k, e in errs.items() if 'cond_net' in k}
+    assert cond and max(cond.values()) < 5e-3, cond
+    assert float(np.median(list(errs.values()))) < 2e-3 and max(errs.values()) < 3e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:4]

@@ -117,3 +117,22 @@ def test_oracle_istft_round_trip_and_denoise_shape():
     assert y.shape == w.shape and np.abs(y[512:-512] - w[512:-512]).max() < 1e-6
     d = FE.denoise(w, 0.1, 1024, 256, 512)
     assert d.shape == w.shape and np.abs(d).max() < np.abs(w).max()
+
+
+@pytest.mark.parametrize('name', ['mpd', 'msd'])
+def test_cond_discriminators_match_reference(golden_dir, name):
+    """use_cond=True (mel-conditioned cond_net + 2 input channels): oracle vs the fixture the reference modules wrote."""
+    g = np.load(os.path.join(golden_dir, 'discriminators_cond.npz'))
+    sd = S.make_mpd_state_dict(SEED, use_cond=True) if name == 'mpd' else S.make_msd_state_dict(SEED, use_cond=True)
+    w = O.fold_discriminator_weights(sd)
+    y = S.make_wave_batch(2, 8192, seed=SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=SEED + 5)[:, None]).clamp(-1, 1)
+    mel, _ = S.make_mel_f0(2, 32, SEED)
+    with torch.no_grad():
+        rs, gs, fr, fg = (O.mpd_forward if name == 'mpd' else O.msd_forward)(y, y_hat, w, mel=mel)
+        losses = [float(O.feature_loss(fr, fg)), *[float(v) for v in O.discriminator_loss(rs, gs)], float(O.generator_loss(gs)),
+                  float(sum((dg ** 2).mean() for dg in gs) / len(gs))]
+    np.testing.assert_allclose(losses, g[f'{name}/losses'], rtol=2e-5)
+    for i, (r, gg) in enumerate(zip(rs, gs)):
+        assert np.abs(r.numpy() - g[f'{name}/logit_r{i}']).max() < 2e-5 * max(1.0, np.abs(g[f'{name}/logit_r{i}']).max())
+        assert np.abs(gg.numpy() - g[f'{name}/logit_g{i}']).max() < 2e-5 * max(1.0, np.abs(g[f'{name}/logit_g{i}']).max())
