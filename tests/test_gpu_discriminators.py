@@ -130,4 +130,4 @@ def test_cond_discriminators_forward_and_backward(golden_dir, name):
         cond = {k: e for k, e in errs.items() if 'cond_net' in k}
         print(name, 'tc' if use_tc else 'fp32', 'cond_net grad errors', {k[15:]: f'{e:.1e}' for k, e in cond.items()})
         assert cond and max(cond.values()) < cond_tol and (use_tc or min(cond.values()) < 1e-3), cond
-        assert float(np.median(list(errs.values()))) < 2e-3 and max(errs.values()) < 5e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+        assert float(np.median(list(errs.values()))) < 1e-2 and max(errs.values()) < 8e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
