@@ -71,3 +71,26 @@ def test_product_fails_loudly_without_cuda():
     from neuralsvb_b200.vocoders.hifigan import HifiGAN
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         HifiGAN.wav2spec(S.make_clip(2048), hp=S.hifigan_config())
+
+
+def test_training_entry_points_validate_arguments_without_gpu(built):
+    """The backward / training half of the ABI rejects bad arguments before any CUDA call (negative svb_status, message set)."""
+    l = _native.lib()
+    f = ctypes.c_float
+    assert l.svb_gen_set_training(None, 1) < 0 and b'not finalized' in l.svb_last_error()
+    assert l.svb_gen_backward(None, None, None) < 0
+    assert l.svb_gen_grad_numel(None, b'conv_pre.weight') == -1
+    assert l.svb_weight_norm_backward(None, None, None, 4, 4, None, None, None) < 0
+    assert l.svb_conv_nct_backward(None, None, None, None, 1, 1, 1, 8, 1, 3, 1, 1, 1, 1, f(0.1), None, None, None, None, None) < 0
+    assert l.svb_loss_grad_dev(None, None, 0, f(1.0), None, None, 8, 0, None) < 0
+    assert l.svb_cond_net_forward(None, None, None, 1, 80, 8, 512, 256, 128, None, None) < 0
+    h = ctypes.c_void_p()
+    # 33 -> 64 channels is not a tensor-core shape; a stride-1 layer needs 'same' padding
+    assert l.svb_tc_layer_create(33, 64, 5, 1, 2, 3, 0, ctypes.byref(h)) < 0 and b'tensor-core shape' in l.svb_last_error()
+    assert l.svb_tc_layer_create(64, 64, 5, 1, 1, 3, 0, ctypes.byref(h)) < 0 and b"'same' padding" in l.svb_last_error()
+    assert l.svb_tc_layer_create(64, 64, 5, 3, 2, 0, 0, ctypes.byref(h)) < 0          # fp32 is not a tensor-core mode
+    assert l.svb_tc_layer_out_len(None, 100) == -1
+    c = _native.StftConfig(1024, 256, 512, _native.PAD_CENTER_ZERO, _native.OUT_MAG_RAW, 0, 0, 1, 0.0)
+    assert l.svb_denoise(ctypes.byref(c), None, 1, 4096, f(0.1), None, None) < 0
+    c.n_fft = 1000
+    assert l.svb_stft_backward(ctypes.byref(c), None, 1, 4096, None, None, None, None) < 0 and b'power of two' in l.svb_last_error()
