@@ -74,3 +74,41 @@ def test_mel_basis_and_pad_helpers():
     assert audio.librosa_pad_lr(x, 1024, 256, 1) == (0, 173 * 256 - 44100)
     l, r = audio.librosa_pad_lr(x, 1024, 256, 2)
     assert l + r == 173 * 256 - 44100
+
+
+def test_vocoder_training_task_wiring_on_cpu(monkeypatch, tmp_path):
+    """egs/vocoder_train_synthetic.yaml -> HifiGanTask: modules with the reference's parameter names, two AdamW optimizers
+    over disjoint parameter sets (the trainer's two-optimizer contract), synthetic batches of the yaml's shape.
+    No kernel runs here (no GPU): this pins the host-side wiring only."""
+    from neuralsvb_b200.tasks.vocoder.hifigan import HifiGanTask
+    monkeypatch.chdir(tmp_path)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hp = HP.set_hparams(config=os.path.join(root, 'egs/vocoder_train_synthetic.yaml'), exp_name='',
+                        hparams_str='max_sentences=3,max_samples=4096,num_train_batches=2', print_hparams=False)
+    assert hp['task_cls'].endswith('HifiGanTask') and hp['lambda_mel'] == 5.0 and hp['upsample_rates'] == [8, 8, 2, 2]
+    HP.hparams['infer'] = False
+    task = HifiGanTask()
+    assert task.build_model() is None
+    gen_names = set(dict(task.model_gen.named_parameters()))
+    assert gen_names == set(S.make_generator_state_dict(S.hifigan_config(), 1))         # the reference's checkpoint keys
+    assert set(task.model_disc['mpd'].state_dict()) == set(S.make_mpd_state_dict(1))
+    assert set(task.model_disc['msd'].state_dict()) == set(S.make_msd_state_dict(1))
+    og, od = task.configure_optimizers()
+    ids_g = {id(p) for g in og.param_groups for p in g['params']}
+    ids_d = {id(p) for g in od.param_groups for p in g['params']}
+    assert ids_g and ids_d and not (ids_g & ids_d)
+    assert og.defaults['betas'] == (0.8, 0.99) and abs(og.defaults['lr'] - 2e-4) < 1e-12
+    batches = task.train_dataloader()
+    assert len(batches) == 2 and tuple(batches[0]['wavs'].shape) == (3, 1, 4096) and tuple(batches[0]['f0'].shape) == (3, 16)
+
+
+def test_tensor_core_eligibility_of_discriminator_layers():
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    # MPD: (cin, cout) with k 5, stride 3 (1 for the last), pad 2
+    assert not D.tc_eligible(1, 32, 5, 3, 1, 2, 1)             # 1 input channel: fp32 kernel
+    assert D.tc_eligible(32, 128, 5, 3, 1, 2, 1) and D.tc_eligible(512, 1024, 5, 3, 1, 2, 1)
+    assert D.tc_eligible(1024, 1024, 5, 1, 1, 2, 1)            # stride 1, 'same' padding
+    assert not D.tc_eligible(1024, 1, 3, 1, 1, 1, 1)           # conv_post: one output channel
+    # MSD: grouped layers stay on CUDA cores, the dense 1024 -> 1024 k5 layer does not
+    assert not D.tc_eligible(128, 128, 41, 2, 1, 20, 4) and D.tc_eligible(1024, 1024, 5, 1, 1, 2, 1)
+    assert not D.tc_eligible(1024, 1024, 5, 1, 1, 1, 1)        # not 'same' padding
