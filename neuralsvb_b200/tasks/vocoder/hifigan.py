@@ -4,9 +4,9 @@ the way every NeuralSVB task uses the vocoder at test time (``tasks/tts/fs2.py:3
 ``tasks/singing/svb_vae_task.py:346-356``; SURVEY D2: in the reference the vocoder is inference-only).
 
 The reference names ``tasks.vocoder.hifigan.HifiGanTask`` in ``egs/egs_bases/tts/vocoder/hifigan.yaml:2``
-but ships no such module; the G + MPD + MSD *training* step behind that name needs the
-backward kernels that are not built yet, so ``HifiGanTask`` here refuses to train
-and ``HifiGanInferTask`` provides the inference half.
+but ships no such module.  ``HifiGanInferTask`` is the inference half; ``HifiGanTask`` adds the
+generator + MPD + MSD training step (``vocoder_losses``) under the trainer's two-optimizer contract, every forward and
+backward operator being a CUDA kernel of this package.
 
 Test items: ``hparams['test_input_dir']`` with ``*.npz`` files holding ``mel [T, 80]`` (log10) and
 optionally ``f0 [T]``; without it, ``hparams['num_test_samples']`` synthetic clips of
