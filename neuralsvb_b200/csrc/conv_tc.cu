@@ -51,6 +51,7 @@ struct TcArgs {
 };
 
 constexpr int kMaxW = 8;
+constexpr int kMaxDevices = 64;     // per-device caches of function attributes / SM counts
 // Warp roles.  The SM's issue arbiter favours HIGH warp ids, so the two latency-critical single-thread
 // roles get the highest ids: warps 0-7 epilogue, 8-15 operand transform, 16 TMA producer, 17 MMA issuer.
 constexpr int kTcThreadsP = 576;
@@ -576,15 +577,20 @@ bool tc_supported(const TcWeights &w, const ConvArgs &a) {
 template <int MODE>
 static int launch_mode(const TcArgs &p, int grid, size_t smem, cudaStream_t st) {
     auto kern = conv1d_c4_tc_kernel<MODE>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    // function attributes are per device: one process may drive several GPUs (the reference's mp.spawn gives one each,
+    // but nothing in the C ABI forbids a handle per device in one process)
+    static size_t configured[kMaxDevices] = {};
+    static bool carve[kMaxDevices] = {};
+    int dev = 0;
+    SVB_CUDA(cudaGetDevice(&dev));
+    dev = dev < kMaxDevices ? dev : kMaxDevices - 1;
+    if (smem > configured[dev] || dev == kMaxDevices - 1) {
         SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev] = smem;
     }
-    static bool carve = false;
-    if (!carve) {   // keep the SM's smem/L1 split fixed across the differently-sized launches of a forward
+    if (!carve[dev]) {   // keep the SM's smem/L1 split fixed across the differently-sized launches of a forward
         SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        carve = true;
+        carve[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kTcThreadsP), cfg.dynamicSmemBytes = smem, cfg.stream = st;
@@ -597,14 +603,15 @@ static int launch_mode(const TcArgs &p, int grid, size_t smem, cudaStream_t st) 
 }
 
 static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev < kMaxDevices ? dev : kMaxDevices - 1;
+    if (n[slot] == 0 || slot == kMaxDevices - 1) {
+        cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, dev);
+        if (n[slot] <= 0) n[slot] = 148;
     }
-    return n;
+    return n[slot];
 }
 
 int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st, int max_ctas) {

@@ -98,6 +98,7 @@ struct svb_gen {
 
     // training (generator_bwd.cu): tape kept by forward, dgrad packings, gradient buffers
     bool training = false, ws_training = false, dirty = false;
+    bool bwd_built = false;         // data-gradient packings + gather jobs exist (they survive set_training(0))
     std::vector<svb::BwdStage> bwd;
     float *zero_bias = nullptr;     // [max channels] zeros: the dgrad convs have no bias
     float *post_w_nat = nullptr;    // conv_post weight [C][K]

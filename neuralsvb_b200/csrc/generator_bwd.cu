@@ -246,9 +246,17 @@ extern "C" int svb_gen_set_training(svb_gen_t *g, int32_t on) {
         return SVB_OK;
     }
     if (g->training) return SVB_OK;
+    if (g->bwd_built) {
+        // train -> eval -> train: the data-gradient packings and the gather jobs are still alive and were refreshed
+        // together with the forward packings by every svb_gen_update_weights(_dev) since; rebuilding them from host_w
+        // (which svb_gen_set_weight_dev never touches) would bring back the weights of handle creation.
+        g->training = true;
+        return SVB_OK;
+    }
     SVB_CHECK(!g->host_w.empty(), SVB_ERR_STATE, "set_training: host weights are gone");
     SVB_TRY(gen_build_bwd_layers(g));
     SVB_TRY(build_jobs(g));
+    g->bwd_built = true;
     if (!g->grad_flat) {        // one flat buffer, one view per folded tensor (the reference's names and layouts)
         size_t total = 0;
         for (auto &kv : g->host_w) total += (kv.second.data.size() + 63) / 64 * 64;
@@ -267,10 +275,12 @@ extern "C" int svb_gen_set_training(svb_gen_t *g, int32_t on) {
 
 extern "C" int svb_gen_update_weights(svb_gen_t *g) {
     SVB_CHECK(g && g->finalized, SVB_ERR_STATE, "update_weights: generator not finalized");
-    SVB_TRY(gen_build_layers(g));
+    SVB_TRY(gen_build_layers(g));      // frees every device packing, the data-gradient twins included
+    g->bwd_built = false;
     if (g->training) {
         SVB_TRY(gen_build_bwd_layers(g));
         SVB_TRY(build_jobs(g));
+        g->bwd_built = true;
     }
     // the device copies of the folded tensors (if any) are stale now: drop them, they are re-created on demand
     for (auto &kv : g->nat_dev) cudaFree(kv.second.p);

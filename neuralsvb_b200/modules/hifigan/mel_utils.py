@@ -62,3 +62,23 @@ def mel_spectrogram(y, hparams, center=False, complex=False):
            _native.OUT_LN_MEL, 1, int(hparams['audio_num_mel_bins']), 0, 1e-5)
     frames = int(lib.svb_stft_num_frames(ctypes.byref(_native.StftConfig(*cfg)), n))
     return StftFn.apply(y, cfg, _basis(hparams, y.device), (B, cfg[6], frames))
+
+
+def wav2spec_mel(y, hparams, frames=None):
+    """y [B, T_wav] on a CUDA device -> log10-mel [B, n_mels, frames] exactly as the binarizer stores it and as the
+    plugin's ``spec2wav`` receives it: ``process_utterance`` (data_gen/tts/data_gen_utils.py:123-134) =
+    librosa.stft(center=True, pad_mode='constant') -> |.| -> mel basis -> log10(max(wav2spec_eps, .)).
+    This is the generator's CONDITIONING input in training (``mel_spectrogram`` above is only the mel-L1 loss
+    transform: natural log, clamp 1e-5, half-reflect padding).  ``frames`` crops to the clip's own frame count
+    (len // hop, the binarized ``mel[:T]`` aligned with ``wav[:T * hop]``); no gradient flows through it."""
+    if not y.is_cuda:
+        raise RuntimeError('wav2spec_mel needs a CUDA tensor: there is no CPU fallback')
+    lib = _native.lib()
+    B, n = y.shape
+    cfg = (int(hparams['fft_size']), int(hparams['hop_size']), int(hparams['win_size']), _native.PAD_CENTER_ZERO,
+           _native.OUT_LOG10_MEL, 0, int(hparams['audio_num_mel_bins']), 0, float(hparams.get('wav2spec_eps', 1e-10)))
+    total = int(lib.svb_stft_num_frames(ctypes.byref(_native.StftConfig(*cfg)), n))
+    with torch.no_grad():
+        mel = StftFn.apply(y.detach(), cfg, _basis(hparams, y.device), (B, cfg[6], total))
+    frames = n // cfg[1] if frames is None else frames
+    return mel[:, :, :frames].contiguous()

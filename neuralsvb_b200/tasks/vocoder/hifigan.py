@@ -134,10 +134,15 @@ class HifiGanTask(HifiGanInferTask):
         self.opt_d = torch.optim.AdamW(self.model_disc.parameters(), **kw)
         return [self.opt_g, self.opt_d]
 
+    def grad_segments(self, opt_idx):
+        """Exchange segments of the discriminator optimizer: MSD's backward finishes long before MPD's, so its
+        all-reduce (118 MB) overlaps the rest of the D backward (utils/ddp_utils.FlatGradReducer)."""
+        if opt_idx != 1:
+            return None
+        return [list(self.model_disc['msd'].parameters()), list(self.model_disc['mpd'].parameters())]
+
     def train_dataloader(self):
         """Synthetic clips of ``max_samples`` samples (hifigan.yaml:23-24), ``max_sentences`` per batch, sharded by rank."""
-        import torch
-        from neuralsvb_b200.modules.hifigan.mel_utils import mel_spectrogram
         from neuralsvb_b200.utils import synthetic as S
         hop = hparams['hop_size']
         n = int(hparams.get('max_samples', 8192)) // hop * hop
@@ -152,15 +157,9 @@ class HifiGanTask(HifiGanInferTask):
         return batches
 
     def training_step(self, sample, batch_idx, optimizer_idx=-1):
-        import torch
-        from neuralsvb_b200.modules.hifigan.mel_utils import mel_spectrogram
         y = sample['wavs'].cuda().float()
         f0 = sample['f0'].cuda().float() if hparams.get('use_pitch_embed', True) else None
-        if 'mels' in sample:
-            mel = sample['mels'].cuda().float()
-        else:
-            with torch.no_grad():
-                mel = mel_spectrogram(y.squeeze(1), hparams)
+        mel = self._cond_mel(sample, y)
         disc_on = self.global_step >= hparams.get('disc_start_steps', 0)
         if optimizer_idx == 0:
             loss, logs, self._y_hat = vocoder_losses(self.model_gen, self.model_disc['mpd'] if disc_on else None,
@@ -170,8 +169,21 @@ class HifiGanTask(HifiGanInferTask):
                 return {'loss': None}
             loss, logs, _ = vocoder_losses(None, self.model_disc['mpd'], self.model_disc['msd'], y, mel, f0, hparams, 1,
                                            y_hat=self._y_hat)
-        logs = {k: float(v) for k, v in logs.items()}
+        # device scalars: the trainer converts them only when it prints / writes TensorBoard (every tb_log_interval
+        # steps), so an optimizer pass has no host synchronisation of its own
+        logs = {k: (v.detach() if hasattr(v, 'detach') else v) for k, v in logs.items()}
         return {'loss': loss, 'progress_bar': logs, 'tb_log': logs}
+
+    @staticmethod
+    def _cond_mel(sample, y):
+        """The generator's conditioning input [B, 80, T]: the binarized log10 ``mels`` when the loader provides them
+        ([B, T, 80], ``base_binarizer.py:172-178``), else the same transform computed on the device (``wav2spec_mel``).
+        Never ``mel_spectrogram`` -- that is the loss-side mel (ln, clamp 1e-5, half-reflect) and a generator trained
+        on it would not match what ``HifiGAN.wav2spec -> spec2wav`` feeds it at inference."""
+        from neuralsvb_b200.modules.hifigan.mel_utils import wav2spec_mel
+        if 'mels' in sample:
+            return sample['mels'].cuda().float().transpose(1, 2).contiguous()
+        return wav2spec_mel(y.squeeze(1), hparams)
 
     def val_dataloader(self):
         return self.train_dataloader()[:1]
@@ -181,9 +193,8 @@ class HifiGanTask(HifiGanInferTask):
         from neuralsvb_b200.modules.hifigan.mel_utils import mel_spectrogram
         y = sample['wavs'].cuda().float()
         f0 = sample['f0'].cuda().float() if hparams.get('use_pitch_embed', True) else None
-        mel = mel_spectrogram(y.squeeze(1), hparams)
-        y_hat = self.model_gen(mel, f0)
-        return {'val_loss': float(D.l1_loss(mel_spectrogram(y_hat.squeeze(1), hparams), mel))}
+        y_hat = self.model_gen(self._cond_mel(sample, y), f0)
+        return {'val_loss': float(D.l1_loss(mel_spectrogram(y_hat.squeeze(1), hparams), mel_spectrogram(y.squeeze(1), hparams)))}
 
     def validation_end(self, outputs):
         v = sum(o['val_loss'] for o in outputs) / max(len(outputs), 1)

@@ -101,6 +101,10 @@ class Trainer:
         self.use_ddp = True
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29541')
+        # the mp.spawn path (the reference's default, utils/trainer.py:94-107) starts without torchrun's variables:
+        # export them so everything that shards by rank (task dataloaders, ddp_utils.dist_env) sees this worker's rank
+        os.environ['RANK'], os.environ['WORLD_SIZE'] = str(self.proc_rank), str(world)
+        os.environ['LOCAL_RANK'] = str(local_idx)
         backend = self.dist_backend or ('nccl' if self.on_gpu else 'gloo')
         if not dist.is_initialized():
             dist.init_process_group(backend, rank=self.proc_rank, world_size=world)
@@ -128,8 +132,11 @@ class Trainer:
             broadcast_module(task)                      # once; buffers are not re-broadcast every forward
         if not self.testing:
             self.optimizers = task.configure_optimizers()
-            self.reducers = [FlatGradReducer([p for g in o.param_groups for p in g['params']]) if (o is not None and self.use_ddp)
-                             else None for o in self.optimizers]
+            # gradient exchange: one flat buffer per optimizer; a task may split it into segments whose all-reduce is
+            # launched as soon as their last gradient lands (``grad_segments(opt_idx)`` -> lists of parameters)
+            seg_fn = getattr(task, 'grad_segments', lambda i: None)
+            self.reducers = [FlatGradReducer([p for g in o.param_groups for p in g['params']], seg_fn(i))
+                             if (o is not None and self.use_ddp) else None for i, o in enumerate(self.optimizers)]
             self.first_epoch = True
         if checkpoint is not None:
             self.restore_opt_state(checkpoint)
@@ -209,7 +216,7 @@ class Trainer:
                 if (self.global_step + 1) % self.tb_log_interval == 0:
                     self.log_metrics_to_tb(tb_metrics)
                     if self.proc_rank == 0 and pbar_metrics:
-                        print(f'| step {self.global_step}: {pbar_metrics}', flush=True)
+                        print(f'| step {self.global_step}: ' + ', '.join(f'{k} {float(_scalar(v)):.4f}' for k, v in pbar_metrics.items()), flush=True)
                 self.global_step += 1
                 task.global_step = self.global_step
                 if self.global_step > self.max_updates:
@@ -220,6 +227,10 @@ class Trainer:
             epoch += 1
             if n_batches == 0:
                 break
+        if self.proc_rank == 0 and not get_all_ckpts(self.work_dir):
+            # the reference saves only after a validation (utils/trainer.py:155-164): a run shorter than
+            # val_check_interval would end with nothing for the vocoder plugin to load
+            self.save_checkpoint(epoch=self.current_epoch)
         task.on_train_end()
 
     def run_training_batch(self, batch_idx, batch):
@@ -245,7 +256,10 @@ class Trainer:
                 loss = loss / self.accumulate_grad_batches
             if loss.requires_grad:
                 if self.reducers and self.reducers[opt_idx] is not None:
-                    self.reducers[opt_idx].rebind()
+                    if (self.global_step + 1) % self.accumulate_grad_batches == 0:
+                        self.reducers[opt_idx].arm()                # exchange overlaps the rest of this backward
+                    else:
+                        self.reducers[opt_idx].rebind()
                 self.amp_scalar.scale(loss).backward() if self.amp else loss.backward()
             if self.print_nan_grads:
                 bad = [n for n, p in task.named_parameters() if p.grad is not None and torch.isnan(p.grad.float()).any()]
@@ -254,7 +268,7 @@ class Trainer:
                     sys.exit(0)
             if (self.global_step + 1) % self.accumulate_grad_batches == 0:
                 if self.reducers and self.reducers[opt_idx] is not None:
-                    self.reducers[opt_idx].reduce()                 # the ONE collective of this optimizer step
+                    self.reducers[opt_idx].reduce()                 # finish this optimizer's exchange (one collective per segment)
                 task.on_before_optimization(opt_idx)
                 if self.amp:
                     self.amp_scalar.step(optimizer)

@@ -177,3 +177,12 @@ def wav2spec(wav, hp, return_linear=False):
     if return_linear:
         return res[0], res[1].T, res[2].T
     return res[0], res[1].T
+
+
+def float_to_int16(wav, norm=False):
+    """save_wav's sample conversion (utils/audio.py:11-16): optional peak normalisation, ``wav * 32767``, then
+    numpy's float -> int16 cast (truncation toward zero)."""
+    wav = np.asarray(wav, np.float32)
+    if norm:
+        wav = wav / np.abs(wav).max()
+    return (wav * np.float32(32767)).astype(np.int16)

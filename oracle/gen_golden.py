@@ -164,13 +164,198 @@ def gen_discriminators_cond():
     np.savez_compressed(os.path.join(OUT, 'discriminators_cond.npz'), **out)
 
 
+# ---------------------------------------------------------------------------------- round 2: branches the first set left unpinned
+def extra_config(name, nsf=True):
+    """Architectures of the extra generator cases (shared with the tests)."""
+    if name == 'small_rb2':
+        h = S.small_config(nsf)
+        h['resblock'], h['resblock_dilation_sizes'] = '2', [[1, 3], [1, 3], [1, 3]]
+    elif name == 'hop256_rb2':
+        h = S.hifigan_config(nsf)
+        h['resblock'], h['resblock_dilation_sizes'] = '2', [[1, 3], [1, 3], [1, 3]]
+    elif name == 'hop128':
+        h = S.hifigan_config(nsf, hop=128)
+    else:
+        raise KeyError(name)
+    return h
+
+
+GEN_EXTRA_CASES = {
+    # name: (config, B, T_frames, nsf, subsample stride)      ResBlock2 (hifigan.py:70-91) and the hop-128 singing architecture
+    'small_rb2': ('small_rb2', 2, 24, True, 1),
+    'small_rb2_plain': ('small_rb2', 1, 37, False, 1),
+    'hop256_rb2_t12': ('hop256_rb2', 1, 12, True, 1),
+    'hop128_t20': ('hop128', 2, 20, True, 1),
+}
+
+
+def gen_generator_extra():
+    out = {}
+    for name, (cfg, B, T, nsf, stride) in GEN_EXTRA_CASES.items():
+        h = extra_config(cfg, nsf)
+        hop = int(np.prod(h['upsample_rates']))
+        sd = S.make_generator_state_dict(h, SEED)
+        mel, f0 = S.make_mel_f0(B, T, SEED)
+        model = R.build_generator(h, sd)
+        if nsf:
+            ri, nz = S.make_nsf_noise(B, T * hop, SEED)
+            y = R.run_generator(model, mel, f0, ri, nz)
+        else:
+            y = R.run_generator(model, mel, None)
+        y = y.numpy()[:, 0]
+        out[f'{name}/y_sub'] = y[:, ::stride].astype(np.float32)
+        out[f'{name}/rms'] = np.sqrt((y.astype(np.float64) ** 2).mean(axis=1))
+        out[f'{name}/meta'] = np.array([B, T, int(nsf), stride, hop], np.int64)
+        print(name, y.shape, 'rms', out[f'{name}/rms'].mean())
+    np.savez_compressed(os.path.join(OUT, 'generator_extra.npz'), **out)
+
+
+GRAD_STRIDE, DISC_GRAD_STRIDE = 7, 211     # gradients are stored subsampled plus their exact L2 norm
+
+
+def grad_stride(numel, stride):
+    return 1 if numel <= 4096 else stride
+
+
+def _pack_grads(out, prefix, named_grads, stride=GRAD_STRIDE):
+    for k, g in named_grads:
+        g = g.detach().double().reshape(-1)
+        out[f'{prefix}/{k}/norm'] = np.float64(g.norm())
+        out[f'{prefix}/{k}/sub'] = g[::grad_stride(g.numel(), stride)].float().numpy()
+
+
+def gen_generator_grads():
+    """Parameter gradients by torch autograd through the REFERENCE generator modules (weight norm live, not folded):
+    d sum(y * cot) / d every parameter, small configs (ResBlock1 NSF, ResBlock2 NSF)."""
+    R.install()
+    out = {}
+    for name, cfg, B, T in (('small_nsf', None, 2, 24), ('small_rb2', 'small_rb2', 2, 24)):
+        h = S.small_config(True) if cfg is None else extra_config(cfg, True)
+        hop = int(np.prod(h['upsample_rates']))
+        sd = S.make_generator_state_dict(h, SEED)
+        mel, f0 = S.make_mel_f0(B, T, SEED)
+        ri, nz = S.make_nsf_noise(B, T * hop, SEED)
+        cot = torch.randn(B, 1, T * hop, generator=torch.Generator().manual_seed(7))
+        model = R.build_generator(h, sd, fold=False).train()
+        with R.injected_noise(ri, nz):
+            y = model(mel, f0)
+        (y * cot).sum().backward()
+        _pack_grads(out, name, [(k, p.grad) for k, p in model.named_parameters()])
+        out[f'{name}/y_sub'] = y.detach().numpy()[:, 0, ::3].astype(np.float32)
+        print(name, 'params', len(list(model.parameters())))
+    np.savez_compressed(os.path.join(OUT, 'generator_grads.npz'), **out)
+
+
+def gen_losses_extra():
+    """use_mel_loss STFT loss (modules/parallel_wavegan/stft_loss.py:13-100), the vocoder_denoise_c post-filter
+    (vocoders/vocoder_utils.py:7-15) and save_wav's float -> int16 conversion (utils/audio.py:11-16)."""
+    import tempfile
+    R.install()
+    from utils.hparams import hparams as ref_hp
+    from modules.parallel_wavegan.stft_loss import MultiResolutionSTFTLoss as MelMR
+    from vocoders.vocoder_utils import denoise
+    from utils.audio import save_wav
+    from scipy.io import wavfile
+    out = {}
+    y = S.make_wave_batch(2, 8192, seed=SEED)
+    x = (y + 0.05 * S.make_wave_batch(2, 8192, seed=SEED + 1)).clamp(-1, 1)
+    with R.legacy_stft(), R.cpu_cuda(), torch.no_grad():
+        m = MelMR(use_mel_loss=True)
+        sc, mag = m(x, y)
+        out['mr_stft_mel/sc_mag'] = np.array([float(sc), float(mag)], np.float64)
+        per = []
+        for f in m.stft_losses:
+            s1, m1 = f(x, y)
+            per += [float(s1), float(m1)]
+        out['mr_stft_mel/per_resolution'] = np.array(per, np.float64)
+    xg = x.clone().requires_grad_(True)
+    with R.legacy_stft(), R.cpu_cuda():
+        sc, mag = MelMR(use_mel_loss=True)(xg, y)
+        (sc + mag).backward()
+    out['mr_stft_mel/dx_norm'] = np.float64(xg.grad.double().norm())
+    out['mr_stft_mel/dx_sub'] = xg.grad.numpy()[:, ::5].astype(np.float32)
+    for win in (512, 1024):
+        ref_hp.update({'fft_size': 1024, 'hop_size': 256, 'win_size': win})
+        wav = S.make_clip(256 * 40, seed=SEED + 3)
+        out[f'denoise/win{win}'] = np.asarray(denoise(wav, v=0.1), np.float32)
+    wav = S.make_clip(4000, seed=SEED + 4) * 1.7
+    wav = np.clip(wav, -1.0, 1.0).astype(np.float32)
+    for norm in (False, True):
+        with tempfile.TemporaryDirectory() as d:
+            fn = os.path.join(d, 'a.wav')
+            save_wav(wav.copy(), fn, 22050, norm=norm)
+            sr, data = wavfile.read(fn)
+        assert sr == 22050 and data.dtype == np.int16
+        out[f'save_wav/int16_norm{int(norm)}'] = data
+    np.savez_compressed(os.path.join(OUT, 'losses_extra.npz'), **out)
+    print('losses_extra.npz', out['mr_stft_mel/sc_mag'], out['denoise/win512'].shape)
+
+
+def gen_discriminators_train():
+    """Training-mode discriminators from the reference modules: (i) MSD in train() mode -- torch's spectral_norm runs
+    one power iteration per forward of every DiscriminatorS[0] conv (hifigan.py:261,294), so two MSD forwards =
+    four iterations: logits and the u buffers after each forward; (ii) parameter gradients of the D loss and
+    d(G adversarial + feature loss)/d y_hat by autograd through the reference MPD / MSD."""
+    R.install()
+    from utils.hparams import hparams as ref_hp
+    ref_hp['hop_size'] = 256
+    from modules.hifigan.hifigan import (MultiPeriodDiscriminator, MultiScaleDiscriminator, discriminator_loss, feature_loss,
+                                         generator_loss)
+    out = {}
+    y = S.make_wave_batch(2, 8192, seed=SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=SEED + 5)[:, None]).clamp(-1, 1)
+    for name, cls, sd in (('mpd', MultiPeriodDiscriminator, S.make_mpd_state_dict(SEED)),
+                          ('msd', MultiScaleDiscriminator, S.make_msd_state_dict(SEED))):
+        m = cls()
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        # ---- forward 1 (+ D-loss gradients), then forward 2 on the updated u / v
+        rs, gs, fr, fg = m(y, y_hat)
+        r_loss, g_loss = discriminator_loss(rs, gs)
+        (r_loss + g_loss).backward()
+        out[f'{name}/d_loss'] = np.array([float(r_loss), float(g_loss)], np.float64)
+        _pack_grads(out, f'{name}/d_grad', [(k, p.grad) for k, p in m.named_parameters()], DISC_GRAD_STRIDE)
+        for i, (r, g) in enumerate(zip(rs, gs)):
+            out[f'{name}/fwd1/logit_r{i}'], out[f'{name}/fwd1/logit_g{i}'] = r.detach().numpy(), g.detach().numpy()
+        if name == 'msd':
+            for k, b in m.named_buffers():
+                if k.endswith('weight_u'):
+                    out[f'{name}/fwd1/{k}'] = b.detach().numpy().copy()
+        m.zero_grad()
+        with torch.no_grad():
+            rs2, gs2, _, _ = m(y, y_hat)
+        for i, (r, g) in enumerate(zip(rs2, gs2)):
+            out[f'{name}/fwd2/logit_r{i}'], out[f'{name}/fwd2/logit_g{i}'] = r.numpy(), g.numpy()
+        if name == 'msd':
+            for k, b in m.named_buffers():
+                if k.endswith('weight_u'):
+                    out[f'{name}/fwd2/{k}'] = b.detach().numpy().copy()
+        # ---- generator side: d (generator_loss + feature_loss) / d y_hat with the discriminator frozen (eval-mode
+        # spectral norm so the fixture does not depend on how many iterations ran before)
+        m2 = cls()
+        m2.load_state_dict(sd, strict=True)
+        m2.eval()
+        for p in m2.parameters():
+            p.requires_grad_(False)
+        yh = y_hat.clone().requires_grad_(True)
+        rs, gs, fr, fg = m2(y, yh)
+        lg = generator_loss(gs) + feature_loss(fr, fg)
+        lg.backward()
+        out[f'{name}/g_loss'] = np.float64(lg)
+        out[f'{name}/g_dyhat_norm'] = np.float64(yh.grad.double().norm())
+        out[f'{name}/g_dyhat_sub'] = yh.grad.numpy()[:, 0, ::5].astype(np.float32)
+        print(name, out[f'{name}/d_loss'], float(lg))
+    np.savez_compressed(os.path.join(OUT, 'discriminators_train.npz'), **out)
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
-    which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond']
+    which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond', 'generator_extra',
+                             'generator_grads', 'losses_extra', 'discriminators_train']
     for w in which:
         globals()[f'gen_{w}']()
 

@@ -335,3 +335,51 @@ def fold_discriminator_weights(sd):
         else:
             out[k] = v
     return out
+
+
+# ------------------------------------------------------------------ spectral norm, training mode
+def spectral_power_iteration(sd, prefix):
+    """One power iteration of torch.nn.utils.spectral_norm (the forward pre-hook runs it on EVERY training-mode
+    forward, under no_grad): v <- normalize(W^T u), u <- normalize(W v); the buffers in ``sd`` are updated in
+    place.  hifigan.py:261 (norm_f = spectral_norm) + :294 (DiscriminatorS(use_spectral_norm=True))."""
+    with torch.no_grad():
+        wm = sd[prefix + 'weight_orig'].detach().flatten(1)
+        v = F.normalize(torch.mv(wm.t(), sd[prefix + 'weight_u']), dim=0, eps=1e-12)
+        u = F.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+        sd[prefix + 'weight_u'], sd[prefix + 'weight_v'] = u, v
+
+
+def disc_s_train_weights(sd, d):
+    """Effective weights of MSD discriminator ``d`` for ONE training-mode forward: spectral-normed layers run their
+    power iteration first (buffers of ``sd`` updated), sigma = u . (W v) with u, v constants (the gradient reaches
+    weight_orig through both the numerator and sigma)."""
+    out = {}
+    pre = f'discriminators.{d}.'
+    for k in [k for k in sd if k.startswith(pre)]:
+        v = sd[k]
+        if k.endswith('.weight_orig'):
+            p = k[:-len('weight_orig')]
+            spectral_power_iteration(sd, p)
+            sigma = torch.dot(sd[p + 'weight_u'], torch.mv(v.flatten(1), sd[p + 'weight_v']))
+            out[p + 'weight'] = v / sigma
+        elif k.endswith('.weight_v') and k[:-1] + 'g' in sd:
+            out[k[:-2]] = torch._weight_norm(v, sd[k[:-1] + 'g'], 0)
+        elif k.endswith('.weight_g') or k.endswith('.weight_u') or k.endswith('.weight_v'):
+            continue
+        else:
+            out[k] = v
+    return out
+
+
+def msd_forward_train(y, y_hat, sd, mel=None):
+    """MultiScaleDiscriminator.forward in train() mode (hifigan.py:309-325): every DiscriminatorS call is its own
+    forward, so discriminator 0 runs one power iteration for ``y`` and another for ``y_hat``."""
+    y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
+    for i in range(3):
+        if i != 0:
+            y = F.avg_pool1d(y, 4, 2, padding=1)
+            y_hat = F.avg_pool1d(y_hat, 4, 2, padding=1)
+        r, fr = disc_s_forward(y, disc_s_train_weights(sd, i), f'discriminators.{i}', mel)
+        g, fg = disc_s_forward(y_hat, disc_s_train_weights(sd, i), f'discriminators.{i}', mel)
+        y_d_rs.append(r), fmap_rs.append(fr), y_d_gs.append(g), fmap_gs.append(fg)
+    return y_d_rs, y_d_gs, fmap_rs, fmap_gs

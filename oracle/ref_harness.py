@@ -50,6 +50,18 @@ def _torch_stft_librosa(y, n_fft=2048, hop_length=None, win_length=None, window=
     return s.numpy().astype(np.complex64)
 
 
+def _torch_istft_librosa(stft_matrix, hop_length=None, win_length=None, window='hann', center=True, length=None, **_):
+    """librosa.istft stand-in built on torch.istft (window sum-square normalisation, centre padding trimmed) --
+    independent of oracle/frontend.istft_librosa, so it pins it."""
+    s = torch.from_numpy(np.asarray(stft_matrix)).to(torch.complex128)
+    n_fft = 2 * (s.shape[0] - 1)
+    win_length = n_fft if win_length is None else win_length
+    hop_length = win_length // 4 if hop_length is None else hop_length
+    w = torch.hann_window(win_length, periodic=True, dtype=torch.float64)
+    y = torch.istft(s, n_fft, hop_length, win_length, w, center=center, length=length)
+    return y.numpy().astype(np.float32)
+
+
 def _torchaudio_mel(sr, n_fft, n_mels=128, fmin=0.0, fmax=None, **_):
     import torchaudio
     fmax = sr / 2.0 if fmax is None else fmax
@@ -76,7 +88,7 @@ def install():
     sys.modules['skimage.transform'].resize = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
     sys.modules['skimage'].transform = sys.modules['skimage.transform']
     sys.modules['textgrid'].TextGrid = object
-    lib = _stub('librosa', stft=_torch_stft_librosa)
+    lib = _stub('librosa', stft=_torch_stft_librosa, istft=_torch_istft_librosa)
     lib.filters = _stub('librosa.filters', mel=_torchaudio_mel)
     lib.core = _stub('librosa.core')
     sys.path.insert(0, REF_ROOT)
@@ -98,6 +110,18 @@ def legacy_stft():
         yield
     finally:
         torch.stft = orig
+
+
+@contextlib.contextmanager
+def cpu_cuda():
+    """``Tensor.cuda()`` -> identity while the block runs: modules/parallel_wavegan/stft_loss.py:45 hard-codes
+    ``.cuda()`` on its mel basis; the arithmetic is device independent."""
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig
 
 
 @contextlib.contextmanager

@@ -1,0 +1,203 @@
+"""-m gpu: the CUDA path against the round-2 fixtures written by the UNMODIFIED reference modules
+(oracle/gen_golden.py: generator_extra / generator_grads / losses_extra / discriminators_train) -- the branches that
+round 1 checked against the oracle only: ResBlock2, the hop-128 architecture, the use_mel_loss STFT loss, the
+denoise post-filter, save_wav's int16 conversion, training-mode spectral norm, and parameter gradients taken by
+autograd through the reference modules themselves."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from neuralsvb_b200.modules.hifigan.hifigan import HifiGanGenerator
+from neuralsvb_b200.utils import synthetic as S
+from oracle.gen_golden import DISC_GRAD_STRIDE, GEN_EXTRA_CASES, GRAD_STRIDE, SEED, extra_config, grad_stride
+from tests import gpu_util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2_sub(t, g, prefix, k, stride):
+    """Relative L2 error of a gradient on the fixture's subsample + relative error of its full L2 norm."""
+    t = t.detach().double().reshape(-1).cpu()
+    ref_s = torch.from_numpy(g[f'{prefix}/{k}/sub'].astype(np.float64))
+    sub = t[::grad_stride(t.numel(), stride)]
+    assert sub.shape == ref_s.shape, k
+    ref_n = float(g[f'{prefix}/{k}/norm'])
+    e_sub = float((sub - ref_s).norm() / ref_s.norm().clamp_min(1e-30))
+    e_norm = abs(float(t.norm()) - ref_n) / max(ref_n, 1e-30)
+    return e_sub, e_norm
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16x3'])
+@pytest.mark.parametrize('name', list(GEN_EXTRA_CASES))
+def test_generator_extra_architectures_match_reference_fixture(golden_dir, name, prec):
+    """a8 ResBlock2 (hifigan.py:70-91) + the hop-128 singing architecture: waveform <= 1e-4 RMS vs the reference."""
+    g = np.load(os.path.join(golden_dir, 'generator_extra.npz'))
+    cfg, B, T, nsf, stride = GEN_EXTRA_CASES[name]
+    h = extra_config(cfg, nsf)
+    hop = int(np.prod(h['upsample_rates']))
+    m = HifiGanGenerator(h, precision=prec)
+    m.load_state_dict(S.make_generator_state_dict(h, SEED), strict=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.remove_weight_norm()
+    m = m.eval().cuda()
+    mel, f0 = S.make_mel_f0(B, T, SEED)
+    with torch.no_grad():
+        if nsf:
+            ri, nz = S.make_nsf_noise(B, T * hop, SEED)
+            y = m(mel.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda())
+        else:
+            y = m(mel.cuda())
+    y = y.cpu().numpy()[:, 0]
+    assert y.shape == (B, T * hop)                                       # sample indexing: bit exact
+    err = U.rms(y[:, ::stride], g[f'{name}/y_sub'])
+    assert err < 1e-4, err
+    np.testing.assert_allclose(np.sqrt((y.astype(np.float64) ** 2).mean(axis=1)), g[f'{name}/rms'], rtol=1e-3)
+
+
+@pytest.mark.parametrize('name,cfg', [('small_nsf', None), ('small_rb2', 'small_rb2')])
+def test_generator_backward_matches_reference_autograd_fixture(golden_dir, name, cfg):
+    """svb_gen_backward (fp32 mode pins the logic) against gradients taken by torch autograd through the reference
+    HifiGanGenerator with live weight norm: every parameter tensor, relative L2 on the stored subsample + norm."""
+    g = np.load(os.path.join(golden_dir, 'generator_grads.npz'))
+    h = S.small_config(True) if cfg is None else extra_config(cfg, True)
+    B, T = 2, 24
+    hop = int(np.prod(h['upsample_rates']))
+    m = HifiGanGenerator(h, precision='fp32')
+    m.load_state_dict(S.make_generator_state_dict(h, SEED), strict=True)
+    m = m.cuda().train()
+    mel, f0 = S.make_mel_f0(B, T, SEED)
+    ri, nz = S.make_nsf_noise(B, T * hop, SEED)
+    cot = torch.randn(B, 1, T * hop, generator=torch.Generator().manual_seed(7))
+    y = m(mel.cuda(), f0.cuda(), rand_ini=ri.cuda(), noise=nz.cuda())
+    assert np.abs(y.detach().cpu().numpy()[:, 0, ::3] - g[f'{name}/y_sub']).max() < 1e-5
+    (y * cot.cuda()).sum().backward()
+    worst = 0.0
+    for k, p in m.named_parameters():
+        e_sub, e_norm = _rel_l2_sub(p.grad, g, name, k, GRAD_STRIDE)
+        worst = max(worst, e_sub, e_norm)
+        assert e_sub < 2e-4 and e_norm < 2e-4, (k, e_sub, e_norm)
+    print(f'{name}: worst relative gradient error vs the reference autograd fixture {worst:.2e}')
+
+
+def test_eval_between_training_steps_keeps_backward_weights_current():
+    """train forward -> optimizer step -> eval forward -> train forward/backward must differentiate the
+    CURRENT weights (set_training(1) used to rebuild the data-gradient packings from the host copy of handle
+    creation).  Checker: torch autograd through the oracle on the updated parameters."""
+    from oracle import hifigan as O
+    h = S.small_config(True)
+    B, T, hop = 1, 16, 16
+    m = HifiGanGenerator(h, precision='fp32')
+    m.load_state_dict(S.make_generator_state_dict(h, SEED), strict=True)
+    m = m.cuda().train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    mel, f0 = S.make_mel_f0(B, T, SEED)
+    ri, nz = S.make_nsf_noise(B, T * hop, SEED)
+    cot = torch.randn(B, 1, T * hop, generator=torch.Generator().manual_seed(7))
+    kw = dict(rand_ini=ri.cuda(), noise=nz.cuda())
+    (m(mel.cuda(), f0.cuda(), **kw) * cot.cuda()).sum().backward()
+    opt.step(), opt.zero_grad()                                          # weights move a lot (lr 0.05)
+    (m(mel.cuda(), f0.cuda(), **kw) * cot.cuda()).sum().backward()       # device-side re-pack happens here
+    opt.zero_grad()
+    m.eval()
+    with torch.no_grad():
+        m(mel.cuda(), f0.cuda(), **kw)                                   # validation between two optimizer steps
+    m.train()
+    (m(mel.cuda(), f0.cuda(), **kw) * cot.cuda()).sum().backward()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    (O.generator_forward(O.fold_weight_norm(p), h, mel, f0, ri, nz) * cot).sum().backward()
+    worst = max(float((q.grad.cpu() - p[k].grad).norm() / p[k].grad.norm().clamp_min(1e-30)) for k, q in m.named_parameters())
+    assert worst < 2e-4, worst
+
+
+def test_mel_stft_loss_matches_reference_fixture(golden_dir):
+    """a14: STFTLoss(use_mel_loss=True) (modules/parallel_wavegan/stft_loss.py:13-100): value and d/dx."""
+    from neuralsvb_b200.modules.parallel_wavegan.losses.stft_loss import multi_resolution_stft_loss
+    g = np.load(os.path.join(golden_dir, 'losses_extra.npz'))
+    y = S.make_wave_batch(2, 8192, seed=SEED)
+    x = (y + 0.05 * S.make_wave_batch(2, 8192, seed=SEED + 1)).clamp(-1, 1)
+    xc = x.cuda().requires_grad_(True)
+    sc, mag = multi_resolution_stft_loss(xc, y.cuda(), use_mel_loss=True)
+    np.testing.assert_allclose([float(sc), float(mag)], g['mr_stft_mel/sc_mag'], rtol=1e-3)   # north star: 1e-3 on spectral features
+    (sc + mag).backward()
+    dx = xc.grad.cpu()
+    ref = g['mr_stft_mel/dx_sub']
+    assert abs(float(dx.double().norm()) - float(g['mr_stft_mel/dx_norm'])) < 2e-3 * float(g['mr_stft_mel/dx_norm'])
+    assert np.linalg.norm(dx.numpy()[:, ::5] - ref) < 2e-3 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize('win', [512, 1024])
+def test_denoise_matches_reference_fixture(golden_dir, win):
+    """N4: vocoder_denoise_c post-filter (vocoders/vocoder_utils.py:7-15) against the reference function itself."""
+    from neuralsvb_b200.vocoders.vocoder_utils import denoise
+    g = np.load(os.path.join(golden_dir, 'losses_extra.npz'))
+    hp = dict(S.hifigan_config(), win_size=win)
+    wav = S.make_clip(256 * 40, seed=SEED + 3)
+    got = denoise(wav, v=0.1, hp=hp)
+    ref = g[f'denoise/win{win}']
+    assert got.shape == ref.shape
+    assert U.rms(got, ref) < 1e-5 and np.abs(got - ref).max() < 1e-4
+
+
+@pytest.mark.parametrize('name', ['mpd', 'msd'])
+def test_training_mode_discriminators_match_reference_fixture(golden_dir, name):
+    """a11 gap of round 1: MSD in train() mode -- two consecutive forwards (four power iterations of the spectral
+    norm): logits and u buffers; D-loss parameter gradients and d(G loss)/d y_hat vs autograd through the reference."""
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    g = np.load(os.path.join(golden_dir, 'discriminators_train.npz'))
+    if name == 'mpd':
+        mk, sd = D.MultiPeriodDiscriminator, S.make_mpd_state_dict(SEED)
+    else:
+        mk, sd = D.MultiScaleDiscriminator, S.make_msd_state_dict(SEED)
+    y = S.make_wave_batch(2, 8192, seed=SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=SEED + 5)[:, None]).clamp(-1, 1)
+    tol = lambda ref: 5e-4 * max(1.0, np.abs(ref).max())
+    for use_tc, gtol in ((False, 1e-3), (True, 2e-2)):
+        D.USE_TC = use_tc
+        try:
+            m = mk()
+            m.load_state_dict(sd, strict=True)
+            m = m.cuda().train()
+            rs, gs, _, _ = m(y.cuda(), y_hat.cuda())
+            r_loss, g_loss = D.discriminator_loss(rs, gs)
+            np.testing.assert_allclose([float(r_loss), float(g_loss)], g[f'{name}/d_loss'], rtol=5e-4)
+            (r_loss + g_loss).backward()
+            for i, (r, gg) in enumerate(zip(rs, gs)):
+                assert np.abs(r.detach().cpu().numpy() - g[f'{name}/fwd1/logit_r{i}']).max() < tol(g[f'{name}/fwd1/logit_r{i}'])
+                assert np.abs(gg.detach().cpu().numpy() - g[f'{name}/fwd1/logit_g{i}']).max() < tol(g[f'{name}/fwd1/logit_g{i}'])
+            bufs = dict(m.named_buffers())
+            for k in [k for k in bufs if k.endswith('weight_u')]:
+                assert np.abs(bufs[k].cpu().numpy() - g[f'{name}/fwd1/{k}']).max() < 1e-4, k
+            errs = {}
+            for k, p in m.named_parameters():
+                e_sub, e_norm = _rel_l2_sub(p.grad, g, f'{name}/d_grad', k, DISC_GRAD_STRIDE)
+                errs[k] = max(e_sub, e_norm)
+            med, worst = float(np.median(list(errs.values()))), max(errs.values())
+            print(f'{name} {"tc" if use_tc else "fp32"}: D-loss gradient error vs reference autograd: median {med:.1e}, worst {worst:.1e}')
+            assert med < gtol / 4 and worst < gtol * 4, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+            with torch.no_grad():
+                rs2, gs2, _, _ = m(y.cuda(), y_hat.cuda())
+            for i, (r, gg) in enumerate(zip(rs2, gs2)):
+                assert np.abs(r.cpu().numpy() - g[f'{name}/fwd2/logit_r{i}']).max() < tol(g[f'{name}/fwd2/logit_r{i}'])
+                assert np.abs(gg.cpu().numpy() - g[f'{name}/fwd2/logit_g{i}']).max() < tol(g[f'{name}/fwd2/logit_g{i}'])
+            for k in [k for k in bufs if k.endswith('weight_u')]:
+                assert np.abs(bufs[k].cpu().numpy() - g[f'{name}/fwd2/{k}']).max() < 1e-4, k
+            # generator side: eval-mode weights, discriminator frozen
+            m2 = mk()
+            m2.load_state_dict(sd, strict=True)
+            m2 = m2.cuda().eval()
+            for p in m2.parameters():
+                p.requires_grad_(False)
+            yh = y_hat.cuda().requires_grad_(True)
+            rs, gs, fr, fg = m2(y.cuda(), yh)
+            lg = D.generator_loss(gs) + D.feature_loss(fr, fg)
+            lg.backward()
+            np.testing.assert_allclose(float(lg), float(g[f'{name}/g_loss']), rtol=5e-4)
+            ref = g[f'{name}/g_dyhat_sub']
+            e = np.linalg.norm(yh.grad.cpu().numpy()[:, 0, ::5] - ref) / np.linalg.norm(ref)
+            assert e < gtol, e
+        finally:
+            D.USE_TC = True

@@ -136,3 +136,135 @@ def test_cond_discriminators_match_reference(golden_dir, name):
     for i, (r, gg) in enumerate(zip(rs, gs)):
         assert np.abs(r.numpy() - g[f'{name}/logit_r{i}']).max() < 2e-5 * max(1.0, np.abs(g[f'{name}/logit_r{i}']).max())
         assert np.abs(gg.numpy() - g[f'{name}/logit_g{i}']).max() < 2e-5 * max(1.0, np.abs(g[f'{name}/logit_g{i}']).max())
+
+
+# ---------------------------------------------------------------------------------- round 2 fixtures (previously unpinned branches)
+from oracle.gen_golden import DISC_GRAD_STRIDE, GEN_EXTRA_CASES, GRAD_STRIDE, extra_config, grad_stride  # noqa: E402
+
+
+def _check_grads(g, prefix, named, stride, rtol):
+    """Fixture = exact L2 norm + every `stride`-th element of each gradient tensor (gen_golden._pack_grads)."""
+    worst = 0.0
+    for k, t in named:
+        t = t.detach().double().reshape(-1)
+        ref_n, ref_s = float(g[f'{prefix}/{k}/norm']), g[f'{prefix}/{k}/sub'].astype(np.float64)
+        sub = t[::grad_stride(t.numel(), stride)].numpy()
+        assert sub.shape == ref_s.shape, k
+        scale = max(ref_n / np.sqrt(t.numel()), 1e-30)                      # RMS element of the reference gradient
+        err = float(np.abs(sub - ref_s).max() / scale)
+        worst = max(worst, err)
+        assert abs(float(t.norm()) - ref_n) <= rtol * max(ref_n, 1e-30), (k, float(t.norm()), ref_n)
+        assert err < rtol * 50, (k, err)                                    # element-wise, in units of the RMS element
+    return worst
+
+
+@pytest.mark.parametrize('name', list(GEN_EXTRA_CASES))
+def test_generator_extra_architectures_match_reference(golden_dir, name):
+    """ResBlock2 (hifigan.py:70-91) and the hop-128 singing architecture, from the reference modules."""
+    g = np.load(os.path.join(golden_dir, 'generator_extra.npz'))
+    cfg, B, T, nsf, stride = GEN_EXTRA_CASES[name]
+    h = extra_config(cfg, nsf)
+    hop = int(np.prod(h['upsample_rates']))
+    w = O.fold_weight_norm(S.make_generator_state_dict(h, SEED))
+    mel, f0 = S.make_mel_f0(B, T, SEED)
+    with torch.no_grad():
+        if nsf:
+            ri, nz = S.make_nsf_noise(B, T * hop, SEED)
+            y = O.generator_forward(w, h, mel, f0, ri, nz)
+        else:
+            y = O.generator_forward(w, h, mel)
+    y = y.numpy()[:, 0]
+    assert y.shape == (B, T * hop) and tuple(g[f'{name}/meta']) == (B, T, int(nsf), stride, hop)
+    assert float(np.sqrt(((y[:, ::stride] - g[f'{name}/y_sub']) ** 2).mean())) < 1e-6
+
+
+@pytest.mark.parametrize('name,cfg', [('small_nsf', None), ('small_rb2', 'small_rb2')])
+def test_generator_gradients_match_reference_autograd(golden_dir, name, cfg):
+    """torch autograd through the oracle == torch autograd through the reference modules (weight norm live)."""
+    g = np.load(os.path.join(golden_dir, 'generator_grads.npz'))
+    h = S.small_config(True) if cfg is None else extra_config(cfg, True)
+    B, T = 2, 24
+    hop = int(np.prod(h['upsample_rates']))
+    p = {k: v.clone().requires_grad_(True) for k, v in S.make_generator_state_dict(h, SEED).items()}
+    mel, f0 = S.make_mel_f0(B, T, SEED)
+    ri, nz = S.make_nsf_noise(B, T * hop, SEED)
+    cot = torch.randn(B, 1, T * hop, generator=torch.Generator().manual_seed(7))
+    y = O.generator_forward(O.fold_weight_norm(p), h, mel, f0, ri, nz)
+    (y * cot).sum().backward()
+    assert np.abs(y.detach().numpy()[:, 0, ::3] - g[f'{name}/y_sub']).max() < 1e-6
+    _check_grads(g, name, [(k, v.grad) for k, v in p.items()], GRAD_STRIDE, 1e-4)
+
+
+def test_mel_stft_loss_denoise_and_int16_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'losses_extra.npz'))
+    y = S.make_wave_batch(2, 8192, seed=SEED)
+    x = (y + 0.05 * S.make_wave_batch(2, 8192, seed=SEED + 1)).clamp(-1, 1)
+    # use_mel_loss (modules/parallel_wavegan/stft_loss.py:43-47): values, per resolution, and d/dx
+    xg = x.clone().requires_grad_(True)
+    sc, mag = O.mr_stft_loss(xg, y, use_mel_loss=True)
+    np.testing.assert_allclose([float(sc), float(mag)], g['mr_stft_mel/sc_mag'], rtol=2e-5)
+    per = []
+    for fs, ss, wl in O.MR_STFT:
+        mb = torch.from_numpy(FE.mel_filterbank(22050, fs, 80)).T
+        s1, m1 = O.stft_loss(x, y, fs, ss, wl, mb)
+        per += [float(s1), float(m1)]
+    np.testing.assert_allclose(per, g['mr_stft_mel/per_resolution'], rtol=2e-5)
+    (sc + mag).backward()
+    assert abs(float(xg.grad.double().norm()) - float(g['mr_stft_mel/dx_norm'])) < 1e-4 * float(g['mr_stft_mel/dx_norm'])
+    assert np.abs(xg.grad.numpy()[:, ::5] - g['mr_stft_mel/dx_sub']).max() < 1e-3 * np.abs(g['mr_stft_mel/dx_sub']).max()
+    # denoise (vocoders/vocoder_utils.py:7-15; librosa istft restated in oracle/frontend.py)
+    for win in (512, 1024):
+        wav = S.make_clip(256 * 40, seed=SEED + 3)
+        d = FE.denoise(wav, 0.1, 1024, 256, win)
+        ref = g[f'denoise/win{win}']
+        assert d.shape == ref.shape and np.abs(d - ref).max() < 2e-6
+    # save_wav float -> int16 (utils/audio.py:11-16): bit exact
+    wav = np.clip(S.make_clip(4000, seed=SEED + 4) * 1.7, -1.0, 1.0).astype(np.float32)
+    for norm in (0, 1):
+        assert np.array_equal(FE.float_to_int16(wav, bool(norm)), g[f'save_wav/int16_norm{norm}'])
+
+
+@pytest.mark.parametrize('name', ['mpd', 'msd'])
+def test_training_mode_discriminators_match_reference(golden_dir, name):
+    """Training-mode MPD / MSD from the reference modules: two consecutive forwards (spectral-norm power iteration of
+    MSD[0]: logits + u buffers), D-loss parameter gradients, d(G adversarial + feature loss)/d y_hat."""
+    g = np.load(os.path.join(golden_dir, 'discriminators_train.npz'))
+    sd0 = S.make_mpd_state_dict(SEED) if name == 'mpd' else S.make_msd_state_dict(SEED)
+    is_buf = lambda k: k.endswith('weight_u') or (k.endswith('weight_v') and k[:-1] + 'orig' in sd0)
+    sd = {k: (v.clone() if is_buf(k) else v.clone().requires_grad_(True)) for k, v in sd0.items()}
+    y = S.make_wave_batch(2, 8192, seed=SEED)[:, None]
+    y_hat = (y + 0.1 * S.make_wave_batch(2, 8192, seed=SEED + 5)[:, None]).clamp(-1, 1)
+
+    def fwd():
+        if name == 'mpd':
+            return O.mpd_forward(y, y_hat, O.fold_discriminator_weights(sd))
+        return O.msd_forward_train(y, y_hat, sd)
+    rs, gs, _, _ = fwd()
+    r_loss, g_loss = O.discriminator_loss(rs, gs)
+    np.testing.assert_allclose([float(r_loss), float(g_loss)], g[f'{name}/d_loss'], rtol=2e-5)
+    (r_loss + g_loss).backward()
+    tol = lambda ref: 3e-5 * max(1.0, np.abs(ref).max())
+    for i, (r, gg) in enumerate(zip(rs, gs)):
+        assert np.abs(r.detach().numpy() - g[f'{name}/fwd1/logit_r{i}']).max() < tol(g[f'{name}/fwd1/logit_r{i}'])
+        assert np.abs(gg.detach().numpy() - g[f'{name}/fwd1/logit_g{i}']).max() < tol(g[f'{name}/fwd1/logit_g{i}'])
+    if name == 'msd':
+        for k in [k for k in sd if k.endswith('weight_u')]:
+            assert np.abs(sd[k].numpy() - g[f'{name}/fwd1/{k}']).max() < 1e-5, k
+    _check_grads(g, f'{name}/d_grad', [(k, v.grad) for k, v in sd.items() if not is_buf(k)], DISC_GRAD_STRIDE, 2e-4)
+    with torch.no_grad():
+        rs2, gs2, _, _ = fwd()
+    for i, (r, gg) in enumerate(zip(rs2, gs2)):
+        assert np.abs(r.numpy() - g[f'{name}/fwd2/logit_r{i}']).max() < tol(g[f'{name}/fwd2/logit_r{i}'])
+        assert np.abs(gg.numpy() - g[f'{name}/fwd2/logit_g{i}']).max() < tol(g[f'{name}/fwd2/logit_g{i}'])
+    if name == 'msd':
+        for k in [k for k in sd if k.endswith('weight_u')]:
+            assert np.abs(sd[k].numpy() - g[f'{name}/fwd2/{k}']).max() < 1e-5, k
+    # generator side (eval-mode weights, discriminator frozen)
+    w = O.fold_discriminator_weights(sd0)
+    yh = y_hat.clone().requires_grad_(True)
+    rs, gs, fr, fg = (O.mpd_forward if name == 'mpd' else O.msd_forward)(y, yh, w)
+    lg = O.generator_loss(gs) + O.feature_loss(fr, fg)
+    lg.backward()
+    np.testing.assert_allclose(float(lg), float(g[f'{name}/g_loss']), rtol=2e-5)
+    assert abs(float(yh.grad.double().norm()) - float(g[f'{name}/g_dyhat_norm'])) < 2e-4 * float(g[f'{name}/g_dyhat_norm'])
+    assert np.abs(yh.grad.numpy()[:, 0, ::5] - g[f'{name}/g_dyhat_sub']).max() < 2e-3 * np.abs(g[f'{name}/g_dyhat_sub']).max()

@@ -49,7 +49,7 @@ class ToyGanTask(BaseTask):
 
     def training_step(self, batch, batch_idx, optimizer_idx=-1):
         ToyGanTask.calls.append(('train', batch_idx, optimizer_idx, self.model_gen.weight.requires_grad,
-                                 self.model_disc.weight.requires_grad))
+                                 next(self.model_disc.parameters()).requires_grad))
         y = self.model_gen(batch)
         if optimizer_idx == 0:
             loss = (1 - self.model_disc(y)).pow(2).mean()
@@ -195,3 +195,78 @@ def test_ddp_world_size_2_gloo_one_allreduce_per_optimizer_step(tmp_path, monkey
     t.fit(ToyGanTask)
     for name, v in t.task.model_gen.state_dict().items():
         assert torch.allclose(v, r0['gen'][name], atol=1e-6), name
+
+
+class SegTask(ToyGanTask):
+    """Discriminator optimizer exchanged in two segments (the vocoder task splits MSD / MPD the same way)."""
+
+    def build_model(self):
+        super().build_model()
+        self.model_disc = nn.Sequential(nn.Linear(4, 3), nn.Linear(3, 1))
+        return None
+
+    def grad_segments(self, opt_idx):
+        if opt_idx != 1:
+            return None
+        return [list(self.model_disc[1].parameters()), list(self.model_disc[0].parameters())]
+
+
+def _seg_worker(rank, world, port, work_dir, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES='')
+    hparams.clear()
+    hparams.update(HP)
+    t = Trainer(work_dir=os.path.join(work_dir, f'r{rank}'), val_check_interval=100, tb_log_interval=1000, max_updates=3,
+                num_sanity_val_steps=0, dist_backend='gloo', debug=True)
+    t.fit(SegTask)
+    torch.save({'gen': t.task.model_gen.state_dict(), 'disc': t.task.model_disc.state_dict(), 'steps': t.global_step,
+                'collectives': [r.collectives for r in t.reducers], 'bounds': [r.bounds for r in t.reducers]},
+               os.path.join(out, f'rank{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_ddp_segmented_exchange_matches_single_process(tmp_path, monkeypatch):
+    """grad_segments: the all-reduce of a segment is launched from the autograd hook of its last gradient (overlapping
+    the rest of backward); one collective per segment per optimizer step; same result as un-sharded training."""
+    world = 2
+    mp.spawn(_seg_worker, nprocs=world, args=(world, _free_port(), str(tmp_path), str(tmp_path)), join=True)
+    r0, r1 = (torch.load(tmp_path / f'rank{r}.pt', weights_only=False) for r in range(world))
+    for k in ('gen', 'disc'):
+        for name in r0[k]:
+            assert torch.equal(r0[k][name], r1[k][name])
+    assert r0['collectives'] == [r0['steps'], 2 * r0['steps']] and r0['bounds'][1] == [(0, 4), (4, 19)]
+    monkeypatch.setenv('CUDA_VISIBLE_DEVICES', '')
+    hparams.clear()
+    hparams.update(HP)
+    t = Trainer(work_dir=str(tmp_path / 'single'), val_check_interval=100, tb_log_interval=1000, max_updates=3, num_sanity_val_steps=0)
+    t.fit(SegTask)
+    for k, mod in (('gen', t.task.model_gen), ('disc', t.task.model_disc)):
+        for name, v in mod.state_dict().items():
+            assert torch.allclose(v, r0[k][name], atol=1e-6), (k, name)
+
+
+class RankProbeTask(ToyGanTask):
+    def train_dataloader(self):
+        rank, world, local = ddp_utils.dist_env()
+        with open(os.path.join(hparams['probe_dir'], f'probe{dist.get_rank()}.txt'), 'w') as f:
+            f.write(f'{rank} {world} {local} {os.environ.get("RANK")} {os.environ.get("WORLD_SIZE")}')
+        return [torch.stack(ddp_utils.shard(list(b), rank, world)) for b in self._data()]
+
+
+def _spawn_path_worker(local_idx, work_dir, port):
+    # what Trainer.fit's mp.spawn branch runs (utils/trainer.py: reference behaviour keyed on CUDA_VISIBLE_DEVICES):
+    # no torchrun variables in the environment
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+        os.environ.pop(k, None)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES='')
+    t = Trainer(work_dir=os.path.join(work_dir, f'r{local_idx}'), val_check_interval=100, tb_log_interval=1000, max_updates=1,
+                num_sanity_val_steps=0, dist_backend='gloo', debug=True)
+    t._ddp_worker(local_idx, RankProbeTask, dict(HP, probe_dir=work_dir), None, 2)
+    dist.destroy_process_group()
+
+
+def test_spawn_path_exports_rank_so_shards_are_disjoint(tmp_path):
+    """on the mp.spawn path every worker saw dist_env() == (0, 1, 0) and trained on identical shards."""
+    mp.spawn(_spawn_path_worker, nprocs=2, args=(str(tmp_path), _free_port()), join=True)
+    got = [open(tmp_path / f'probe{r}.txt').read().split() for r in range(2)]
+    assert got[0] == ['0', '2', '0', '0', '2'] and got[1] == ['1', '2', '1', '1', '2']
