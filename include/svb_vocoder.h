@@ -115,6 +115,15 @@ int svb_gen_forward(svb_gen_t *g, const float *mel_dev, const float *f0_dev, con
 int svb_gen_spec2wav_host(svb_gen_t *g, const float *mel_host, const float *f0_host, uint64_t seed,
                           int32_t B, int32_t T, float *wav_host, void *stream);
 
+/* spec2wav followed by save_wav's sample conversion (utils/audio.py:11-16: [norm: wav / max|wav| per clip,]
+ * wav * 32767, float -> int16 truncation toward zero) ON THE DEVICE, so the D2H copy is 2 bytes per sample:
+ * the reference moves the fp32 waveform to the host (vocoders/hifigan.py:63-66) and converts it in a CPU pool
+ * (tasks/tts/tts.py:111, svb_vae_task.py:373-375).  wav_host int16 [B, T*hop]. */
+int svb_gen_spec2wav_host_i16(svb_gen_t *g, const float *mel_host, const float *f0_host, uint64_t seed, int32_t B,
+                              int32_t T, int32_t norm, int16_t *wav_host, void *stream);
+/* the conversion alone on device buffers: wav_dev fp32 [B, n] -> out_dev int16 [B, n] (stream-ordered). */
+int svb_wav_to_int16(const float *wav_dev, int32_t B, int64_t n, int32_t norm, int16_t *out_dev, void *stream);
+
 /* Intermediate tap for layer-level parity tests: copies a named activation of the LAST forward
  * ("har_source" [B,T*hop]; "conv_pre", "ups{i}", "stage{i}" as [B,C,T_i]) to out_dev. */
 int svb_gen_get_tap(svb_gen_t *g, const char *name, float *out_dev, int64_t capacity_floats,
@@ -300,6 +309,15 @@ int svb_denoise(const svb_stft_config *cfg, const float *wav_dev, int32_t B, int
 int64_t svb_wav2spec_host(const svb_stft_config *cfg, const float *wav_host, int64_t n,
                           const float *mel_basis_host, float *mel_host, float *wav_out_host, int device,
                           void *stream);
+
+/* The binarizer's call site (data_gen/tts/base_binarizer.py:168-178, data_gen/singing/binarize_para.py:116-217 call
+ * wav2spec once per file from a CPU process pool) as ONE call over a ragged batch: `n_clips` waveforms concatenated in
+ * wav_concat_host with their lengths; mel_concat_host receives the [frames_c, n_mels] log10-mels back to back and
+ * frames_out[c] their frame counts (1 + lengths[c] / hop each).  One H2D, one kernel launch over all frames of all
+ * clips, one D2H.  Returns the total frame count or a negative status. */
+int64_t svb_wav2spec_batch_host(const svb_stft_config *cfg, const float *wav_concat_host, const int64_t *lengths,
+                                int32_t n_clips, const float *mel_basis_host, float *mel_concat_host, int64_t *frames_out,
+                                int device, void *stream);
 
 #ifdef __cplusplus
 }

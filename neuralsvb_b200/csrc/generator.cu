@@ -1,6 +1,8 @@
 // HiFi-GAN(-NSF) generator handle: weight packing, workspace planning and the forward schedule.
 // Reference: HifiGanGenerator (modules/hifigan/hifigan.py:104-178) as driven by
 // vocoders/hifigan.py:17-33 (load_model) and :55-69 (spec2wav).
+#include <algorithm>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -349,6 +351,7 @@ extern "C" void svb_gen_destroy(svb_gen_t *g) {
     if (g->pin_out) cudaFreeHost(g->pin_out);
     if (g->dev_in) cudaFree(g->dev_in);
     if (g->dev_out) cudaFree(g->dev_out);
+    if (g->dev_i16) cudaFree(g->dev_i16);
     for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 3; ++i) {
         if (g->side[i]) cudaStreamDestroy(g->side[i]);
@@ -499,6 +502,94 @@ extern "C" int svb_gen_spec2wav_host(svb_gen_t *g, const float *mel_host, const 
     SVB_CUDA(cudaMemcpyAsync(g->pin_out, g->dev_out, n_out * 4, cudaMemcpyDeviceToHost, st));
     SVB_CUDA(cudaStreamSynchronize(st));
     memcpy(wav_host, g->pin_out, n_out * 4);
+    return SVB_OK;
+}
+
+// ---- save_wav's sample conversion on the device (utils/audio.py:11-16): [norm: wav / max|wav| per clip,] wav * 32767,
+// numpy's float -> int16 cast (truncation toward zero).  Done before the D2H copy, the transfer is 2 bytes per sample.
+namespace {
+__global__ void clip_absmax_kernel(const float *__restrict__ x, long long n, unsigned *__restrict__ mx) {
+    const int b = blockIdx.y;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[(size_t)b * n + i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(mx + b, __float_as_uint(m));      // non-negative floats order like their bit patterns
+}
+__global__ void to_int16_kernel(const float *__restrict__ x, long long n, const unsigned *__restrict__ mx, int16_t *__restrict__ y) {
+    const int b = blockIdx.y;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = x[(size_t)b * n + i];
+        if (mx) v = __fdiv_rn(v, __uint_as_float(mx[b]));
+        v = __fmul_rn(v, 32767.f);
+        y[(size_t)b * n + i] = (int16_t)__float2int_rz(v);
+    }
+}
+int wav_to_int16(const float *wav_dev, int B, long long n, int norm, int16_t *out_dev, unsigned *mx_dev, cudaStream_t st) {
+    const dim3 grid((unsigned)std::min<long long>((n + 255) / 256, 148 * 4), (unsigned)B);
+    if (norm) {
+        SVB_CUDA(cudaMemsetAsync(mx_dev, 0, (size_t)B * sizeof(unsigned), st));
+        clip_absmax_kernel<<<grid, 256, 0, st>>>(wav_dev, n, mx_dev);
+    }
+    to_int16_kernel<<<grid, 256, 0, st>>>(wav_dev, n, norm ? mx_dev : nullptr, out_dev);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+}  // namespace
+
+extern "C" int svb_wav_to_int16(const float *wav_dev, int32_t B, int64_t n, int32_t norm, int16_t *out_dev, void *stream) {
+    SVB_CHECK(wav_dev && out_dev && B > 0 && n > 0, SVB_ERR_INVALID, "wav_to_int16: bad argument");
+    cudaStream_t st = as_stream(stream);
+    unsigned *mx = nullptr;
+    if (norm) SVB_CUDA(cudaMallocAsync((void **)&mx, (size_t)B * sizeof(unsigned), st));
+    const int rc = wav_to_int16(wav_dev, B, n, norm, out_dev, mx, st);
+    if (mx) cudaFreeAsync(mx, st);
+    return rc;
+}
+
+extern "C" int svb_gen_spec2wav_host_i16(svb_gen_t *g, const float *mel_host, const float *f0_host, uint64_t seed, int32_t B,
+                                         int32_t T, int32_t norm, int16_t *wav_host, void *stream) {
+    SVB_CHECK(g && g->finalized, SVB_ERR_STATE, "spec2wav_i16: generator not finalized");
+    SVB_CHECK(mel_host && wav_host && B > 0 && T > 0, SVB_ERR_INVALID, "spec2wav_i16: null buffer or empty input");
+    SVB_CUDA(cudaSetDevice(g->device));
+    cudaStream_t st = as_stream(stream);
+    const size_t n_mel = (size_t)B * T * g->cfg.n_mel, n_f0 = f0_host ? (size_t)B * T : 0;
+    const size_t n_in = n_mel + n_f0, n_out = (size_t)B * T * g->hop;
+    if (n_in > g->pin_in_cap) {
+        if (g->pin_in) cudaFreeHost(g->pin_in);
+        if (g->dev_in) cudaFree(g->dev_in);
+        g->pin_in = nullptr, g->dev_in = nullptr, g->pin_in_cap = 0;
+        SVB_CUDA(cudaMallocHost((void **)&g->pin_in, n_in * 4));
+        SVB_CUDA(cudaMalloc((void **)&g->dev_in, n_in * 4));
+        g->pin_in_cap = n_in;
+    }
+    if (n_out > g->pin_out_cap) {
+        if (g->pin_out) cudaFreeHost(g->pin_out);
+        if (g->dev_out) cudaFree(g->dev_out);
+        g->pin_out = nullptr, g->dev_out = nullptr, g->pin_out_cap = 0;
+        SVB_CUDA(cudaMallocHost((void **)&g->pin_out, n_out * 4));
+        SVB_CUDA(cudaMalloc((void **)&g->dev_out, n_out * 4));
+        g->pin_out_cap = n_out;
+    }
+    if (n_out > g->i16_cap) {
+        if (g->dev_i16) cudaFree(g->dev_i16);
+        g->dev_i16 = nullptr, g->i16_cap = 0;
+        SVB_CUDA(cudaMalloc((void **)&g->dev_i16, n_out * 2 + (size_t)4096 * sizeof(unsigned)));
+        g->i16_cap = n_out;
+    }
+    SVB_CHECK(B <= 4096, SVB_ERR_INVALID, "spec2wav_i16: batch %d > 4096", B);
+    memcpy(g->pin_in, mel_host, n_mel * 4);
+    if (f0_host) memcpy(g->pin_in + n_mel, f0_host, n_f0 * 4);
+    SVB_CUDA(cudaMemcpyAsync(g->dev_in, g->pin_in, n_in * 4, cudaMemcpyHostToDevice, st));
+    SVB_TRY(forward_impl(g, g->dev_in, true, f0_host ? g->dev_in + n_mel : nullptr, nullptr, nullptr, seed, B, T, g->dev_out, st));
+    unsigned *mx;
+    mx = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(g->dev_i16) + (g->i16_cap * 2 + 3) / 4 * 4);
+    SVB_TRY(wav_to_int16(g->dev_out, B, (long long)T * g->hop, norm, g->dev_i16, mx, st));
+    // the pinned float staging buffer is large enough for the 2-byte samples
+    SVB_CUDA(cudaMemcpyAsync(g->pin_out, g->dev_i16, n_out * 2, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    memcpy(wav_host, g->pin_out, n_out * 2);
     return SVB_OK;
 }
 

@@ -118,6 +118,8 @@ struct svb_gen {
     // host staging (spec2wav_host)
     float *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
     size_t pin_in_cap = 0, pin_out_cap = 0;
+    int16_t *dev_i16 = nullptr;      // int16 samples + per-clip peak (svb_gen_spec2wav_host_i16)
+    size_t i16_cap = 0;
 
     int64_t last_launches = 0;
     double last_flops = 0;

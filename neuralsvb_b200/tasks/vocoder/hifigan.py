@@ -55,7 +55,12 @@ class HifiGanInferTask(BaseTask):
 
     def test_step(self, sample, batch_idx):
         t0 = time.time()
-        wav = self.vocoder.spec2wav(sample['mel'], f0=sample['f0'] if hparams.get('use_pitch_embed', True) else None)
+        f0 = sample['f0'] if hparams.get('use_pitch_embed', True) else None
+        if hparams.get('vocoder_denoise_c', 0.0) > 0 or not hparams.get('save_int16_on_device', True):
+            wav = self.vocoder.spec2wav(sample['mel'], f0=f0)
+        else:           # save_wav's float -> int16 on the device: half the D2H bytes (utils/audio.py:11-16)
+            wav = self.vocoder.spec2wav_batch(np.asarray(sample['mel'], np.float32)[None],
+                                              None if f0 is None else np.asarray(f0, np.float32)[None], int16=True)[0]
         dt = time.time() - t0
         audio.save_wav(wav.copy(), os.path.join(self.gen_dir, sample['name'] + '.wav'), hparams['audio_sample_rate'])
         return {'audio_s': len(wav) / hparams['audio_sample_rate'], 'wall_s': dt}
@@ -141,9 +146,26 @@ class HifiGanTask(HifiGanInferTask):
             return None
         return [list(self.model_disc['msd'].parameters()), list(self.model_disc['mpd'].parameters())]
 
+    def _dataset_loader(self, prefix, shuffle, endless):
+        """IndexedDataset-backed batches (tasks/vocoder/dataset_utils.py) when ``binary_data_dir/{prefix}.data`` exists."""
+        import torch
+        from neuralsvb_b200.tasks.vocoder.dataset_utils import VocoderBatchLoader
+        path = os.path.join(hparams.get('binary_data_dir') or '', prefix)
+        if not hparams.get('binary_data_dir') or not os.path.exists(path + '.data'):
+            return None
+        rank, world, local = ddp_utils.dist_env()
+        dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
+        return VocoderBatchLoader(path, hparams['hop_size'], hparams.get('max_samples', 8192), hparams.get('max_sentences', 24),
+                                  rank=rank, world=world, seed=hparams['seed'], shuffle=shuffle, endless=endless,
+                                  n_mel=hparams['audio_num_mel_bins'], device=dev)
+
     def train_dataloader(self):
-        """Synthetic clips of ``max_samples`` samples (hifigan.yaml:23-24), ``max_sentences`` per batch, sharded by rank."""
+        """A binarized dataset (``binary_data_dir``: the reference's IndexedDataset format) when there is one; otherwise
+        synthetic clips of ``max_samples`` samples (hifigan.yaml:23-24), ``max_sentences`` per batch, sharded by rank."""
         from neuralsvb_b200.utils import synthetic as S
+        ds = self._dataset_loader('train', True, hparams.get('endless_ds', False))
+        if ds is not None:
+            return ds
         hop = hparams['hop_size']
         n = int(hparams.get('max_samples', 8192)) // hop * hop
         B = int(hparams.get('max_sentences', 24))
@@ -186,6 +208,9 @@ class HifiGanTask(HifiGanInferTask):
         return wav2spec_mel(y.squeeze(1), hparams)
 
     def val_dataloader(self):
+        ds = self._dataset_loader('valid', False, False)
+        if ds is not None:
+            return ds
         return self.train_dataloader()[:1]
 
     def validation_step(self, sample, batch_idx):

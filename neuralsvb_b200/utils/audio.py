@@ -65,9 +65,14 @@ def normalize(S, hparams):
 
 
 def save_wav(wav, path, sr, norm=False):
-    """float waveform -> int16 wav file (utils/audio.py:11-16)."""
+    """float waveform -> int16 wav file (utils/audio.py:11-16).  An int16 array (the device-side conversion of
+    ``HifiGAN.spec2wav_batch(int16=True)``) is written as is."""
     from scipy.io import wavfile
-    wav = np.asarray(wav, dtype=np.float32)
+    wav = np.asarray(wav)
+    if wav.dtype == np.int16:
+        wavfile.write(path, sr, wav)
+        return
+    wav = wav.astype(np.float32)
     if norm:
         wav = wav / np.abs(wav).max()
-    wavfile.write(path, sr, (wav * 32767).astype(np.int16))
+    wavfile.write(path, sr, (wav * np.float32(32767)).astype(np.int16))

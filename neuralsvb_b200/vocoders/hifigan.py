@@ -109,9 +109,12 @@ class HifiGAN(BaseVocoder):
                                    else np.asarray(kwargs['f0'], dtype=np.float32)[None],
                                    seed=kwargs.get('seed'))[0]
 
-    def spec2wav_batch(self, mels, f0s=None, seed=None):
+    def spec2wav_batch(self, mels, f0s=None, seed=None, int16=False, norm=False):
         """mels [B, T, n_mel], f0s [B, T] or None (host arrays) -> np.float32 [B, T*hop].
-        One call = pinned staging + H2D + generator + D2H + stream sync (svb_gen_spec2wav_host)."""
+        One call = pinned staging + H2D + generator + D2H + stream sync (svb_gen_spec2wav_host).
+        ``int16=True``: save_wav's sample conversion (utils/audio.py:11-16; ``norm`` = its peak normalisation) runs on
+        the device and np.int16 [B, T*hop] comes back -- half the D2H bytes, nothing left for the CPU writer pool to do
+        but ``wavfile.write`` (svb_gen_spec2wav_host_i16; the denoise post-filter needs the float path)."""
         mels = np.ascontiguousarray(mels, dtype=np.float32)
         B, T, C = mels.shape
         if f0s is not None:
@@ -120,10 +123,21 @@ class HifiGAN(BaseVocoder):
         lib = _native.lib()
         g = self.model.native_handle(self.device)
         hop = int(lib.svb_gen_hop(g))
-        out = np.empty((B, T * hop), np.float32)
+        if int16 and hparams.get('vocoder_denoise_c', 0.0) > 0:
+            raise ValueError('int16 output and vocoder_denoise_c > 0 are exclusive (the post-filter works on floats)')
+        out = np.empty((B, T * hop), np.int16 if int16 else np.float32)
         if seed is None:
             self.model.seed += 1
             seed = self.model.seed
+        if int16:
+            with torch.no_grad(), torch.cuda.device(self.device):
+                with utils.Timer('hifigan', enable=hparams.get('profile_infer', False)):
+                    _native.check(lib.svb_gen_spec2wav_host_i16(
+                        g, mels.ctypes.data_as(ctypes.c_void_p),
+                        None if f0s is None else f0s.ctypes.data_as(ctypes.c_void_p),
+                        ctypes.c_uint64(seed), B, T, int(bool(norm)), out.ctypes.data_as(ctypes.c_void_p),
+                        _native.current_stream_ptr(self.device)), 'spec2wav_i16')
+            return out
         with torch.no_grad(), torch.cuda.device(self.device):
             with utils.Timer('hifigan', enable=hparams.get('profile_infer', False)):
                 st = _native.current_stream_ptr(self.device)
@@ -134,6 +148,45 @@ class HifiGAN(BaseVocoder):
         if hparams.get('vocoder_denoise_c', 0.0) > 0:                  # vocoders/hifigan.py:66-69
             from neuralsvb_b200.vocoders.vocoder_utils import denoise
             out = np.stack([denoise(o, v=hparams['vocoder_denoise_c']) for o in out])
+        return out
+
+    @staticmethod
+    def wav2spec_batch(wav_fns, hp=None):
+        """The binarizer's per-file ``wav2spec`` loop (data_gen/tts/base_binarizer.py:168-178,
+        data_gen/singing/binarize_para.py:116-217) as ONE device call over a ragged batch: list of paths / float arrays
+        -> list of (wav [T*hop], mel [T, n_mel] log10), identical to ``wav2spec`` clip by clip
+        (svb_wav2spec_batch_host: one H2D, one launch over all frames of all clips, one D2H)."""
+        hp = hparams if hp is None else hp
+        device = _require_cuda()
+        if hp.get('loud_norm', False):
+            raise NotImplementedError('loud_norm (pyloudnorm BS.1770) is data preparation, outside this path')
+        wavs = [_load_wav(w, hp['audio_sample_rate']) if isinstance(w, str) else np.ascontiguousarray(w, dtype=np.float32)
+                for w in wav_fns]
+        if not wavs:
+            return []
+        lib = _native.lib()
+        cfg = stft_config(hp, _native.PAD_CENTER_ZERO, _native.OUT_LOG10_MEL, float(hp.get('wav2spec_eps', 1e-10)))
+        lengths = np.array([len(w) for w in wavs], np.int64)
+        frames = lengths // cfg.hop + 1
+        cat = np.ascontiguousarray(np.concatenate(wavs))
+        basis = np.ascontiguousarray(audio.build_mel_basis(hp))
+        mel = np.empty((int(frames.sum()), cfg.n_mels), np.float32)
+        got = np.zeros(len(wavs), np.int64)
+        with torch.cuda.device(device):
+            rc = lib.svb_wav2spec_batch_host(ctypes.byref(cfg), cat.ctypes.data_as(ctypes.c_void_p),
+                                             lengths.ctypes.data_as(ctypes.c_void_p), len(wavs),
+                                             basis.ctypes.data_as(ctypes.c_void_p), mel.ctypes.data_as(ctypes.c_void_p),
+                                             got.ctypes.data_as(ctypes.c_void_p), device.index,
+                                             _native.current_stream_ptr(device))
+            _native.check(rc, 'wav2spec_batch')
+        assert np.array_equal(got, frames), (got, frames)
+        out, o = [], 0
+        for w, fr in zip(wavs, frames):
+            n_out = int(fr) * cfg.hop                       # audio.librosa_pad_lr + wav[:T * hop] (data_gen_utils.py:138-140)
+            wo = np.zeros(n_out, np.float32)
+            wo[:min(len(w), n_out)] = w[:n_out]
+            out.append((wo, mel[o:o + int(fr)]))
+            o += int(fr)
         return out
 
     @staticmethod

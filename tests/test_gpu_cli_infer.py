@@ -50,7 +50,7 @@ def test_run_py_trains_the_vocoder_for_a_few_steps(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert 'Training end' in r.stdout
     import re
-    mels = [float(m) for m in re.findall(r"'mel': ([0-9.eE+-]+)", r.stdout)]
+    mels = [float(m) for m in re.findall(r"\bmel ([0-9.eE+-]+)", r.stdout)]        # '| step N: mel 1.2345, a 0.5, ...' 
     assert len(mels) >= 4 and mels[-1] < mels[0], mels
     ckpts = list((tmp_path / 'checkpoints' / 'cli_train').glob('model_ckpt_steps_*.ckpt'))
     assert ckpts, r.stdout[-2000:]

@@ -201,3 +201,103 @@ def test_training_mode_discriminators_match_reference_fixture(golden_dir, name):
             assert e < gtol, e
         finally:
             D.USE_TC = True
+
+
+def test_int16_conversion_matches_reference_save_wav_fixture(golden_dir):
+    """N4: save_wav's float -> int16 (utils/audio.py:11-16) on the device, bit exact against the reference's wav file."""
+    from neuralsvb_b200.vocoders.vocoder_utils import wav_to_int16
+    g = np.load(os.path.join(golden_dir, 'losses_extra.npz'))
+    wav = np.clip(S.make_clip(4000, seed=SEED + 4) * 1.7, -1.0, 1.0).astype(np.float32)
+    for norm in (0, 1):
+        got = wav_to_int16(torch.from_numpy(wav).cuda(), bool(norm)).cpu().numpy()
+        assert got.dtype == np.int16 and np.array_equal(got, g[f'save_wav/int16_norm{norm}']), norm
+    # batched, per-clip peak
+    w2 = np.stack([wav, 0.25 * wav[::-1]])
+    got = wav_to_int16(torch.from_numpy(w2.copy()).cuda(), True).cpu().numpy()
+    from oracle import frontend as FE
+    assert np.array_equal(got[0], FE.float_to_int16(w2[0], True)) and np.array_equal(got[1], FE.float_to_int16(w2[1], True))
+
+
+def test_spec2wav_int16_output_is_the_converted_float_output():
+    from neuralsvb_b200.vocoders.hifigan import HifiGAN
+    from oracle import frontend as FE
+    h = S.hifigan_config()
+    m = U.cuda_generator('hop256', True, 'bf16x3')
+    voc = HifiGAN.from_model(m, h)
+    mel, f0 = S.make_mel_f0(2, 24, SEED)
+    mels, f0s = np.ascontiguousarray(mel.permute(0, 2, 1).numpy()), f0.numpy()
+    yf = voc.spec2wav_batch(mels, f0s, seed=11)
+    for norm in (False, True):
+        yi = voc.spec2wav_batch(mels, f0s, seed=11, int16=True, norm=norm)
+        assert yi.dtype == np.int16 and yi.shape == yf.shape
+        for b in range(2):
+            assert np.array_equal(yi[b], FE.float_to_int16(yf[b], norm)), (norm, b)
+
+
+def test_wav2spec_batch_is_the_per_clip_call_and_matches_the_reference_fixture(golden_dir):
+    """N2: a ragged batch through ONE device call == wav2spec clip by clip == the reference's process_utterance."""
+    from neuralsvb_b200.vocoders.hifigan import HifiGAN
+    g = np.load(os.path.join(golden_dir, 'frontend.npz'))
+    hp = dict(S.hifigan_config(), min_level_db=-100)
+    lens = [44100, 1000, 255, 256, 7777, 1]
+    wavs = [S.make_clip(n, seed=SEED) for n in lens]
+    got = HifiGAN.wav2spec_batch(wavs, hp=hp)
+    assert len(got) == len(wavs)
+    for n, w, (wo, mel) in zip(lens, wavs, got):
+        w1, m1 = HifiGAN.wav2spec(w, hp=hp)
+        assert mel.shape == (n // 256 + 1, 80) and len(wo) == mel.shape[0] * 256          # frame indexing: bit exact
+        assert np.array_equal(mel, m1) and np.array_equal(wo, w1)
+    for name, idx in (('cfg1_win512', 0), ('ragged_short', 1)):
+        ref = g[f'{name}/mel']
+        assert np.abs(got[idx][1] - ref).max() / np.abs(ref).max() < 1e-3                   # north star: 1e-3 rel L-inf on mel frames
+
+
+def test_binarizer_dataset_loader_and_training_step(tmp_path):
+    """N2 + N3 end to end: VocoderBinarizer (batched wav2spec on the device, the reference's IndexedDataset on disk)
+    -> VocoderBatchLoader (pinned ring, its own H2D stream) -> one G + D training step of HifiGanTask's wiring."""
+    from neuralsvb_b200.data_gen.tts.base_binarizer import VocoderBinarizer
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    from neuralsvb_b200.tasks.vocoder.dataset_utils import VocoderBatchLoader
+    from neuralsvb_b200.tasks.vocoder.hifigan import HifiGanTask, vocoder_losses
+    from neuralsvb_b200.utils.hparams import hparams
+    from neuralsvb_b200.utils.indexed_datasets import IndexedDataset
+    from neuralsvb_b200.vocoders.hifigan import HifiGAN
+    hp = dict(S.hifigan_config(), vocoder='neuralsvb_b200.vocoders.hifigan.HifiGAN', binary_data_dir=str(tmp_path), seed=SEED,
+              lambda_mel=5.0, lambda_adv=1.0, use_fm_loss=False, use_ms_stft=False)
+    hparams.clear()
+    hparams.update(hp)
+    try:
+        clips = [S.make_clip(256 * (40 + 3 * i) + 17 * i, seed=SEED + i) for i in range(6)]
+        items = {'train': [(f'clip{i}', c, 0) for i, c in enumerate(clips)]}
+        f0_of = lambda wav, mel: np.full(len(mel), 220.0, np.float32)
+        stats = VocoderBinarizer(items, pitch_fn=f0_of, batch_seconds=2.0).process()
+        assert stats['train']['items'] == 6
+        ds = IndexedDataset(str(tmp_path / 'train'))
+        it = ds[2]
+        w1, m1 = HifiGAN.wav2spec(clips[2], hp=hp)
+        assert it['wav'].dtype == np.float16 and np.array_equal(it['mel'], m1) and it['len'] == len(m1)     # base_binarizer.py:176
+        assert np.array_equal(it['wav'], w1.astype(np.float16))
+        ld = VocoderBatchLoader(str(tmp_path / 'train'), 256, 8192, 3, seed=SEED, device='cuda:0')
+        batches = list(ld)
+        assert len(batches) == 2 and batches[0]['wavs'].is_cuda and batches[0]['mels'].shape == (3, 32, 80)
+        b = batches[0]
+        i = int(b['item_names'][0][4:])
+        full = ds[i]
+        # the crop is frame aligned: its mel rows are rows of the stored mel
+        hit = [s for s in range(len(full['mel']) - 31) if np.array_equal(full['mel'][s:s + 32], b['mels'][0].cpu().numpy())]
+        assert len(hit) == 1
+        s = hit[0]
+        assert np.array_equal(b['wavs'][0, 0].cpu().numpy(), full['wav'][s * 256:(s + 32) * 256].astype(np.float32))
+        # one G + D step on the loaded batch (conditioning mel = the binarized log10-mel, [B, T, 80] -> [B, 80, T])
+        gen = HifiGanGenerator(hp, precision='bf16x3').cuda().train()
+        mpd, msd = D.MultiPeriodDiscriminator().cuda().train(), D.MultiScaleDiscriminator().cuda().train()
+        mel = HifiGanTask._cond_mel(b, b['wavs'])
+        assert mel.shape == (3, 80, 32)
+        lg, _, yh = vocoder_losses(gen, mpd, msd, b['wavs'], mel, b['f0'], hp, 0)
+        lg.backward()
+        ld_, _, _ = vocoder_losses(None, mpd, msd, b['wavs'], mel, b['f0'], hp, 1, y_hat=yh)
+        ld_.backward()
+        assert np.isfinite(float(lg)) and np.isfinite(float(ld_))
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in gen.parameters())
+    finally:
+        hparams.clear()

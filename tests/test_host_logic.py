@@ -112,3 +112,52 @@ def test_tensor_core_eligibility_of_discriminator_layers():
     # MSD: grouped layers stay on CUDA cores, the dense 1024 -> 1024 k5 layer does not
     assert not D.tc_eligible(128, 128, 41, 2, 1, 20, 4) and D.tc_eligible(1024, 1024, 5, 1, 1, 2, 1)
     assert not D.tc_eligible(1024, 1024, 5, 1, 1, 1, 1)        # not 'same' padding
+
+
+def test_indexed_dataset_format_and_vocoder_loader(tmp_path):
+    """N3: the reference's on-disk format ({path}.data = concatenated pickles, {path}.idx = np.save'd offsets,
+    utils/indexed_datasets.py:7-54) and the batch loader on top of it: frame-aligned crops, [B,1,n] / [B,T,80] / [B,T]
+    tensors, the global batch sharded batch[rank::world] with disjoint shards, uneven tails dropped."""
+    import pickle
+    import numpy as np
+    from neuralsvb_b200.tasks.vocoder.dataset_utils import VocoderBatchLoader
+    from neuralsvb_b200.utils.indexed_datasets import IndexedDataset, IndexedDatasetBuilder
+    hop, n_items = 16, 11
+    rs = np.random.RandomState(0)
+    path = str(tmp_path / 'train')
+    b = IndexedDatasetBuilder(path)
+    items = []
+    for i in range(n_items):
+        T = 20 + 3 * i
+        mel = rs.randn(T, 80).astype(np.float32)
+        wav = (np.arange(T * hop) % hop + 100 * i).astype(np.float16)          # sample value encodes (item, position in frame)
+        f0 = np.arange(T, dtype=np.float32) + 1000 * i
+        items.append({'item_name': f'it{i}', 'mel': mel, 'wav': wav, 'f0': f0, 'len': T, 'sec': T * hop / 22050})
+        b.add_item(items[-1])
+    b.finalize()
+    # byte layout of the reference: offsets index concatenated pickles
+    off = np.load(path + '.idx', allow_pickle=True).item()['offsets']
+    raw = open(path + '.data', 'rb').read()
+    assert len(off) == n_items + 1 and off[-1] == len(raw)
+    assert pickle.loads(raw[off[3]:off[4]])['item_name'] == 'it3'
+    ds = IndexedDataset(path)
+    assert len(ds) == n_items and np.array_equal(ds[5]['mel'], items[5]['mel'])
+    with pytest.raises(IndexError):
+        ds[n_items]
+    seen = []
+    for rank in range(2):
+        ld = VocoderBatchLoader(path, hop, max_samples=8 * hop, max_sentences=2, rank=rank, world=2, seed=3, pin=False)
+        assert len(ld) == n_items // 4
+        batches = list(ld)
+        assert len(batches) == 2                                               # 11 items, global batch 4: the tail of 3 is dropped
+        for bt in batches:
+            assert bt['wavs'].shape == (2, 1, 8 * hop) and bt['mels'].shape == (2, 8, 80) and bt['f0'].shape == (2, 8)
+            for j, name in enumerate(bt['item_names']):
+                i = int(name[2:])
+                s = int(bt['f0'][j, 0]) - 1000 * i                             # crop start frame, recovered from f0
+                assert np.array_equal(bt['mels'][j].numpy(), items[i]['mel'][s:s + 8])
+                assert np.array_equal(bt['wavs'][j, 0].numpy(), items[i]['wav'][s * hop:(s + 8) * hop].astype(np.float32))
+            seen.append((rank, tuple(bt['item_names'])))
+    r0 = {n for r, names in seen if r == 0 for n in names}
+    r1 = {n for r, names in seen if r == 1 for n in names}
+    assert not (r0 & r1) and len(r0) == len(r1) == 4                           # disjoint shards of the same global batches
