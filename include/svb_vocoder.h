@@ -181,6 +181,15 @@ int svb_loss_grad_dev(const float *a_dev, const float *b_dev, int32_t kind, floa
 typedef struct svb_tc_layer svb_tc_layer_t;
 int svb_tc_layer_create(int32_t Cin, int32_t Cout, int32_t K, int32_t stride, int32_t pad, int32_t precision, int device,
                         svb_tc_layer_t **out);
+/* The GROUPED k = 41 layers of DiscriminatorS (Conv1d(128,128,41,2,groups=4) ... Conv1d(1024,1024,41,1,groups=16),
+ * modules/hifigan/hifigan.py:263-267: 32 % of the discriminators' FLOPs) on the same tcgen05 kernel, in polyphase
+ * form: a stride-s conv with K taps = a stride-1 conv with ceil(K/s) taps over Cin*s "space-to-depth" channels (a
+ * permutation of the input, 1x traffic); every GEMM column block contracts only over the input channels of its own conv
+ * groups.  forward / backward / set_weight_dev / out_len / destroy are the svb_tc_layer_* calls below; weights are
+ * the natural [Cout, Cin/groups, K] tensor.  Needs ceil(K/stride) odd and (Cin/groups*stride, Cout/groups) to tile into
+ * 32-channel chunks (pairs of narrow groups share a tile). */
+int svb_tc_layer_create_grouped(int32_t Cin, int32_t Cout, int32_t K, int32_t stride, int32_t pad, int32_t groups,
+                                int32_t precision, int device, svb_tc_layer_t **out);
 void svb_tc_layer_destroy(svb_tc_layer_t *layer);
 int svb_tc_layer_set_weight_dev(svb_tc_layer_t *layer, const float *w_dev, const float *bias_dev, void *stream);
 int64_t svb_tc_layer_out_len(const svb_tc_layer_t *layer, int64_t T);

@@ -114,6 +114,7 @@ _PROTOS = {
     'svb_loss_grad': (ctypes.c_int, [_P, _P, _I32, ctypes.c_float, _P, _I64, _I32, _P]),
     'svb_loss_grad_dev': (ctypes.c_int, [_P, _P, _I32, ctypes.c_float, _P, _P, _I64, _I32, _P]),
     'svb_tc_layer_create': (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, ctypes.c_int, ctypes.POINTER(_P)]),
+    'svb_tc_layer_create_grouped': (ctypes.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, _I32, ctypes.c_int, ctypes.POINTER(_P)]),
     'svb_tc_layer_destroy': (None, [_P]),
     'svb_tc_layer_set_weight_dev': (ctypes.c_int, [_P, _P, _P, _P]),
     'svb_tc_layer_out_len': (_I64, [_P, _I64]),

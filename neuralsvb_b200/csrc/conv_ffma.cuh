@@ -28,6 +28,8 @@ struct ConvArgs {
     float in_slope;       // leaky-relu slope applied to `in` on load (1 = identity)
     float out_scale;
     int accumulate;
+    int cin_blk = 0;      // grouped convolution (tensor-core kernel only): input channels read by ONE column block
+                          // (block nblk reads channels [nblk*cin_blk, (nblk+1)*cin_blk)); 0 = dense (all Cin)
 };
 
 int launch_conv_ffma(const ConvArgs &a, cudaStream_t st);

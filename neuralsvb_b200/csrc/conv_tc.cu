@@ -41,6 +41,7 @@ struct TcArgs {
     int n_sets;                 // accumulator sets in TMEM: 2 = epilogue of group g overlaps MMAs of g+1; 1 = MT can be twice as large
     int col_blocks, groups_per_b, total_groups;
     int tps, n_st, w_resident;  // taps per weight stage, stages per chunk, whole layer resident in smem
+    int blk_chunk_step;         // grouped conv: first input chunk of column block nblk = nblk * blk_chunk_step (0: dense)
     uint32_t wstage_bytes;      // ring slot = tps weight tiles
     int pdl;                    // launched with programmatic stream serialization
     int dbg;                    // SVB_TC_DBG bit mask: 1 no MMAs, 2 hi*hi only, 4 no transform, 8 no epilogue ld/st
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
             for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
                 const int b = rb % a.B, nblk = rb / a.B;
                 const int t0 = tg * (kTcM * p.MT);
-                const float *in_c = a.in + ((size_t)b * gin * a.in_Tp + (kPad + t0 - halo)) * 32;
+                const float *in_c = a.in + (((size_t)b * gin + (size_t)nblk * p.blk_chunk_step) * a.in_Tp + (kPad + t0 - halo)) * 32;
                 const unsigned char *w_c = p.w + (size_t)nblk * p.n_chunks * chunk_w_bytes;
                 for (int c = 0; c < p.n_chunks; ++c) {
                     mbar_wait(a_empty + sA, phA);                                 // MMAs of the slot's previous slab retired
@@ -478,9 +479,10 @@ static int pick_n_tile(int CoutP) {      // columns per CTA: a multiple of 32 (o
 
 // Weight tiles in K-major SWIZZLE_128B order: row n (output column) = 128 bytes holding the 32 input
 // channels of the chunk; the 16-byte chunk c of row n is stored at chunk position c ^ (n & 7).
-int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs) {
+int tc_pack_weights(const float *packed, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs, int force_n_tile) {
     out->KS = KS, out->Cin = Cin, out->CoutP = CoutP, out->ok = false;
-    const int n_tile = pick_n_tile(CoutP);
+    const int n_tile = force_n_tile > 0 ? force_n_tile : pick_n_tile(CoutP);
+    if (force_n_tile > 0 && (CoutP % force_n_tile != 0 || force_n_tile % 32 != 0 || force_n_tile > 128)) return SVB_OK;
     if (n_tile == 0 || n_tile % 8 != 0 || Cin % 4 != 0) return SVB_OK;    // CUDA cores handle it
     out->n_tile = n_tile;
     // input channels are padded to whole 32-channel groups (zero weights against the zero pad channels of G32T)
@@ -570,6 +572,7 @@ int tc_repack_weights_dev(const float *packed_dev, const TcWeights &w, cudaStrea
 }
 
 bool tc_supported(const TcWeights &w, const ConvArgs &a) {
+    if (a.cin_blk > 0 && (a.cin_blk % 32 != 0 || a.ups_u != 0 || (a.CoutP / w.n_tile) * a.cin_blk != a.Cin || w.Cin != a.cin_blk)) return false;
     return w.ok && a.Cin % 4 == 0 && a.bias != nullptr && (a.KS - 1) / 2 * a.dil <= kPad &&
            (a.ups_u == 0 || a.Cout % 32 == 0) && a.Cout <= 3072;
 }
@@ -619,7 +622,9 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
               precision);
     TcArgs p;
     p.a = a, p.w = reinterpret_cast<const unsigned char *>(w.blob[precision]);
-    p.n_tile = w.n_tile, p.n_chunks = (a.Cin + kTcCK - 1) / kTcCK;
+    const int cin_eff = a.cin_blk > 0 ? a.cin_blk : a.Cin;     // input channels one column block contracts over
+    p.n_tile = w.n_tile, p.n_chunks = (cin_eff + kTcCK - 1) / kTcCK;
+    p.blk_chunk_step = a.cin_blk > 0 ? p.n_chunks : 0;
     const int halo = (a.KS - 1) / 2 * a.dil;
     const int tiles = (a.Tq + kTcM - 1) / kTcM;              // 128-row tiles per clip
     p.col_blocks = a.CoutP / p.n_tile;

@@ -14,7 +14,10 @@ struct TcWeights {
 };
 
 // packed_ffma: [KS][Cin][CoutP] fp32 (the FFMA packing).  Allocations are appended to `allocs`.
-int tc_pack_weights(const float *packed_ffma, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs);
+// force_n_tile > 0: GEMM columns per CTA fixed by the caller (grouped layers: one tile = whole conv groups; `Cin` is then
+// the number of input channels ONE column block contracts over and packed_ffma is [KS][Cin][CoutP])
+int tc_pack_weights(const float *packed_ffma, int KS, int Cin, int CoutP, TcWeights *out, std::vector<void *> *allocs,
+                    int force_n_tile = 0);
 // same packing on the device, from a device copy of the FFMA packing into the blobs tc_pack_weights allocated
 // (training: the weights change after every optimizer step)
 int tc_repack_weights_dev(const float *packed_ffma_dev, const TcWeights &w, cudaStream_t st);

@@ -49,7 +49,7 @@ __global__ void expand_to_g32t_kernel(const float *__restrict__ x, const float *
 
 // y[b][c][t][w] = lrelu(g[clip][c][t], slope)
 __global__ void g32t_to_nctw_kernel(const float *__restrict__ g, int B, int C, int T, int W, int Tp, float slope,
-                                    float *__restrict__ y) {
+                                    float *__restrict__ y, int row0) {
     const int groups = c4t_groups(C);
     const long long total = (long long)B * C * T * W;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -58,7 +58,7 @@ __global__ void g32t_to_nctw_kernel(const float *__restrict__ g, int B, int C, i
         const int t = (int)(r % T);
         r /= T;
         const int c = (int)(r % C), b = (int)(r / C);
-        const float v = g[((((size_t)b * W + w) * groups + (c >> 5)) * Tp + kPad + t) * 32 + (c & 31)];
+        const float v = g[((((size_t)b * W + w) * groups + (c >> 5)) * Tp + kPad + row0 + t) * 32 + (c & 31)];
         y[i] = v >= 0.f ? v : v * slope;
     }
 }
@@ -129,6 +129,9 @@ struct svb_tc_layer {
     float *bias = nullptr, *zero_bias = nullptr;
     std::vector<void *> allocs;
     bool has_w = false;
+    // grouped layers (svb_tc_layer_create_grouped): polyphase form, see below
+    bool poly = false;
+    int groups = 1, KSp = 1, halo = 0, cin_blk_f = 0, cin_blk_b = 0;
 };
 
 static std::vector<int> to_idx(const std::vector<float> &v) {
@@ -194,6 +197,95 @@ extern "C" int svb_tc_layer_create(int32_t Cin, int32_t Cout, int32_t K, int32_t
     return SVB_OK;
 }
 
+
+// ---- grouped (and strided) convolutions: the k = 41 layers of DiscriminatorS (hifigan.py:263-267, groups 4 / 16) ----------
+// Polyphase ("space to depth") form: with k = q*s + r,
+//     y[to] = sum_q sum_r w[q*s + r] x[(to + q)*s + r - pad]  =  sum_q W'_q . x'[to + q],   x'[c*s + r][m] = x[c][m*s + r - pad]
+// i.e. a STRIDE-1 convolution with KS' = ceil(K / s) taps over Cin*s channels -- a permutation of the input (1x traffic;
+// the tap-major expansion of the dense strided layers would cost K = 41x).  x' has T' = Tout + KS' - 1 rows; output row
+// `to` is row to + h of the centred conv (h = (KS' - 1) / 2).  Conv groups stay contiguous channel ranges of x', so column
+// block nb of the GEMM (n_tile = gpt whole conv groups of outputs) contracts only over ITS input chunks
+// (ConvArgs::cin_blk); when a conv group is narrower than a 32-channel chunk (cin/g * s = 16) gpt = 2 groups share a
+// tile with block-diagonal weights.  Data gradient = the same kernel on the transposed, tap-flipped weights (dy -> dx'),
+// then the inverse permutation; weight gradient = wgrad_tc in grouped / polyphase mode.
+extern "C" int svb_tc_layer_create_grouped(int32_t Cin, int32_t Cout, int32_t K, int32_t stride, int32_t pad, int32_t groups,
+                                           int32_t precision, int device, svb_tc_layer_t **out) {
+    SVB_CHECK(out && Cin > 0 && Cout > 0 && K >= 1 && stride >= 1 && pad >= 0 && groups >= 1, SVB_ERR_INVALID,
+              "tc_layer_create_grouped: bad argument");
+    SVB_CHECK(precision >= 1 && precision <= 3, SVB_ERR_INVALID, "tc_layer_create_grouped: precision must be a tensor-core mode");
+    SVB_CHECK(Cin % groups == 0 && Cout % groups == 0, SVB_ERR_INVALID, "tc_layer_create_grouped: channels not divisible by groups");
+    const int s = stride, cin_g = Cin / groups, cout_g = Cout / groups, pc_g = cin_g * s;      // polyphase channels per conv group
+    const int KSp = (K + s - 1) / s, h = (KSp - 1) / 2, Ce = Cin * s;
+    SVB_CHECK(KSp % 2 == 1 && h <= kPad, SVB_ERR_INVALID, "tc_layer_create_grouped: K %d / stride %d gives %d taps (must be odd, halo <= %d)",
+              K, s, KSp, kPad);
+    int gpt = 1;
+    while (gpt <= groups && ((gpt * pc_g) % 32 != 0 || (gpt * cout_g) % 32 != 0)) gpt *= 2;
+    SVB_CHECK(gpt <= groups && groups % gpt == 0 && gpt * pc_g <= 128 && gpt * cout_g <= 128, SVB_ERR_INVALID,
+              "tc_layer_create_grouped: %d groups of %d x %d channels (stride %d) do not tile the tensor-core kernel", groups, cin_g, cout_g, s);
+    SVB_CHECK((long long)Cout * cin_g * K < (1 << 24), SVB_ERR_INVALID, "tc_layer_create_grouped: weight tensor too large for the index maps");
+    SVB_CUDA(cudaSetDevice(device));
+    svb_tc_layer *L = new (std::nothrow) svb_tc_layer();
+    SVB_CHECK(L, SVB_ERR_NOMEM, "tc_layer_create_grouped: out of host memory");
+    L->device = device, L->precision = precision, L->Cin = Cin, L->Cout = Cout, L->K = K, L->stride = s, L->pad = pad, L->KE = s;
+    L->poly = true, L->groups = groups, L->KSp = KSp, L->halo = h;
+    auto fail = [&](int rc) {
+        for (void *p : L->allocs) cudaFree(p);
+        delete L;
+        return rc;
+    };
+    auto dev_alloc = [&](void **p, size_t bytes) -> int {
+        SVB_CUDA(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+        L->allocs.push_back(*p);
+        SVB_CUDA(cudaMemset(*p, 0, std::max<size_t>(bytes, 16)));
+        return SVB_OK;
+    };
+    auto nat = [&](int co, int c_local, int k) { return (float)(((size_t)co * cin_g + c_local) * K + k + 1); };   // 1-based index
+    // forward: [KS'][cin_blk_f][Cout], column = output channel; tile = gpt conv groups
+    const int nt_f = gpt * cout_g, cb_f = gpt * pc_g;
+    std::vector<float> pf((size_t)KSp * cb_f * Cout, 0.f);
+    for (int q = 0; q < KSp; ++q)
+        for (int lc = 0; lc < cb_f; ++lc)
+            for (int co = 0; co < Cout; ++co) {
+                const int gl = lc / pc_g, pc = lc - gl * pc_g, c_local = pc / s, r = pc - c_local * s;
+                if (gl != (co % nt_f) / cout_g) continue;                       // block diagonal inside a shared tile
+                const int k = q * s + r;
+                if (k < K) pf[((size_t)q * cb_f + lc) * Cout + co] = nat(co, c_local, k);
+            }
+    // data gradient: [KS'][cin_blk_b][Ce], column = polyphase input channel, rows = dy channels of the tile's conv groups
+    const int nt_b = gpt * pc_g, cb_b = gpt * cout_g;
+    std::vector<float> pb((size_t)KSp * cb_b * Ce, 0.f);
+    for (int qf = 0; qf < KSp; ++qf)
+        for (int lc = 0; lc < cb_b; ++lc)
+            for (int col = 0; col < Ce; ++col) {
+                const int g = col / pc_g, pc = col - g * pc_g, c_local = pc / s, r = pc - c_local * s;
+                const int gl = lc / cout_g, co_l = lc - gl * cout_g;
+                if (gl != (col % nt_b) / pc_g) continue;
+                const int k = (KSp - 1 - qf) * s + r;                           // flipped taps
+                if (k < K) pb[((size_t)qf * cb_b + lc) * Ce + col] = nat(g * cout_g + co_l, c_local, k);
+            }
+    int rc;
+    auto setup = [&](ConvLayer &cl, int ci_total, int co, int cin_blk, int n_tile, const std::vector<float> &pk, int **map) -> int {
+        cl.Cin = ci_total, cl.Cout = co, cl.CoutP = co, cl.KS = KSp, cl.dil = 1, cl.ups_u = 0;
+        cl.macs_per_row = (double)cin_blk / gpt * co * KSp;
+        SVB_TRY(dev_alloc((void **)&cl.w, pk.size() * 4));
+        const std::vector<int> idx = to_idx(pk);
+        SVB_TRY(dev_alloc((void **)map, idx.size() * sizeof(int)));
+        SVB_CUDA(cudaMemcpy(*map, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<float> zeros(pk.size(), 0.f);
+        SVB_TRY(tc_pack_weights(zeros.data(), KSp, cin_blk, co, &cl.tc, &L->allocs, n_tile));
+        SVB_CHECK(cl.tc.ok, SVB_ERR_INVALID, "tc_layer_create_grouped: no tensor-core tiling (%d channels per block, %d columns)", cin_blk, n_tile);
+        return SVB_OK;
+    };
+    if ((rc = setup(L->fwd, Ce, Cout, cb_f, nt_f, pf, &L->map_f)) != SVB_OK) return fail(rc);
+    if ((rc = setup(L->bwd, Cout, Ce, cb_b, nt_b, pb, &L->map_b)) != SVB_OK) return fail(rc);
+    L->n_f = pf.size(), L->n_b = pb.size(), L->cin_blk_f = cb_f, L->cin_blk_b = cb_b;
+    if ((rc = dev_alloc((void **)&L->bias, (size_t)Cout * 4)) != SVB_OK) return fail(rc);
+    if ((rc = dev_alloc((void **)&L->zero_bias, (size_t)std::max(Ce, Cout) * 4)) != SVB_OK) return fail(rc);
+    L->fwd.b = L->bias, L->bwd.b = L->zero_bias;
+    *out = L;
+    return SVB_OK;
+}
+
 extern "C" void svb_tc_layer_destroy(svb_tc_layer_t *L) {
     if (!L) return;
     cudaSetDevice(L->device);
@@ -215,11 +307,13 @@ extern "C" int svb_tc_layer_set_weight_dev(svb_tc_layer_t *L, const float *w_dev
     return SVB_OK;
 }
 
-static int run_tc(const svb_tc_layer *L, const ConvLayer &cl, const float *in, float *out, int Tp, int clips, int Tq, cudaStream_t st) {
+static int run_tc(const svb_tc_layer *L, const ConvLayer &cl, const float *in, float *out, int Tp, int clips, int Tq, cudaStream_t st,
+                  int cin_blk = 0) {
     ConvArgs a;
     a.in = in, a.w = cl.w, a.bias = cl.b, a.res = nullptr, a.out = out;
     a.B = clips, a.Cin = cl.Cin, a.in_Tp = Tp, a.Cout = cl.Cout, a.out_Tp = Tp, a.CoutP = cl.CoutP, a.Tq = Tq;
     a.KS = cl.KS, a.dil = 1, a.ups_u = 0, a.in_slope = 1.f, a.out_scale = 1.f, a.accumulate = 0;
+    a.cin_blk = cin_blk;
     SVB_CHECK(tc_supported(cl.tc, a), SVB_ERR_INVALID, "tc_layer: shape not supported by the tensor-core kernel");
     return launch_conv_tc(cl.tc, a, L->precision, st);
 }
@@ -234,6 +328,19 @@ extern "C" int svb_tc_layer_forward(svb_tc_layer_t *L, const float *x_dev, int32
     SVB_CHECK(L && L->has_w && x_dev && y_dev && B > 0 && T > 0 && W > 0, SVB_ERR_INVALID, "tc_layer_forward: bad argument");
     SVB_CUDA(cudaSetDevice(L->device));
     cudaStream_t st = as_stream(stream);
+    if (L->poly) {                              // grouped / polyphase layer
+        const int To = (int)svb_tc_layer_out_len(L, T), Tr = To + 2 * L->halo, Tp = c4t_rows(Tr), clips = B * W, Ce = L->Cin * L->KE;
+        SVB_CHECK(To > 0, SVB_ERR_INVALID, "tc_layer_forward: empty output");
+        const size_t n_x = c4t_floats(clips, Ce, Tr), n_y = c4t_floats(clips, L->Cout, Tr);
+        char *base;
+        SVB_TRY(arena_get(L->device, (n_x + n_y) * 4, &base));
+        float *xe = reinterpret_cast<float *>(base), *yg = xe + n_x;
+        expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, xe);
+        SVB_TRY(run_tc(L, L->fwd, xe, yg, Tp, clips, Tr, st, L->cin_blk_f));
+        g32t_to_nctw_kernel<<<blocks_for((long long)B * L->Cout * To * W), 256, 0, st>>>(yg, B, L->Cout, To, W, Tp, out_slope, y_dev, L->halo);
+        SVB_CUDA(cudaGetLastError());
+        return SVB_OK;
+    }
     const int Tq = (int)svb_tc_layer_out_len(L, T), Tp = c4t_rows(Tq), clips = B * W, Ce = L->Cin * L->KE;
     const int gather_pad = L->stride > 1 ? L->pad : 0;      // a stride-1 layer pads physically (G32T zero rows)
     SVB_CHECK(Tq > 0, SVB_ERR_INVALID, "tc_layer_forward: empty output");
@@ -244,7 +351,7 @@ extern "C" int svb_tc_layer_forward(svb_tc_layer_t *L, const float *x_dev, int32
     expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, gather_pad,
                                                                          Tq, Tp, xe);
     SVB_TRY(run_tc(L, L->fwd, xe, yg, Tp, clips, Tq, st));
-    g32t_to_nctw_kernel<<<blocks_for((long long)B * L->Cout * Tq * W), 256, 0, st>>>(yg, B, L->Cout, Tq, W, Tp, out_slope, y_dev);
+    g32t_to_nctw_kernel<<<blocks_for((long long)B * L->Cout * Tq * W), 256, 0, st>>>(yg, B, L->Cout, Tq, W, Tp, out_slope, y_dev, 0);
     SVB_CUDA(cudaGetLastError());
     return SVB_OK;
 }
@@ -256,6 +363,33 @@ extern "C" int svb_tc_layer_backward(svb_tc_layer_t *L, const float *x_dev, cons
     SVB_CHECK(out_slope == 1.f || y_dev, SVB_ERR_INVALID, "tc_layer_backward: the activation mask needs the forward output");
     SVB_CUDA(cudaSetDevice(L->device));
     cudaStream_t st = as_stream(stream);
+    if (L->poly) {                              // grouped / polyphase layer
+        const int To = (int)svb_tc_layer_out_len(L, T), Tr = To + 2 * L->halo, Tp = c4t_rows(Tr), clips = B * W, Ce = L->Cin * L->KE;
+        const size_t n_x = c4t_floats(clips, Ce, Tr), n_y = c4t_floats(clips, L->Cout, Tr);
+        char *base;
+        SVB_TRY(arena_get(L->device, (2 * n_x + n_y) * 4, &base));
+        float *xe = reinterpret_cast<float *>(base), *dxe = xe + n_x, *dzg = dxe + n_x;
+        // masked output gradient at rows [halo, halo + To) of the T'-row signal, zeros elsewhere
+        expand_to_g32t_kernel<<<blocks_for((long long)n_y), 256, 0, st>>>(dy_dev, out_slope == 1.f ? nullptr : y_dev, out_slope, B, L->Cout,
+                                                                             To, W, 1, 1, L->halo, Tr, Tp, dzg);
+        if (db_dev) SVB_TRY(launch_colsum(dzg, clips, L->Cout, Tr, Tp, db_dev, st));
+        if (dw_dev) {
+            expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, xe);
+            WgradArgs a;
+            a.A = xe, a.G = dzg, a.out = dw_dev, a.B = clips, a.Tq = Tr, a.Ca = Ce, a.TpA = Tp, a.Cg = L->Cout, a.TpG = Tp, a.K = L->KSp;
+            a.sa = 1, a.da = 1, a.pa = L->halo, a.sb = 1, a.db = 0, a.pb = 0, a.slope = 1.f;
+            a.s_co = (long long)(L->Cin / L->groups) * L->K, a.s_ci = L->K, a.s_k = 1;
+            a.allow_tc = 1, a.cgroups = L->groups, a.poly_s = L->stride > 1 ? L->stride : 0, a.K_nat = L->K;
+            SVB_CHECK(wgrad_tc_supported(a), SVB_ERR_INVALID, "tc_layer_backward: grouped weight gradient shape not supported");
+            SVB_TRY(launch_wgrad_tc(a, st));
+        }
+        if (dx_dev) {
+            SVB_TRY(run_tc(L, L->bwd, dzg, dxe, Tp, clips, Tr, st, L->cin_blk_b));
+            col2im_to_nctw_kernel<<<blocks_for((long long)B * L->Cin * T * W), 256, 0, st>>>(dxe, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, dx_dev);
+        }
+        SVB_CUDA(cudaGetLastError());
+        return SVB_OK;
+    }
     const int Tq = (int)svb_tc_layer_out_len(L, T), Tp = c4t_rows(Tq), clips = B * W, Ce = L->Cin * L->KE;
     const int gather_pad = L->stride > 1 ? L->pad : 0;
     const size_t n_x = c4t_floats(clips, Ce, Tq), n_y = c4t_floats(clips, L->Cout, Tq);
@@ -280,7 +414,7 @@ extern "C" int svb_tc_layer_backward(svb_tc_layer_t *L, const float *x_dev, cons
     if (dx_dev) {
         SVB_TRY(run_tc(L, L->bwd, dzg, dxe, Tp, clips, Tq, st));
         const long long total = (long long)B * L->Cin * T * W;
-        if (L->stride == 1) g32t_to_nctw_kernel<<<blocks_for(total), 256, 0, st>>>(dxe, B, L->Cin, T, W, Tp, 1.f, dx_dev);
+        if (L->stride == 1) g32t_to_nctw_kernel<<<blocks_for(total), 256, 0, st>>>(dxe, B, L->Cin, T, W, Tp, 1.f, dx_dev, 0);
         else col2im_to_nctw_kernel<<<blocks_for(total), 256, 0, st>>>(dxe, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tq, Tp, dx_dev);
     }
     SVB_CUDA(cudaGetLastError());

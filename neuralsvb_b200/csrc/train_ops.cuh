@@ -18,6 +18,11 @@ struct WgradArgs {
     float slope;                // leaky-relu slope applied to A on load (1 = identity)
     long long s_ci, s_co, s_k;
     int allow_tc = 0;           // 1: stride-1 shapes may run on the tcgen05 kernel (wgrad_tc.cu, split-bf16 operands)
+    // grouped convolution (tcgen05 kernel only): `cgroups` conv groups; A channel ci and G channel co interact only when
+    // ci / (Ca / cgroups) == co / (Cg / cgroups).  poly_s > 0: A is the polyphase (space-to-depth) form of a stride-poly_s
+    // conv input -- A channel (c * poly_s + r) of a group, tap q  ->  natural weight element [co][c][q * poly_s + r]
+    // (dropped when q * poly_s + r >= K_nat); out is then the natural [Cg][Ca / cgroups / poly_s][K_nat] tensor.
+    int cgroups = 1, poly_s = 0, K_nat = 0;
 };
 int launch_wgrad(const WgradArgs &a, cudaStream_t st);
 bool wgrad_tc_supported(const WgradArgs &a);

@@ -28,6 +28,7 @@ constexpr int kWgThreads = 320;
 struct WgTcArgs {
     WgradArgs a;
     int gA, gG, n_pairs, n_cosets, n_tapsets, splits, chunks_per_b;
+    int n_eg, gA_g, gG_g;                   // grouped conv: effective groups, G32T channel groups of A / G per effective group
     int Rx, Rxp;                            // rows of an A slab (chunk + tap reach), rounded up to whole 8-row atoms
     uint32_t x_tile_bytes, stage_bytes;
 };
@@ -74,9 +75,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgTcArgs p) {
     const int sp = blockIdx.x - cls * p.splits;
     const int tapset = cls % p.n_tapsets;
     cls /= p.n_tapsets;
-    const int coset = cls % p.n_cosets, pair = cls / p.n_cosets;
+    const int coset = cls % p.n_cosets;
+    cls /= p.n_cosets;
+    const int pair = cls % p.n_pairs, eg = cls / p.n_pairs;          // eg: effective conv group (0 when dense)
     const int k0 = tapset * kWgTaps, ntaps = min(kWgTaps, a.K - k0);
-    const int nxa = min(2, p.gA - pair * 2), ng = min(2, p.gG - coset * 2);        // real channel groups of this CTA
+    const int nxa = min(2, p.gA_g - pair * 2), ng = min(2, p.gG_g - coset * 2);    // real channel groups of this CTA
+    const int ga0 = eg * p.gA_g + pair * 2, gg0 = eg * p.gG_g + coset * 2;          // first G32T channel group of A / G
     const int N = 64 * ng;
     const int n_units = a.B * p.chunks_per_b;
 
@@ -104,10 +108,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgTcArgs p) {
                 mbar_wait(empty + s, ph);
                 mbar_expect_tx(full + s, bytes);
                 for (int g = 0; g < nxa; ++g)
-                    bulk_g2s(x_tile(s, g), a.A + (((size_t)b * p.gA + pair * 2 + g) * a.TpA + kPad + t0 - a.pa) * 32, (uint32_t)p.Rx * 128,
+                    bulk_g2s(x_tile(s, g), a.A + (((size_t)b * p.gA + ga0 + g) * a.TpA + kPad + t0 - a.pa) * 32, (uint32_t)p.Rx * 128,
                              full + s);
                 for (int j = 0; j < ng; ++j)
-                    bulk_g2s(g_tile(s, j), a.G + (((size_t)b * p.gG + coset * 2 + j) * a.TpG + kPad + t0) * 32, kWgChunk * 128, full + s);
+                    bulk_g2s(g_tile(s, j), a.G + (((size_t)b * p.gG + gg0 + j) * a.TpG + kPad + t0) * 32, kWgChunk * 128, full + s);
                 if (++s == kWgStages) s = 0, ph ^= 1;
             }
         }
@@ -163,8 +167,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgTcArgs p) {
             tc_fence_after();
             const int lane_base = 32 * (warp & 3);
             const int m = lane_base + lane;                             // accumulator row
-            const int gm = m >> 6, ci = ((pair * 2 + gm) << 5) + (m & 31);
+            const int gm = m >> 6, ci = ((ga0 + gm) << 5) + (m & 31);
             const bool row_ok = gm < nxa && ci < a.Ca;
+            const int ca_g = a.Ca / a.cgroups, cg_g = a.Cg / a.cgroups;            // channels per conv group
+            const int cgrp = ci / ca_g, ci_l = ci - cgrp * ca_g;                   // conv group / local channel of this row
             for (int tk = 0; tk < ntaps; ++tk)
                 for (int j = 0; j < ng; ++j) {
                     float vh[32], vl[32];
@@ -172,11 +178,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgTcArgs p) {
                     tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + col, vh);
                     tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + col + 32, vl);
                     if (!row_ok) continue;
-                    float *o = a.out + (long long)ci * a.s_ci + (long long)(k0 + tk) * a.s_k;
+                    if (a.cgroups == 1) {
+                        float *o = a.out + (long long)ci * a.s_ci + (long long)(k0 + tk) * a.s_k;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int co = ((coset * 2 + j) << 5) + c;
-                        if (co < a.Cg) atomicAdd(o + (long long)co * a.s_co, vh[c] + vl[c]);
+                        for (int c = 0; c < 32; ++c) {
+                            const int co = ((gg0 + j) << 5) + c;
+                            if (co < a.Cg) atomicAdd(o + (long long)co * a.s_co, vh[c] + vl[c]);
+                        }
+                    } else {
+                        // grouped: only the block diagonal exists; polyphase rows map back to natural taps
+                        int c_nat = ci_l, k_nat = k0 + tk;
+                        if (a.poly_s > 0) {
+                            c_nat = ci_l / a.poly_s;
+                            k_nat = (k0 + tk) * a.poly_s + (ci_l - c_nat * a.poly_s);
+                            if (k_nat >= a.K_nat) continue;
+                        }
+                        const int cin_nat = a.poly_s > 0 ? ca_g / a.poly_s : ca_g, K_out = a.poly_s > 0 ? a.K_nat : a.K;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int co = ((gg0 + j) << 5) + c;
+                            if (co < a.Cg && co / cg_g == cgrp)
+                                atomicAdd(a.out + ((long long)co * cin_nat + c_nat) * K_out + k_nat, vh[c] + vl[c]);
+                        }
                     }
                 }
             tc_fence_before();
@@ -194,16 +217,28 @@ bool wgrad_tc_supported(const WgradArgs &a) {
     if (!on) return false;
     const int reach = (a.K - 1) * a.da;
     return a.sa == 1 && a.sb == 1 && a.db == 0 && a.pb == 0 && a.da >= 1 && a.pa >= 0 && a.pa <= kPad && reach - a.pa <= kPad &&
-           a.slope >= 0.f && a.slope <= 1.f && a.Ca >= 32 && a.Cg >= 32;
+           a.slope >= 0.f && a.slope <= 1.f && a.Ca >= 32 && a.Cg >= 32 &&
+           (a.cgroups == 1 || (a.Ca % a.cgroups == 0 && a.Cg % a.cgroups == 0 && a.Ca % 32 == 0 && a.Cg % 32 == 0));
 }
 
 int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
     WgTcArgs p;
     p.a = a;
     p.gA = c4t_groups(a.Ca), p.gG = c4t_groups(a.Cg);
-    p.n_pairs = (p.gA + 1) / 2, p.n_cosets = (p.gG + 1) / 2, p.n_tapsets = (a.K + kWgTaps - 1) / kWgTaps;
+    p.n_eg = 1, p.gA_g = p.gA, p.gG_g = p.gG;
+    if (a.cgroups > 1) {
+        // effective groups: merge conv groups until both sides own whole 32-channel G32T groups (the epilogue masks the
+        // cross-group products of a merged block)
+        int merge = 1;
+        while ((a.Ca / a.cgroups * merge) % 32 != 0 || (a.Cg / a.cgroups * merge) % 32 != 0) merge *= 2;
+        SVB_CHECK(a.cgroups % merge == 0, SVB_ERR_INVALID, "wgrad_tc: %d conv groups of %d x %d channels do not tile", a.cgroups,
+                  a.Ca / a.cgroups, a.Cg / a.cgroups);
+        p.n_eg = a.cgroups / merge;
+        p.gA_g = p.gA / p.n_eg, p.gG_g = p.gG / p.n_eg;
+    }
+    p.n_pairs = (p.gA_g + 1) / 2, p.n_cosets = (p.gG_g + 1) / 2, p.n_tapsets = (a.K + kWgTaps - 1) / kWgTaps;
     p.chunks_per_b = (a.Tq + kWgChunk - 1) / kWgChunk;
-    const int classes = p.n_pairs * p.n_cosets * p.n_tapsets;
+    const int classes = p.n_eg * p.n_pairs * p.n_cosets * p.n_tapsets;
     const int units = a.B * p.chunks_per_b;
     p.splits = std::max(1, std::min(units, 148 / std::max(1, classes)));
     p.Rx = kWgChunk + (a.K - 1) * a.da;

@@ -68,9 +68,20 @@ USE_TC = True            # dense layers with >= 32 channels run on the tcgen05 k
 TC_PRECISION = 'bf16x3'
 
 
+USE_TC_GROUPED = True    # grouped k = 41 layers of the MSD on tcgen05 in polyphase form (svb_tc_layer_create_grouped)
+
+
 def tc_eligible(cin, cout, K, stride, dil, pad, groups):
-    if not USE_TC or groups != 1 or dil != 1 or cout % 32 or cout > 1024:
+    if not USE_TC or dil != 1 or cout % 32 or cout > 1024:
         return False
+    if groups != 1:
+        if not USE_TC_GROUPED or cin % groups or cout % groups:
+            return False
+        ksp, pc, cg = -(-K // stride), cin // groups * stride, cout // groups
+        gpt = 1
+        while gpt <= groups and ((gpt * pc) % 32 or (gpt * cg) % 32):
+            gpt *= 2
+        return ksp % 2 == 1 and (ksp - 1) // 2 <= 64 and gpt <= groups and groups % gpt == 0 and gpt * pc <= 128 and gpt * cg <= 128
     if stride == 1:
         return cin % 32 == 0 and K % 2 == 1 and pad == (K - 1) // 2
     return (cin * K) % 32 == 0 and cin * K <= 3072
@@ -81,16 +92,21 @@ class TcLayer:
 
     def __init__(self):
         self.h, self.key = None, None
+        self.wkey = None        # (data_ptr, version) of the weight / bias the handle holds: re-packed only when they change
 
-    def get(self, cin, cout, K, stride, pad, device):
-        key = (cin, cout, K, stride, pad, device.index, TC_PRECISION)
+    def get(self, cin, cout, K, stride, pad, device, groups=1):
+        key = (cin, cout, K, stride, pad, device.index, TC_PRECISION, groups)
         if self.h is None or self.key != key:
             self.close()
             h = ctypes.c_void_p()
-            _native.check(_native.lib().svb_tc_layer_create(cin, cout, K, stride, pad, _native.PREC[TC_PRECISION],
-                                                            device.index if device.index is not None else torch.cuda.current_device(),
-                                                            ctypes.byref(h)), 'tc_layer_create')
-            self.h, self.key = h, key
+            dev = device.index if device.index is not None else torch.cuda.current_device()
+            if groups == 1:
+                _native.check(_native.lib().svb_tc_layer_create(cin, cout, K, stride, pad, _native.PREC[TC_PRECISION], dev,
+                                                                ctypes.byref(h)), 'tc_layer_create')
+            else:
+                _native.check(_native.lib().svb_tc_layer_create_grouped(cin, cout, K, stride, pad, groups, _native.PREC[TC_PRECISION],
+                                                                        dev, ctypes.byref(h)), 'tc_layer_create_grouped')
+            self.h, self.key, self.wkey = h, key, None
         return self.h
 
     def close(self):
@@ -105,21 +121,35 @@ class TcLayer:
             pass
 
 
-def conv_tc(x, w, b, layer, K, stride, pad, slope, W):
-    """Dense conv through the tensor-core layer handle; same contract as conv_nct."""
+def conv_tc(x, w, b, layer, K, stride, pad, slope, W, groups=1, wver=None):
+    """Dense (or grouped, polyphase) conv through the tensor-core layer handle; same contract as conv_nct.
+    ``wver``: hashable state the weight is a pure function of (see _tc_sync_weight)."""
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
-        return _TcConvFn.apply(x, w, b, layer, K, stride, pad, slope, W)
-    return _tc_forward(_cuda(x), _cuda(w), _cuda(b), layer, K, stride, pad, slope, W)
+        return _TcConvFn.apply(x, w, b, layer, K, stride, pad, slope, W, groups, wver)
+    return _tc_forward(_cuda(x), _cuda(w), _cuda(b), layer, K, stride, pad, slope, W, groups, wver)
 
 
-def _tc_forward(x, w, b, layer, K, stride, pad, slope, W):
+def _tc_sync_weight(layer, h, w, b, st, wver=None):
+    """Hand the effective weight to the layer handle only when it changed: the packings (gather + tcgen05 tiles for
+    forward and data gradient) are rebuilt once per optimizer step, not on every forward / backward.  The effective
+    weight is a pure function of the layer's parameters (and, for training-mode spectral norm, of its power-iteration
+    count), so ``_NormConv.conv`` passes that state as ``wver``; tensors from elsewhere are keyed by identity and version."""
+    key = wver or (w.data_ptr(), w._version, b.data_ptr(), b._version, tuple(w.shape))
+    if layer.wkey == key:
+        return
+    _native.check(_native.lib().svb_tc_layer_set_weight_dev(h, _native.ptr(w), _native.ptr(b), st), 'tc_layer_set_weight')
+    layer.wkey = key
+    layer.wref = (w, b)         # keep the tensors alive: a freed-and-reused address must not look like the same weight
+
+
+def _tc_forward(x, w, b, layer, K, stride, pad, slope, W, groups=1, wver=None):
     lib = _native.lib()
     B, Cin, Tin = x.shape[0], x.shape[1], x.shape[2]
     Cout = w.shape[0]
     with torch.cuda.device(x.device):
         st = _native.current_stream_ptr(x.device)
-        h = layer.get(Cin, Cout, K, stride, pad, x.device)
-        _native.check(lib.svb_tc_layer_set_weight_dev(h, _native.ptr(w), _native.ptr(b), st), 'tc_layer_set_weight')
+        h = layer.get(Cin, Cout, K, stride, pad, x.device, groups)
+        _tc_sync_weight(layer, h, w, b, st, wver)
         Tout = int(lib.svb_tc_layer_out_len(h, Tin))
         y = torch.empty((B, Cout, Tout) + ((W,) if x.dim() == 4 else ()), device=x.device, dtype=torch.float32)
         _native.check(lib.svb_tc_layer_forward(h, _native.ptr(x), B, Tin, W, ctypes.c_float(slope), _native.ptr(y), st),
@@ -129,17 +159,17 @@ def _tc_forward(x, w, b, layer, K, stride, pad, slope, W):
 
 class _TcConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, layer, K, stride, pad, slope, W):
+    def forward(ctx, x, w, b, layer, K, stride, pad, slope, W, groups=1, wver=None):
         x, w, b = _cuda(x), _cuda(w), _cuda(b)
-        y = _tc_forward(x, w, b, layer, K, stride, pad, slope, W)
+        y = _tc_forward(x, w, b, layer, K, stride, pad, slope, W, groups, wver)
         ctx.save_for_backward(x, w, b, y)
-        ctx.cfg = (layer, K, stride, pad, slope, W)
+        ctx.cfg = (layer, K, stride, pad, slope, W, groups, wver)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, b, y = ctx.saved_tensors
-        layer, K, stride, pad, slope, W = ctx.cfg
+        layer, K, stride, pad, slope, W, groups, wver = ctx.cfg
         lib = _native.lib()
         dy = _cuda(dy)
         need_x, need_w, need_b = ctx.needs_input_grad[:3]
@@ -148,13 +178,12 @@ class _TcConvFn(torch.autograd.Function):
         db = torch.zeros_like(b) if need_b else None
         with torch.cuda.device(x.device):
             st = _native.current_stream_ptr(x.device)
-            h = layer.get(x.shape[1], w.shape[0], K, stride, pad, x.device)
-            # the handle may have served another tensor pair since the forward (y / y_hat share it): re-pack is cheap
-            _native.check(lib.svb_tc_layer_set_weight_dev(h, _native.ptr(w), _native.ptr(b), st), 'tc_layer_set_weight')
+            h = layer.get(x.shape[1], w.shape[0], K, stride, pad, x.device, groups)
+            _tc_sync_weight(layer, h, w, b, st, wver)      # no-op unless the handle took other weights since the forward
             _native.check(lib.svb_tc_layer_backward(h, _native.ptr(x), _native.ptr(y), _native.ptr(dy), x.shape[0], x.shape[2], W,
                                                     ctypes.c_float(slope), _native.ptr(dx), _native.ptr(dw), _native.ptr(db), st),
                           'tc_layer_backward')
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 def _conv_nct_raw(x, w, b, K, stride=1, dil=1, pad=0, groups=1, slope=1.0, W=1):
@@ -193,11 +222,18 @@ class _NormConv(nn.Module):
         self._cache = None
         self.tc = TcLayer()
 
+    def _wver(self):
+        """State the effective weight depends on: parameter versions (+ the power-iteration count of spectral norm)."""
+        wp = self.weight_orig if self.spectral else self.weight_v
+        other = (self.weight_u._version, self.weight_v._version, getattr(self, '_sn_calls', 0), self.training) if self.spectral \
+            else (self.weight_g._version, self.weight_g.data_ptr())
+        return ('wver', id(self), wp._version, wp.data_ptr(), self.bias._version, self.bias.data_ptr()) + other
+
     def conv(self, x, K, stride=1, pad=0, groups=1, slope=1.0, W=1):
         """This layer's convolution on x: the tensor-core handle for dense >= 32-channel layers, else the fp32 kernel."""
         w, bias = self.effective(x.device)
         if tc_eligible(x.shape[1], w.shape[0], K, stride, 1, pad, groups) and x.is_cuda:
-            return conv_tc(x, w, bias, self.tc, K, stride, pad, slope, W)
+            return conv_tc(x, w, bias, self.tc, K, stride, pad, slope, W, groups, self._wver())
         return conv_nct(x, w, bias, K, stride=stride, pad=pad, groups=groups, slope=slope, W=W)
 
     def effective(self, device):
@@ -258,6 +294,7 @@ class _NormConv(nn.Module):
                 v = nn.functional.normalize(torch.mv(wm.t(), self.weight_u), dim=0, eps=1e-12)
                 u = nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
                 self.weight_v.copy_(v), self.weight_u.copy_(u)
+                self._sn_calls = getattr(self, '_sn_calls', 0) + 1         # the effective weight changed
             u, v = self.weight_u.clone(), self.weight_v.clone()
         sigma = torch.dot(u, torch.mv(wm, v))
         return self.weight_orig / sigma

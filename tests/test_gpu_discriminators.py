@@ -131,3 +131,34 @@ def test_cond_discriminators_forward_and_backward(golden_dir, name):
         print(name, 'tc' if use_tc else 'fp32', 'cond_net grad errors', {k[15:]: f'{e:.1e}' for k, e in cond.items()})
         assert cond and max(cond.values()) < cond_tol and (use_tc or min(cond.values()) < 1e-3), cond
         assert float(np.median(list(errs.values()))) < 1e-2 and max(errs.values()) < 8e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+
+
+@pytest.mark.parametrize('T', [700, 2051])
+@pytest.mark.parametrize('layer', range(1, 6))
+def test_grouped_polyphase_tc_layers_match_torch(layer, T):
+    """The grouped k = 41 layers of DiscriminatorS (hifigan.py:263-267) on tcgen05 in polyphase form
+    (svb_tc_layer_create_grouped): forward, data / weight / bias gradients against torch fp64 grouped convolution."""
+    import torch.nn.functional as F
+    from neuralsvb_b200.modules.hifigan import discriminators as D
+    cin, cout, k, s, g, p = S.MSD_LAYERS[layer]
+    assert D.tc_eligible(cin, cout, k, s, 1, p, g)
+    B = 2
+    gen = torch.Generator().manual_seed(100 + layer)
+    x = torch.randn(B, cin, T, generator=gen)
+    w = torch.randn(cout, cin // g, k, generator=gen) * (1.0 / (cin // g * k) ** 0.5)
+    b = torch.randn(cout, generator=gen) * 0.1
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = F.leaky_relu(F.conv1d(xr, wr, br, stride=s, padding=p, groups=g), 0.1)
+    cot = torch.randn(ref.shape, generator=gen)
+    (ref * cot.double()).sum().backward()
+    xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    got = D.conv_tc(xc, wc, bc, D.TcLayer(), k, s, p, 0.1, 1, g)
+    assert got.shape == ref.shape
+    rel = lambda a, r: float((a.detach().cpu().double() - r.detach()).norm() / r.detach().norm())
+    assert rel(got, ref) < 2e-5, rel(got, ref)
+    (got * cot.cuda()).sum().backward()
+    e = {'dx': rel(xc.grad, xr.grad), 'dw': rel(wc.grad, wr.grad), 'db': rel(bc.grad, br.grad)}
+    assert max(e.values()) < 1e-4, e
+    # and the fp32 CUDA-core kernel agrees (the path USE_TC_GROUPED = False takes)
+    got32 = D.conv_nct(x.cuda(), w.cuda(), b.cuda(), k, stride=s, pad=p, groups=g, slope=0.1)
+    assert rel(got32, ref) < 2e-5

@@ -109,8 +109,17 @@ def test_tensor_core_eligibility_of_discriminator_layers():
     assert D.tc_eligible(32, 128, 5, 3, 1, 2, 1) and D.tc_eligible(512, 1024, 5, 3, 1, 2, 1)
     assert D.tc_eligible(1024, 1024, 5, 1, 1, 2, 1)            # stride 1, 'same' padding
     assert not D.tc_eligible(1024, 1, 3, 1, 1, 1, 1)           # conv_post: one output channel
-    # MSD: grouped layers stay on CUDA cores, the dense 1024 -> 1024 k5 layer does not
-    assert not D.tc_eligible(128, 128, 41, 2, 1, 20, 4) and D.tc_eligible(1024, 1024, 5, 1, 1, 2, 1)
+    # MSD: every grouped k = 41 layer (hifigan.py:263-267) tiles the tensor-core kernel in polyphase form; 1 -> 128 k15 does not
+    from neuralsvb_b200.utils.synthetic import MSD_LAYERS
+    for cin, cout, k, s, g, p in MSD_LAYERS[1:6]:
+        assert D.tc_eligible(cin, cout, k, s, 1, p, g), (cin, cout, k, s, g)
+    assert not D.tc_eligible(1, 128, 15, 1, 1, 7, 1) and D.tc_eligible(1024, 1024, 5, 1, 1, 2, 1)
+    assert not D.tc_eligible(128, 128, 40, 2, 1, 20, 4)        # ceil(40 / 2) = 20 taps: even, no centred form
+    D.USE_TC_GROUPED = False
+    try:
+        assert not D.tc_eligible(128, 128, 41, 2, 1, 20, 4)
+    finally:
+        D.USE_TC_GROUPED = True
     assert not D.tc_eligible(1024, 1024, 5, 1, 1, 1, 1)        # not 'same' padding
 
 
