@@ -148,15 +148,22 @@ def test_grouped_polyphase_tc_layers_match_torch(layer, T):
     w = torch.randn(cout, cin // g, k, generator=gen) * (1.0 / (cin // g * k) ** 0.5)
     b = torch.randn(cout, generator=gen) * 0.1
     xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
-    ref = F.leaky_relu(F.conv1d(xr, wr, br, stride=s, padding=p, groups=g), 0.1)
+    ref_lin = F.conv1d(xr, wr, br, stride=s, padding=p, groups=g)
+    ref = F.leaky_relu(ref_lin, 0.1)
     cot = torch.randn(ref.shape, generator=gen)
-    (ref * cot.double()).sum().backward()
     xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
     got = D.conv_tc(xc, wc, bc, D.TcLayer(), k, s, p, 0.1, 1, g)
     assert got.shape == ref.shape
     rel = lambda a, r: float((a.detach().cpu().double() - r.detach()).norm() / r.detach().norm())
     assert rel(got, ref) < 2e-5, rel(got, ref)
     (got * cot.cuda()).sum().backward()
+    # leaky-relu's derivative is discontinuous at 0: with ~10^6 outputs a few pre-activations within the forward's 1e-6
+    # of zero flip their mask and each flip moves the gradients by ~1e-3 relative.  The reference therefore applies the
+    # mask of the CUDA forward itself -- what is compared is the convolution's data / weight / bias gradient.
+    mask = torch.where(got.detach().cpu() > 0, 1.0, 0.1).double()
+    flips = int((mask != torch.where(ref.detach() > 0, 1.0, 0.1)).sum())
+    assert flips <= 1e-4 * mask.numel(), flips
+    (ref_lin * (cot.double() * mask)).sum().backward()
     e = {'dx': rel(xc.grad, xr.grad), 'dw': rel(wc.grad, wr.grad), 'db': rel(bc.grad, br.grad)}
     assert max(e.values()) < 1e-4, e
     # and the fp32 CUDA-core kernel agrees (the path USE_TC_GROUPED = False takes)
