@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <vector>
 
 #include <cuda_bf16.h>
 
@@ -44,6 +45,8 @@ struct TcArgs {
     int blk_chunk_step;         // grouped conv: first input chunk of column block nblk = nblk * blk_chunk_step (0: dense)
     uint32_t wstage_bytes;      // ring slot = tps weight tiles
     int pdl;                    // launched with programmatic stream serialization
+    int collect;                // A-operand collector reuse between the two products of a_hi (SVB_TC_COLLECT, default on)
+    long long *stats;           // SVB_TC_STATS: [grid][kTcStatSlots] blocked-cycle counters (diagnostics build of the kernel)
     int dbg;                    // SVB_TC_DBG bit mask: 1 no MMAs, 2 hi*hi only, 4 no transform, 8 no epilogue ld/st
     uint32_t raw_bytes;         // fp32 slab as TMA delivers it: R rows x 128 B
     uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
@@ -65,7 +68,21 @@ constexpr int kBiasBytes = 4096;        // bias of the layer (Cout <= 1024 float
 // the next group, the transform warps prepare operands while the tensor core works on the
 // previous chunk, and the epilogue drains accumulator set (g & 1) from TMEM while the MMAs of
 // group g + 1 fill the other set.
-template <int MODE>
+// STATS (SVB_TC_STATS=1, diagnostics only): every role accumulates the cycles it spends blocked on each of its
+// barriers; the launcher prints the per-CTA mean / max.  Says which stage of the pipeline the others wait for.
+template <bool ST>
+__device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, long long &acc) {
+    if (ST) {
+        const long long t = clock64();
+        mbar_wait(bar, parity);
+        acc += clock64() - t;
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
+constexpr int kTcStatSlots = 16;
+
+template <int MODE, bool ST = false>
 __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr bool BF = MODE == SVB_PREC_BF16X3;
@@ -83,6 +100,8 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halo = (a.KS - 1) / 2 * a.dil;
     const int acc_cols = p.MT * p.n_tile;                            // columns of one accumulator set
+    long long st_w0 = 0, st_w1 = 0, st_w2 = 0;                       // STATS: cycles blocked on up to three barriers
+    const long long st_t0 = ST ? clock64() : 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(raw_full + i, 1), mbar_init(a_ready + i, 8), mbar_init(a_empty + i, 1);
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 const float *in_c = a.in + (((size_t)b * gin + (size_t)nblk * p.blk_chunk_step) * a.in_Tp + (kPad + t0 - halo)) * 32;
                 const unsigned char *w_c = p.w + (size_t)nblk * p.n_chunks * chunk_w_bytes;
                 for (int c = 0; c < p.n_chunks; ++c) {
-                    mbar_wait(a_empty + sA, phA);                                 // MMAs of the slot's previous slab retired
+                    mbar_wait_t<ST>(a_empty + sA, phA, st_w0);                    // MMAs of the slot's previous slab retired
                     mbar_expect_tx(raw_full + sA, p.raw_bytes);
                     bulk_g2s(op0 + sA * p.op_bytes, in_c, p.raw_bytes, raw_full + sA);
                     in_c += group_stride;
@@ -144,7 +163,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                         for (int st = 0; st < p.n_st; ++st) {
                             const int nt = min(p.tps, a.KS - st * p.tps);
                             const uint32_t bytes = (uint32_t)nt * p.wtile_bytes;
-                            mbar_wait(w_empty + sW, phW);
+                            mbar_wait_t<ST>(w_empty + sW, phW, st_w1);
                             mbar_expect_tx(w_full + sW, bytes);
                             bulk_g2s(wring + sW * p.wstage_bytes, w_k, bytes, w_full + sW);
                             w_k += bytes;
@@ -157,90 +176,113 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 tg += step_tg, rb += step_rb;
                 if (tg >= p.groups_per_b) tg -= p.groups_per_b, ++rb;
             }
+            if (ST) {
+                long long *o = p.stats + (size_t)blockIdx.x * kTcStatSlots;
+                o[0] = st_w0, o[1] = st_w1, o[2] = clock64() - st_t0;
+            }
         }
     } else if (warp == kWarpMma) {
         // ================================ MMA issuer ==================================
-        // The whole warp walks the loop (waits are warp-wide); one elected lane issues the MMAs.
+        // The whole warp walks the loop CONVERGED and every MMA / commit is predicated on the elected lane, so the
+        // descriptors stay in uniform registers (tc_ptx.cuh, "issue discipline": a divergent single-thread issuer
+        // costs 65-82 cycles per MMA, more than the MMA itself for every N below 256).
         const uint32_t elected = elect_one_sync();
         const uint32_t idesc = umma_idesc(BF ? 1 : 2, kTcM, p.n_tile);
         const uint32_t hi_word = desc_hi_sw128(0);
-        const uint32_t a_lo_plane = X3 ? p.op_bytes / 2 : 64u;      // byte offset of the lo plane / half-row
-        const uint32_t b_lo_plane = X3 ? p.wtile_bytes / 2 : 64u;
-        const uint32_t op_base = smem_u32(op0), w_base = smem_u32(wring);
-        const uint32_t tap_step = (uint32_t)a.dil * 128;            // a tap is a row shift of the operand
+        // Descriptors are advanced in their ENCODED form (address >> 4 in the low 14 bits; every offset below is a
+        // multiple of 16 bytes and the sum stays inside shared memory, so the field cannot overflow): one uniform
+        // add per operand and MMA -- the issue loop, not the tensor pipe, sets the pace of the narrow layers.
+        const uint32_t a_lo_plane = (X3 ? p.op_bytes / 2 : 64u) >> 4;      // lo plane / half-row
+        const uint32_t b_lo_plane = (X3 ? p.wtile_bytes / 2 : 64u) >> 4;
+        const uint32_t op_base = desc_lo(smem_u32(op0)), w_base = desc_lo(smem_u32(wring));
+        const uint32_t tap_step = (uint32_t)a.dil * (128 >> 4);            // a tap is a row shift of the operand
+        const uint32_t op_step = p.op_bytes >> 4, wstage_step = p.wstage_bytes >> 4, wtile_step = p.wtile_bytes >> 4;
+        // the ablation switches exist only in the diagnostics instantiation
+        const bool mma_on = ST ? !(p.dbg & 1) : true, hh_only = ST ? (p.dbg & 2) != 0 : false, collect = ST ? p.collect != 0 : true;
         int sA = 0, phA = 0, sW = 0, phW = 0, as = 0, phE = 1;
         bool first_group = true;
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
-            mbar_wait(acc_empty + as, phE);                         // epilogue has drained this accumulator set
+            mbar_wait_t<ST>(acc_empty + as, phE, st_w0);            // epilogue has drained this accumulator set
+            __syncwarp();
             tc_fence_after();
             const uint32_t d_set = tmem_base + (uint32_t)(as * acc_cols);
             uint32_t fresh = 1;                                     // first MMA of the group overwrites
             for (int c = 0; c < p.n_chunks; ++c) {
-                mbar_wait(a_ready + sA, phA);
+                mbar_wait_t<ST>(a_ready + sA, phA, st_w1);
+                __syncwarp();
                 tc_fence_after();
-                uint32_t a_tap = op_base + sA * p.op_bytes;
+                uint32_t a_tap = op_base + sA * op_step;
                 int in_stage = 0;
                 uint32_t b_tap = 0;
                 for (int k = 0; k < a.KS; ++k) {
                     if (in_stage == 0) {                            // first tap of a weight stage
                         if (!(p.w_resident && !first_group)) {
-                            mbar_wait(w_full + sW, phW);
+                            mbar_wait_t<ST>(w_full + sW, phW, st_w2);
+                            __syncwarp();
                             tc_fence_after();
                         }
-                        b_tap = w_base + sW * p.wstage_bytes;
+                        b_tap = w_base + sW * wstage_step;
                     }
-                    if (elected && !(p.dbg & 1)) {
+                    if (mma_on) {
+                        uint32_t d = d_set, a_row = a_tap;
 #pragma unroll 1
                         for (int m = 0; m < p.MT; ++m) {
-                            const uint32_t d = d_set + (uint32_t)(m * p.n_tile);
-                            const uint32_t a_row = a_tap + (uint32_t)m * (kTcM * 128);
-                            uint32_t acc = fresh ^ 1u;
-                            if (BF) {
-#pragma unroll
-                                for (int kb = 0; kb < 2; ++kb) {    // 2 x 16 channels; small cross terms first
-                                    const uint32_t ah = desc_lo(a_row + kb * 32), al = desc_lo(a_row + a_lo_plane + kb * 32);
-                                    const uint32_t bh = desc_lo(b_tap + kb * 32), bl = desc_lo(b_tap + b_lo_plane + kb * 32);
-                                    if (!(p.dbg & 2)) {
-                                        umma<true>(d, al, hi_word, bh, hi_word, idesc, acc);
-                                        umma<true>(d, ah, hi_word, bl, hi_word, idesc, 1u);
-                                        acc = 1u;
-                                    }
-                                    umma<true>(d, ah, hi_word, bh, hi_word, idesc, acc);
-                                    acc = 1u;
+                            const uint32_t acc = fresh ^ 1u;
+                            if (BF) {                               // 2 x 16 channels; small cross terms first
+                                if (hh_only) {
+                                    umma<true>(d, a_row, hi_word, b_tap, hi_word, idesc, acc, elected);
+                                    umma<true>(d, a_row + 2, hi_word, b_tap + 2, hi_word, idesc, 1u, elected);
+                                } else if (collect) {               // a_hi is read from shared memory once for its two products
+                                    umma<true>(d, a_row + a_lo_plane, hi_word, b_tap, hi_word, idesc, acc, elected);
+                                    umma<true, 1>(d, a_row, hi_word, b_tap + b_lo_plane, hi_word, idesc, 1u, elected);
+                                    umma<true, 2>(d, a_row, hi_word, b_tap, hi_word, idesc, 1u, elected);
+                                    umma<true>(d, a_row + a_lo_plane + 2, hi_word, b_tap + 2, hi_word, idesc, 1u, elected);
+                                    umma<true, 1>(d, a_row + 2, hi_word, b_tap + b_lo_plane + 2, hi_word, idesc, 1u, elected);
+                                    umma<true, 2>(d, a_row + 2, hi_word, b_tap + 2, hi_word, idesc, 1u, elected);
+                                } else {
+                                    umma<true>(d, a_row + a_lo_plane, hi_word, b_tap, hi_word, idesc, acc, elected);
+                                    umma<true>(d, a_row, hi_word, b_tap + b_lo_plane, hi_word, idesc, 1u, elected);
+                                    umma<true>(d, a_row, hi_word, b_tap, hi_word, idesc, 1u, elected);
+                                    umma<true>(d, a_row + a_lo_plane + 2, hi_word, b_tap + 2, hi_word, idesc, 1u, elected);
+                                    umma<true>(d, a_row + 2, hi_word, b_tap + b_lo_plane + 2, hi_word, idesc, 1u, elected);
+                                    umma<true>(d, a_row + 2, hi_word, b_tap + 2, hi_word, idesc, 1u, elected);
                                 }
                             } else {
 #pragma unroll
-                                for (int kb = 0; kb < 4; ++kb) {    // 4 x 8 channels
-                                    const uint32_t ah = desc_lo(a_row + kb * 32), bh = desc_lo(b_tap + kb * 32);
+                                for (uint32_t kb = 0; kb < 8; kb += 2) {   // 4 x 8 channels (32 bytes = 2 descriptor units each)
+                                    const uint32_t acc_k = kb == 0 ? acc : 1u;
                                     if (X3) {
-                                        const uint32_t al = desc_lo(a_row + a_lo_plane + kb * 32);
-                                        const uint32_t bl = desc_lo(b_tap + b_lo_plane + kb * 32);
-                                        umma<false>(d, al, hi_word, bh, hi_word, idesc, acc);
-                                        umma<false>(d, ah, hi_word, bl, hi_word, idesc, 1u);
-                                        acc = 1u;
+                                        umma<false>(d, a_row + a_lo_plane + kb, hi_word, b_tap + kb, hi_word, idesc, acc_k, elected);
+                                        umma<false, 1>(d, a_row + kb, hi_word, b_tap + b_lo_plane + kb, hi_word, idesc, 1u, elected);
+                                        umma<false, 2>(d, a_row + kb, hi_word, b_tap + kb, hi_word, idesc, 1u, elected);
+                                    } else {
+                                        umma<false>(d, a_row + kb, hi_word, b_tap + kb, hi_word, idesc, acc_k, elected);
                                     }
-                                    umma<false>(d, ah, hi_word, bh, hi_word, idesc, acc);
-                                    acc = 1u;
                                 }
                             }
+                            d += (uint32_t)p.n_tile, a_row += (kTcM * 128) >> 4;
                         }
                     }
                     fresh = 0;
-                    a_tap += tap_step, b_tap += p.wtile_bytes;
+                    a_tap += tap_step, b_tap += wtile_step;
                     if (++in_stage == p.tps || k + 1 == a.KS) {     // stage consumed: release its ring slot
                         in_stage = 0;
                         if (!p.w_resident) {
-                            if (elected) umma_commit(w_empty + sW);
+                            umma_commit(w_empty + sW, elected);
                             if (++sW == p.nW) sW = 0, phW ^= 1;
                         }
                     }
                 }
-                if (elected) umma_commit(a_empty + sA);
+                umma_commit(a_empty + sA, elected);
                 if (++sA == p.nA) sA = 0, phA ^= 1;
             }
-            if (elected) umma_commit(acc_full + as);
+            umma_commit(acc_full + as, elected);
             if (++as == p.n_sets) as = 0, phE ^= 1;
             first_group = false;
+        }
+        if (ST && elected) {
+            long long *o = p.stats + (size_t)blockIdx.x * kTcStatSlots;
+            o[3] = st_w0, o[4] = st_w1, o[5] = st_w2, o[6] = clock64() - st_t0;
         }
     } else if (warp >= kWarpTransform0) {
         // ====================== operand transform warps (256 threads) =================
@@ -255,7 +297,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         int sA = 0, phA = 0;
         for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
             for (int c = 0; c < p.n_chunks; ++c) {
-                mbar_wait(raw_full + sA, phA);
+                mbar_wait_t<ST>(raw_full + sA, phA, st_w0);
                 uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
                 // 64 rows per pass over the 256 threads: two independent rows per thread for ILP
                 for (int r0 = 0; r0 < ((p.dbg & 4) ? 0 : p.R); r0 += 64) {
@@ -323,6 +365,10 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 if (++sA == p.nA) sA = 0, phA ^= 1;
             }
         }
+        if (ST && tid == 0) {
+            long long *o = p.stats + (size_t)blockIdx.x * kTcStatSlots;
+            o[7] = st_w0, o[8] = clock64() - st_t0;
+        }
     } else {
         // ================================ epilogue warps (256 threads) ================
         // TMEM lane = time row, column = output channel; a warp may only touch lanes 32*(warp%4)..+31,
@@ -384,7 +430,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 return (((size_t)b * gout + (co0 >> 5)) * a.out_Tp + kPad +
                         (a.ups_u > 0 ? (size_t)q_base * a.ups_u + phi : (size_t)q_base)) * 8;
             };
-            mbar_wait(acc_full + as, (p.n_sets == 2 ? (gi >> 1) : gi) & 1);
+            mbar_wait_t<ST>(acc_full + as, (p.n_sets == 2 ? (gi >> 1) : gi) & 1, st_w0);
             tc_fence_after();
             for (int blk = half; blk < nblocks; blk += 2) {
                 const int m = blk / jb, j = blk - m * jb;
@@ -435,9 +481,14 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as);             // this accumulator set may be overwritten
         }
+        if (ST && threadIdx.x == 0) {
+            long long *o = p.stats + (size_t)blockIdx.x * kTcStatSlots;
+            o[9] = st_w0, o[10] = clock64() - st_t0;
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (ST && threadIdx.x == 0) p.stats[(size_t)blockIdx.x * kTcStatSlots + 11] = clock64() - st_t0;
     if (warp == kWarpMma) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
@@ -577,9 +628,9 @@ bool tc_supported(const TcWeights &w, const ConvArgs &a) {
            (a.ups_u == 0 || a.Cout % 32 == 0) && a.Cout <= 3072;
 }
 
-template <int MODE>
+template <int MODE, bool ST>
 static int launch_mode(const TcArgs &p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = conv1d_c4_tc_kernel<MODE>;
+    auto kern = conv1d_c4_tc_kernel<MODE, ST>;
     // function attributes are per device: one process may drive several GPUs (the reference's mp.spawn gives one each,
     // but nothing in the C ABI forbids a handle per device in one process)
     static size_t configured[kMaxDevices] = {};
@@ -632,6 +683,8 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     p.wtile_bytes = (uint32_t)p.n_tile * 128 * planes;
     p.dbg = 0;
     if (const char *e = getenv("SVB_TC_DBG")) p.dbg = atoi(e);
+    p.collect = 1;
+    if (const char *e = getenv("SVB_TC_COLLECT")) p.collect = atoi(e) != 0;
     p.pdl = 1;
     if (const char *e = getenv("SVB_TC_PDL")) p.pdl = atoi(e) != 0;
     int force_mt = 0;
@@ -704,10 +757,33 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     p.groups_per_b = (tiles + p.MT - 1) / p.MT;
     p.total_groups = p.groups_per_b * a.B * p.col_blocks;
     const int grid = std::min(p.total_groups, max_ctas > 0 ? std::min(max_ctas, sm_count()) : sm_count());
+    p.stats = nullptr;
+    const bool want_stats = getenv("SVB_TC_STATS") != nullptr;
+    if ((want_stats || p.dbg != 0 || !p.collect) && precision == SVB_PREC_BF16X3) {
+        // diagnostics: run the instrumented instantiation, wait for it and print where each role was blocked
+        const size_t n = (size_t)grid * kTcStatSlots;
+        SVB_CUDA(cudaMalloc((void **)&p.stats, n * sizeof(long long)));
+        SVB_CUDA(cudaMemsetAsync(p.stats, 0, n * sizeof(long long), st));
+        SVB_TRY((launch_mode<SVB_PREC_BF16X3, true>(p, grid, smem, st)));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> h(n);
+        SVB_CUDA(cudaMemcpy(h.data(), p.stats, n * sizeof(long long), cudaMemcpyDeviceToHost));
+        SVB_CUDA(cudaFree(p.stats));
+        double mean[kTcStatSlots] = {};
+        long long mx[kTcStatSlots] = {};
+        for (int c = 0; c < grid; ++c)
+            for (int i = 0; i < kTcStatSlots; ++i) mean[i] += (double)h[(size_t)c * kTcStatSlots + i] / grid, mx[i] = std::max(mx[i], h[(size_t)c * kTcStatSlots + i]);
+        if (want_stats) fprintf(stderr,
+                "[tc-stats] C%d>%d k%d d%d Tq %d grid %d groups %d MT %d | kcycles mean (max): total %.0f (%.0f) | producer: a_empty %.0f w_empty %.0f of %.0f | "
+                "mma: acc_empty %.0f a_ready %.0f w_full %.0f of %.0f | transform: raw_full %.0f of %.0f | epilogue: acc_full %.0f of %.0f\n",
+                a.Cin, a.CoutP, a.KS, a.dil, a.Tq, grid, p.total_groups, p.MT, mean[11] / 1e3, mx[11] / 1e3, mean[0] / 1e3, mean[1] / 1e3, mean[2] / 1e3,
+                mean[3] / 1e3, mean[4] / 1e3, mean[5] / 1e3, mean[6] / 1e3, mean[7] / 1e3, mean[8] / 1e3, mean[9] / 1e3, mean[10] / 1e3);
+        return SVB_OK;
+    }
     switch (precision) {
-        case SVB_PREC_TF32: return launch_mode<SVB_PREC_TF32>(p, grid, smem, st);
-        case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3>(p, grid, smem, st);
-        default: return launch_mode<SVB_PREC_BF16X3>(p, grid, smem, st);
+        case SVB_PREC_TF32: return launch_mode<SVB_PREC_TF32, false>(p, grid, smem, st);
+        case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3, false>(p, grid, smem, st);
+        default: return launch_mode<SVB_PREC_BF16X3, false>(p, grid, smem, st);
     }
 }
 

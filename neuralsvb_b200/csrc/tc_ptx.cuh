@@ -82,17 +82,13 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// converged-warp form of tcgen05.commit (see the issue discipline above umma)
+__device__ __forceinline__ void umma_commit(uint64_t *bar, uint32_t elected) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(elected)
         : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
 }
 __device__ __forceinline__ void umma_commit_mcast(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -130,25 +126,41 @@ __host__ __device__ inline uint32_t umma_idesc(int fmt, int M, int N) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <bool BF>
+// Issue discipline (measured with tools/mma_probe.cu, profiles/r02_mma_probe.txt): a tcgen05.mma issued from a
+// DIVERGENT single thread (`if (elected) { ... }`) makes the compiler wrap every UTCHMMA in a per-operand R2UR "waterfall"
+// loop (ELECT / R2UR.BROADCAST / BRA.U.ANY): 65-82 cycles per MMA whatever its size, i.e. slower than the tensor
+// pipe for every N < 256.  Issued warp-CONVERGED -- all 32 lanes execute the same instruction stream and the MMA itself
+// is predicated on the elect.sync lane -- descriptors and addresses live in uniform registers and one warp reaches the
+// hardware limits (N = 32: 40 clk = shared-memory operand fetch, N = 64: 48, N = 128: 64 = tensor floor).
+// The MMA warp must therefore be converged whenever it calls umma / umma_commit (hence __syncwarp() after every wait).
+//
+// COLL = use of the tensor core's A-operand collector buffer (PTX .collector::a::*): 0 discard (read A from shared
+// memory, keep nothing), 1 fill (read and keep), 2 lastuse (take A from the collector: no shared-memory read of A),
+// 3 use (take and keep).  Consecutive MMAs with the SAME A descriptor form a fill / use... / lastuse run.
+#define SVB_UMMA_ASM(KIND, COLLECT)                                                                         \
+    asm volatile(                                                                                           \
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"                                                   \
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"                                                \
+        "setp.ne.b32 p, %6, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"                                                \
+        "@q tcgen05.mma.cta_group::1.kind::" KIND COLLECT " [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),        \
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(elected)                      \
+        : "memory")
+
+// `elected` = elect_one_sync() of the converged issuing warp (non-zero in exactly one lane)
+template <bool BF, int COLL = 0>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                     uint32_t idesc, uint32_t acc) {
-    if (BF)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-            "setp.ne.b32 p, %6, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
-            : "memory");
-    else
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-            "setp.ne.b32 p, %6, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-            "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
-            : "memory");
+                                     uint32_t idesc, uint32_t acc, uint32_t elected) {
+    if (BF) {
+        if (COLL == 1) SVB_UMMA_ASM("f16", ".collector::a::fill");
+        else if (COLL == 2) SVB_UMMA_ASM("f16", ".collector::a::lastuse");
+        else if (COLL == 3) SVB_UMMA_ASM("f16", ".collector::a::use");
+        else SVB_UMMA_ASM("f16", "");
+    } else {
+        if (COLL == 1) SVB_UMMA_ASM("tf32", ".collector::a::fill");
+        else if (COLL == 2) SVB_UMMA_ASM("tf32", ".collector::a::lastuse");
+        else if (COLL == 3) SVB_UMMA_ASM("tf32", ".collector::a::use");
+        else SVB_UMMA_ASM("tf32", "");
+    }
 }
 
 __device__ __forceinline__ float to_tf32(float x) {

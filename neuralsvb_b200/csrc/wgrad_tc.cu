@@ -126,28 +126,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(WgTcArgs p) {
         int s = 0, ph = 0;
         uint32_t fresh = 1;
         bool any = false;
+        // converged-warp issue (tc_ptx.cuh, "issue discipline"): every lane walks the loops, MMAs / commits are predicated
         for (int u = sp; u < n_units; u += p.splits) {
             mbar_wait(ready + s, ph);
+            __syncwarp();
             tc_fence_after();
-            if (elected) {
-                const uint32_t xa = smem_u32(x_tile(s, 0)), gb = smem_u32(g_tile(s, 0));
+            const uint32_t xa = smem_u32(x_tile(s, 0)), gb = smem_u32(g_tile(s, 0));
 #pragma unroll 1
-                for (int ks = 0; ks < kWgChunk / 16; ++ks) {
-                    const uint32_t b_lo = (((gb + (uint32_t)ks * 16 * 128) >> 4) & 0x3FFFu) | (lbo_b << 16);
+            for (int ks = 0; ks < kWgChunk / 16; ++ks) {
+                const uint32_t b_lo = (((gb + (uint32_t)ks * 16 * 128) >> 4) & 0x3FFFu) | (lbo_b << 16);
 #pragma unroll 1
-                    for (int tk = 0; tk < ntaps; ++tk) {
-                        const uint32_t row = (uint32_t)ks * 16 + (uint32_t)((k0 + tk) * a.da);
-                        const uint32_t a_lo = (((xa + row * 128) >> 4) & 0x3FFFu) | (lbo_a << 16);
-                        umma<true>(tmem_base + (uint32_t)(tk * 128), a_lo, hi_word, b_lo, hi_word, idesc, fresh ^ 1u);
-                    }
-                    fresh = 0;
+                for (int tk = 0; tk < ntaps; ++tk) {
+                    const uint32_t row = (uint32_t)ks * 16 + (uint32_t)((k0 + tk) * a.da);
+                    const uint32_t a_lo = (((xa + row * 128) >> 4) & 0x3FFFu) | (lbo_a << 16);
+                    umma<true>(tmem_base + (uint32_t)(tk * 128), a_lo, hi_word, b_lo, hi_word, idesc, fresh ^ 1u, elected);
                 }
-                umma_commit(empty + s);
+                fresh = 0;
             }
+            umma_commit(empty + s, elected);
             any = true;
             if (++s == kWgStages) s = 0, ph ^= 1;
         }
-        if (elected) umma_commit(done);
+        umma_commit(done, elected);
         (void)any;
     } else {
         // ====================== operand transform warps (2..9), then epilogue (2..5) ==================
