@@ -9,13 +9,18 @@
 //   PLACE into the MMA operand: leaky-relu pre-activation, hi/lo split (or tf32 rounding) and the
 //   SWIZZLE_128B chunk permutation; one 128-byte K-major row per time step.  A conv tap at
 //   dilation d is a ROW SHIFT of that operand = +128*k*d bytes on the descriptor start address,
-//   so one slab (MT*128 + halo rows) feeds all KS taps of MT accumulator tiles.
+//   so one slab (mt*128 + halo rows) feeds all KS taps of mt accumulator tiles.
 // * B operand = weights, packed and pre-swizzled on the host per (column block, input-channel
 //   chunk, tap), streamed through a ring of bulk copies (or kept resident for narrow layers).
-// * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + elected-lane
-//   MMA issuer, warps 2..5 = operand transform, warps 6..13 = epilogue (tcgen05.ld -> bias /
-//   residual / scale / accumulate -> 128-byte row stores) on the accumulator set the MMAs are not
-//   writing.  HBM tensors stay exact fp32; rounding happens only on the operand copy in smem.
+// * Persistent, warp-specialised: TMA producer warp, MMA warp (TMEM owner; converged-warp issue,
+//   see tc_ptx.cuh), 8 operand-transform warps, 8 epilogue warps (tcgen05.ld -> bias / residual /
+//   scale / accumulate -> 128-byte row stores) on the accumulator set the MMAs are not writing.
+//   HBM tensors stay exact fp32; rounding happens only on the operand copy in smem.
+// * One launch runs a WORK LIST: items (layer, column block, clip, first row, tiles) in the order
+//   each CTA executes them.  A single layer uses the implicit round-robin list; the generator hands
+//   in host-built lists that merge the independent ResBlock chains of a stage into one launch
+//   (up to 3 layers of the same shape class, longest-processing-time balanced over the SMs), so the
+//   pipeline fill / drain of a persistent launch is paid once per step of the chains, not per layer.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -31,25 +36,42 @@ namespace svb {
 
 constexpr int kTcM = 128;       // rows per CTA (UMMA M)
 constexpr int kTcCK = 32;       // input channels per chunk = 4 MMAs of K = 8
+constexpr int kMaxItems = 120;  // work items per CTA staged in shared memory (16 bytes each)
+constexpr int kItemBytes = 2048;
 
 
 // Operand modes (svb_precision): 1 = 1xTF32, 2 = 3xTF32, 3 = 3xBF16 (hi/lo split, 16-bit mantissa).
 // One operand row = 32 input channels = 128 bytes:  TF32: 32 x tf32 ; BF16x3: [32 x bf16 hi | 32 x bf16 lo].
+struct TcLayer {                // what differs between the layers of one launch
+    const float *in;            // G32T input
+    const float *res;           // residual (G32T like out) or nullptr
+    float *out;
+    const float *bias;
+    const unsigned char *w;     // packed, pre-swizzled weight tiles of this layer in the launch's precision mode
+    int KS, dil;
+    float out_scale;
+    int accumulate;
+    int bias_off;               // float offset of this layer's bias in the shared-memory bias area
+    uint32_t w_res_off;         // resident weights: byte offset of this layer's tiles in the resident area
+};
+
 struct TcArgs {
-    ConvArgs a;
-    const unsigned char *w;     // packed, pre-swizzled weight tiles of this mode
-    int n_tile, n_chunks, MT, R, Rp, nW, nA, tmem_cols;
-    int n_sets;                 // accumulator sets in TMEM: 2 = epilogue of group g overlaps MMAs of g+1; 1 = MT can be twice as large
+    ConvArgs a;                 // the shape class (B, channels, rows, in_slope, ups_u ...); per-layer fields live in L[]
+    TcLayer L[kTcMaxLayers];
+    int n_layers;
+    const int4 *work;           // explicit work list (device) or nullptr: implicit round-robin over the groups of layer 0
+    const int *work_off;        // [grid + 1] item ranges per CTA
+    int n_tile, n_chunks, MT, nW, nA, tmem_cols;
+    int n_sets;                 // accumulator sets in TMEM: 2 = epilogue of item n overlaps the MMAs of n + 1
     int col_blocks, groups_per_b, total_groups;
-    int tps, n_st, w_resident;  // taps per weight stage, stages per chunk, whole layer resident in smem
+    int w_resident;             // every layer's tiles stay in shared memory for the whole launch (narrow layers)
     int blk_chunk_step;         // grouped conv: first input chunk of column block nblk = nblk * blk_chunk_step (0: dense)
-    uint32_t wstage_bytes;      // ring slot = tps weight tiles
+    uint32_t w_res_bytes;       // resident: total bytes of all layers' tiles
     int pdl;                    // launched with programmatic stream serialization
     int collect;                // A-operand collector reuse between the two products of a_hi (SVB_TC_COLLECT, default on)
     long long *stats;           // SVB_TC_STATS: [grid][kTcStatSlots] blocked-cycle counters (diagnostics build of the kernel)
     int dbg;                    // SVB_TC_DBG bit mask: 1 no MMAs, 2 hi*hi only, 4 no transform, 8 no epilogue ld/st
-    uint32_t raw_bytes;         // fp32 slab as TMA delivers it: R rows x 128 B
-    uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane)
+    uint32_t op_bytes;          // operand slot: Rp rows x 128 B (x2 with the 3xTF32 lo plane), sized for the largest halo
     uint32_t wtile_bytes;       // one (column block, chunk, tap) weight tile (x2 with the 3xTF32 lo plane)
     uint32_t off_op, off_w, off_stage, off_bias;   // byte offsets of operand slots / weight ring / epilogue tiles / bias in dynamic smem
 };
@@ -61,13 +83,8 @@ constexpr int kMaxDevices = 64;     // per-device caches of function attributes 
 constexpr int kTcThreadsP = 576;
 constexpr int kWarpProducer = 16, kWarpMma = 17, kWarpTransform0 = 8;
 constexpr int kStageBytes = 8 * 4096;   // epilogue transpose tiles: 32 rows x 128 B per epilogue warp
-constexpr int kBiasBytes = 4096;        // bias of the layer (Cout <= 1024 floats; wider layers take 12 KB)
+constexpr int kBiasBytes = 4096;        // bias of the layer(s) (<= 1024 floats; wider layers take 12 KB)
 
-// Persistent kernel: one CTA per SM walks "groups" (MT consecutive 128-row tiles of one clip for
-// one column block).  Every stage is decoupled by mbarriers, so the TMA producer runs ahead into
-// the next group, the transform warps prepare operands while the tensor core works on the
-// previous chunk, and the epilogue drains accumulator set (g & 1) from TMEM while the MMAs of
-// group g + 1 fill the other set.
 // STATS (SVB_TC_STATS=1, diagnostics only): every role accumulates the cycles it spends blocked on each of its
 // barriers; the launcher prints the per-CTA mean / max.  Says which stage of the pipeline the others wait for.
 template <bool ST>
@@ -80,10 +97,32 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, long
         mbar_wait(bar, parity);
     }
 }
+// wait of a converged single-role warp: every lane polls (measured: one polling lane + __syncwarp for the rest doubles the
+// time of every layer), then the warp re-converges -- the uniform-datapath instructions that follow execute once per
+// converged warp (tc_ptx.cuh)
+template <bool ST>
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, long long &acc) {
+    mbar_wait_t<ST>(bar, parity, acc);
+    __syncwarp();
+}
 constexpr int kTcStatSlots = 16;
 
+// a work item, as staged in shared memory: x = layer | column block << 8 | tiles << 24, y = clip, z = first row
+struct TcItem {
+    int layer, nblk, mt, b, t0;
+};
+__device__ __forceinline__ TcItem item_decode(const int4 v) {
+    TcItem it;
+    it.layer = v.x & 0xff, it.nblk = (v.x >> 8) & 0xffff, it.mt = v.x >> 24, it.b = v.y, it.t0 = v.z;
+    return it;
+}
+
+// Persistent kernel: one CTA per SM walks its work items (mt consecutive 128-row tiles of one clip for one
+// column block of one layer).  Every stage is decoupled by mbarriers, so the TMA producer runs ahead into
+// the next item, the transform warps prepare operands while the tensor core works on the previous chunk,
+// and the epilogue drains accumulator set (n & 1) from TMEM while the MMAs of item n + 1 fill the other set.
 template <int MODE, bool ST = false>
-__global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) {
+__global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(const __grid_constant__ TcArgs p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr bool BF = MODE == SVB_PREC_BF16X3;
     constexpr bool X3 = MODE == SVB_PREC_TF32X3;
@@ -94,14 +133,18 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     uint64_t *w_full = bars + 12, *w_empty = bars + 12 + kMaxW;
     uint64_t *acc_full = bars + 12 + 2 * kMaxW, *acc_empty = acc_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    int *n_items_s = reinterpret_cast<int *>(tmem_ptr + 1);
+    TcLayer *Ls = reinterpret_cast<TcLayer *>(smem + 512);                    // per-layer table (dynamic indexing)
+    const int4 *items = reinterpret_cast<const int4 *>(smem + 1024);         // [kMaxItems]
     unsigned char *op0 = smem + p.off_op;                            // [nA][op_bytes]: TMA target AND MMA operand
-    unsigned char *wring = smem + p.off_w;                           // [nW][wtile_bytes]
+    unsigned char *wring = smem + p.off_w;                           // [nW][wtile_bytes] ring, or the resident tiles
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int halo = (a.KS - 1) / 2 * a.dil;
     const int acc_cols = p.MT * p.n_tile;                            // columns of one accumulator set
     long long st_w0 = 0, st_w1 = 0, st_w2 = 0;                       // STATS: cycles blocked on up to three barriers
     const long long st_t0 = ST ? clock64() : 0;
+    unsigned long long st_g0 = 0;
+    if (ST) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_g0));
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(raw_full + i, 1), mbar_init(a_ready + i, 8), mbar_init(a_empty + i, 1);
@@ -110,14 +153,31 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         fence_barrier_init();
     }
     if (warp == kWarpMma) tmem_alloc(tmem_ptr, p.tmem_cols);
-    {   // bias is constant data (not produced by the previous kernel): stage it once, before the PDL wait
+    {   // constant data (not produced by the previous kernel): staged once, before the PDL wait
         float *sb = reinterpret_cast<float *>(smem + p.off_bias);
-        for (int i = threadIdx.x; i < a.Cout; i += kTcThreadsP) sb[i] = __ldg(a.bias + i);
+        for (int l = 0; l < p.n_layers; ++l)
+            for (int i = threadIdx.x; i < a.Cout; i += kTcThreadsP) sb[p.L[l].bias_off + i] = __ldg(p.L[l].bias + i);
+        if (threadIdx.x < p.n_layers) Ls[threadIdx.x] = p.L[threadIdx.x];
+        int4 *it_w = reinterpret_cast<int4 *>(smem + 1024);
+        if (p.work) {                                                // explicit list: this CTA's range
+            const int i0 = __ldg(p.work_off + blockIdx.x), n = __ldg(p.work_off + blockIdx.x + 1) - i0;
+            for (int i = threadIdx.x; i < n; i += kTcThreadsP) it_w[i] = __ldg(p.work + i0 + i);
+            if (threadIdx.x == 0) *n_items_s = n;
+        } else {                                                     // implicit: groups blockIdx.x, + gridDim.x, ... of layer 0
+            const int n = ((int)blockIdx.x < p.total_groups) ? (p.total_groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+            for (int i = threadIdx.x; i < n; i += kTcThreadsP) {
+                const int g = blockIdx.x + i * gridDim.x;
+                const int tg = g % p.groups_per_b, r = g / p.groups_per_b;
+                it_w[i] = make_int4(((r / a.B) << 8) | (p.MT << 24), r % a.B, tg * (kTcM * p.MT), 0);
+            }
+            if (threadIdx.x == 0) *n_items_s = n;
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const int n_items = *n_items_s;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the
     // tail of the previous kernel in the stream; its results are needed from here on.  The next
     // kernel may begin ITS prologue as soon as every CTA of this grid has reached this point.
@@ -126,55 +186,46 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
 
-    // group id -> (column block, clip, first row); consecutive ids are neighbours in time
-    auto decode = [&](int g, int &nblk, int &b, int &t0) {
-        const int tg = g % p.groups_per_b;
-        const int r = g / p.groups_per_b;
-        b = r % a.B, nblk = r / a.B, t0 = tg * (kTcM * p.MT);
-    };
-
-    // The two single-thread roles below are latency-critical (every instruction they execute sits
+    // The two single-warp roles below are latency-critical (every instruction they execute sits
     // between two TMA copies or two MMAs), so all ring indices / phases are kept as incrementing
     // counters -- no runtime integer divisions in the loops.
     if (warp == kWarpProducer) {
         // ================================ TMA producer ================================
-        // One bulk copy per slab (R rows x 128 B, contiguous in G32T) and one per weight stage.
+        // One bulk copy per slab (rows x 128 B, contiguous in G32T) and one per weight tile, issued by one lane (measured:
+        // a converged producer warp is no faster -- the copies are far from their issue limit -- and its item-dependent
+        // addresses would have to be made warp-uniform first, see the MMA warp).
         if (lane == 0) {
             const int gin = c4t_groups(a.Cin);
             const size_t group_stride = (size_t)a.in_Tp * 32;                     // floats between channel groups
-            const size_t chunk_w_bytes = (size_t)a.KS * p.wtile_bytes;
             int sA = 0, phA = 1, sW = 0, phW = 1;                                 // "empty" barriers start free
-            int tg = blockIdx.x % p.groups_per_b, rb = blockIdx.x / p.groups_per_b;   // group -> (time group, b + B*nblk)
-            const int step_tg = gridDim.x % p.groups_per_b, step_rb = gridDim.x / p.groups_per_b;
-            bool first_group = true;
-            for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
-                const int b = rb % a.B, nblk = rb / a.B;
-                const int t0 = tg * (kTcM * p.MT);
-                const float *in_c = a.in + (((size_t)b * gin + (size_t)nblk * p.blk_chunk_step) * a.in_Tp + (kPad + t0 - halo)) * 32;
-                const unsigned char *w_c = p.w + (size_t)nblk * p.n_chunks * chunk_w_bytes;
+            if (p.w_resident && n_items > 0) {                                    // all layers' tiles, once
+                mbar_expect_tx(w_full, p.w_res_bytes);
+                for (int l = 0; l < p.n_layers; ++l)
+                    bulk_g2s(wring + Ls[l].w_res_off, Ls[l].w, (uint32_t)Ls[l].KS * p.wtile_bytes, w_full);
+            }
+            for (int n = 0; n < n_items; ++n) {
+                const TcItem it = item_decode(items[n]);
+                const TcLayer &L = Ls[it.layer];
+                const int halo = (L.KS - 1) / 2 * L.dil;
+                const uint32_t raw_bytes = (uint32_t)(it.mt * kTcM + 2 * halo) * 128;
+                const float *in_c = L.in + (((size_t)it.b * gin + (size_t)it.nblk * p.blk_chunk_step) * a.in_Tp + (kPad + it.t0 - halo)) * 32;
+                const unsigned char *w_k = L.w + (size_t)it.nblk * p.n_chunks * L.KS * p.wtile_bytes;
                 for (int c = 0; c < p.n_chunks; ++c) {
                     mbar_wait_t<ST>(a_empty + sA, phA, st_w0);                    // MMAs of the slot's previous slab retired
-                    mbar_expect_tx(raw_full + sA, p.raw_bytes);
-                    bulk_g2s(op0 + sA * p.op_bytes, in_c, p.raw_bytes, raw_full + sA);
+                    mbar_expect_tx(raw_full + sA, raw_bytes);
+                    bulk_g2s(op0 + sA * p.op_bytes, in_c, raw_bytes, raw_full + sA);
                     in_c += group_stride;
                     if (++sA == p.nA) sA = 0, phA ^= 1;
-                    if (!(p.w_resident && !first_group)) {
-                        const unsigned char *w_k = w_c;
-                        for (int st = 0; st < p.n_st; ++st) {
-                            const int nt = min(p.tps, a.KS - st * p.tps);
-                            const uint32_t bytes = (uint32_t)nt * p.wtile_bytes;
+                    if (!p.w_resident) {
+                        for (int k = 0; k < L.KS; ++k) {
                             mbar_wait_t<ST>(w_empty + sW, phW, st_w1);
-                            mbar_expect_tx(w_full + sW, bytes);
-                            bulk_g2s(wring + sW * p.wstage_bytes, w_k, bytes, w_full + sW);
-                            w_k += bytes;
+                            mbar_expect_tx(w_full + sW, p.wtile_bytes);
+                            bulk_g2s(wring + sW * p.wtile_bytes, w_k, p.wtile_bytes, w_full + sW);
+                            w_k += p.wtile_bytes;
                             if (++sW == p.nW) sW = 0, phW ^= 1;
                         }
                     }
-                    w_c += chunk_w_bytes;
                 }
-                first_group = false;
-                tg += step_tg, rb += step_rb;
-                if (tg >= p.groups_per_b) tg -= p.groups_per_b, ++rb;
             }
             if (ST) {
                 long long *o = p.stats + (size_t)blockIdx.x * kTcStatSlots;
@@ -195,38 +246,44 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         const uint32_t a_lo_plane = (X3 ? p.op_bytes / 2 : 64u) >> 4;      // lo plane / half-row
         const uint32_t b_lo_plane = (X3 ? p.wtile_bytes / 2 : 64u) >> 4;
         const uint32_t op_base = desc_lo(smem_u32(op0)), w_base = desc_lo(smem_u32(wring));
-        const uint32_t tap_step = (uint32_t)a.dil * (128 >> 4);            // a tap is a row shift of the operand
-        const uint32_t op_step = p.op_bytes >> 4, wstage_step = p.wstage_bytes >> 4, wtile_step = p.wtile_bytes >> 4;
+        const uint32_t op_step = p.op_bytes >> 4, wtile_step = p.wtile_bytes >> 4;
         // the ablation switches exist only in the diagnostics instantiation
         const bool mma_on = ST ? !(p.dbg & 1) : true, hh_only = ST ? (p.dbg & 2) != 0 : false, collect = ST ? p.collect != 0 : true;
         int sA = 0, phA = 0, sW = 0, phW = 0, as = 0, phE = 1;
-        bool first_group = true;
-        for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
-            mbar_wait_t<ST>(acc_empty + as, phE, st_w0);            // epilogue has drained this accumulator set
-            __syncwarp();
+        if (p.w_resident && n_items > 0) {
+            mbar_wait_warp<ST>(w_full, 0, st_w2);
+            tc_fence_after();
+        }
+        const int n_items_u = __reduce_max_sync(0xffffffffu, n_items);
+        for (int n = 0; n < n_items_u; ++n) {
+            // The item comes from shared memory, i.e. in a vector register the compiler must assume divergent: with it
+            // every loop bound / descriptor below turns into per-MMA VOTEU / R2UR traffic (+25 % on the narrow layers).
+            // A warp reduction (REDUX) hands the same value back in a UNIFORM register; the layer's fields are then
+            // read from the kernel parameters (constant bank, uniform index).
+            const int ix = __reduce_max_sync(0xffffffffu, items[n].x);
+            const int layer = ix & 0xff, mt = ix >> 24;
+            const int KS = p.L[layer].KS;
+            const uint32_t tap_step = (uint32_t)p.L[layer].dil * (128 >> 4);   // a tap is a row shift of the operand
+            const uint32_t w_res_off = p.L[layer].w_res_off >> 4;
+            mbar_wait_warp<ST>(acc_empty + as, phE, st_w0);                   // epilogue has drained this accumulator set
             tc_fence_after();
             const uint32_t d_set = tmem_base + (uint32_t)(as * acc_cols);
-            uint32_t fresh = 1;                                     // first MMA of the group overwrites
+            uint32_t fresh = 1;                                               // first MMA of the item overwrites
             for (int c = 0; c < p.n_chunks; ++c) {
-                mbar_wait_t<ST>(a_ready + sA, phA, st_w1);
-                __syncwarp();
+                mbar_wait_warp<ST>(a_ready + sA, phA, st_w1);
                 tc_fence_after();
                 uint32_t a_tap = op_base + sA * op_step;
-                int in_stage = 0;
-                uint32_t b_tap = 0;
-                for (int k = 0; k < a.KS; ++k) {
-                    if (in_stage == 0) {                            // first tap of a weight stage
-                        if (!(p.w_resident && !first_group)) {
-                            mbar_wait_t<ST>(w_full + sW, phW, st_w2);
-                            __syncwarp();
-                            tc_fence_after();
-                        }
-                        b_tap = w_base + sW * wstage_step;
+                uint32_t b_tap = w_base + w_res_off;                          // resident tiles (single chunk)
+                for (int k = 0; k < KS; ++k) {
+                    if (!p.w_resident) {
+                        mbar_wait_warp<ST>(w_full + sW, phW, st_w2);
+                        tc_fence_after();
+                        b_tap = w_base + sW * wtile_step;
                     }
                     if (mma_on) {
                         uint32_t d = d_set, a_row = a_tap;
 #pragma unroll 1
-                        for (int m = 0; m < p.MT; ++m) {
+                        for (int m = 0; m < mt; ++m) {
                             const uint32_t acc = fresh ^ 1u;
                             if (BF) {                               // 2 x 16 channels; small cross terms first
                                 if (hh_only) {
@@ -265,12 +322,9 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                     }
                     fresh = 0;
                     a_tap += tap_step, b_tap += wtile_step;
-                    if (++in_stage == p.tps || k + 1 == a.KS) {     // stage consumed: release its ring slot
-                        in_stage = 0;
-                        if (!p.w_resident) {
-                            umma_commit(w_empty + sW, elected);
-                            if (++sW == p.nW) sW = 0, phW ^= 1;
-                        }
+                    if (!p.w_resident) {                            // tile consumed: release its ring slot
+                        umma_commit(w_empty + sW, elected);
+                        if (++sW == p.nW) sW = 0, phW ^= 1;
                     }
                 }
                 umma_commit(a_empty + sA, elected);
@@ -278,7 +332,6 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
             }
             umma_commit(acc_full + as, elected);
             if (++as == p.n_sets) as = 0, phE ^= 1;
-            first_group = false;
         }
         if (ST && elected) {
             long long *o = p.stats + (size_t)blockIdx.x * kTcStatSlots;
@@ -295,19 +348,21 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         const bool odd = cl & 1;
         const float slope = a.in_slope;                         // 0 <= slope <= 1: lrelu(x) = max(x, slope * x)
         int sA = 0, phA = 0;
-        for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x) {
+        for (int n = 0; n < n_items; ++n) {
+            const TcItem it = item_decode(items[n]);
+            const int R = it.mt * kTcM + (Ls[it.layer].KS - 1) / 2 * Ls[it.layer].dil * 2;
             for (int c = 0; c < p.n_chunks; ++c) {
                 mbar_wait_t<ST>(raw_full + sA, phA, st_w0);
                 uint4 *op = reinterpret_cast<uint4 *>(op0 + sA * p.op_bytes);
                 // 64 rows per pass over the 256 threads: two independent rows per thread for ILP
-                for (int r0 = 0; r0 < ((p.dbg & 4) ? 0 : p.R); r0 += 64) {
+                for (int r0 = 0; r0 < ((p.dbg & 4) ? 0 : R); r0 += 64) {
                     int rr[2];
                     bool ok[2];
                     float4 v[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         rr[u] = r0 + 32 * u + (tid >> 3);
-                        ok[u] = rr[u] < p.R;
+                        ok[u] = rr[u] < R;
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (ok[u]) v[u] = *reinterpret_cast<const float4 *>(op + (size_t)rr[u] * 8 + cl);
                     }
@@ -381,83 +436,81 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
         const int lane_base = 32 * (warp & 3);
         const int half = ew >> 2;                                   // 0 / 1: which blocks this warp takes
         const int gout = c4t_groups(a.Cout);
-        const float4 *res4 = reinterpret_cast<const float4 *>(a.res);
-        float4 *out4 = reinterpret_cast<float4 *>(a.out);
         float4 *tile = reinterpret_cast<float4 *>(smem + p.off_stage + ew * 4096);   // [32 rows][8 chunks], chunk ^ (row & 7)
-        const int jb = p.n_tile / 32, nblocks = p.MT * jb;
+        const int jb = p.n_tile / 32;
         const int wr = lane >> 3, wc = lane & 7;                    // wide mapping: row offset / chunk
         const bool no_mem = p.dbg & 8;
-        int gi = 0;
         const size_t rstep = (size_t)(a.ups_u > 0 ? a.ups_u : 1) * 8;      // float4 between consecutive GEMM rows
         float4 rres[8];
-        // (group, block) -> float4 index of row (q_base + 0) of its 32-row x 128-byte tile; rows are rstep apart;
+        // (item, block) -> float4 index of row (q_base + 0) of its 32-row x 128-byte tile; rows are rstep apart;
         // q_base = first GEMM row of this warp in the block
-        auto block_base_g = [&](int g, int blk, int &co0, int &q_base) -> size_t {
-            int nblk, b, t0;
-            decode(g, nblk, b, t0);
+        auto block_base = [&](const TcItem &it, int blk, int &co0, int &q_base) -> size_t {
             const int m = blk / jb, j = blk - m * jb;
-            q_base = t0 + m * kTcM + lane_base;
-            const int cop0 = nblk * p.n_tile + j * 32;              // 32 columns never straddle an upsampler phase
+            q_base = it.t0 + m * kTcM + lane_base;
+            const int cop0 = it.nblk * p.n_tile + j * 32;           // 32 columns never straddle an upsampler phase
             int phi = 0;
             co0 = cop0;
             if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
-            return (((size_t)b * gout + (co0 >> 5)) * a.out_Tp + kPad +
+            return (((size_t)it.b * gout + (co0 >> 5)) * a.out_Tp + kPad +
                     (a.ups_u > 0 ? (size_t)q_base * a.ups_u + phi : (size_t)q_base)) * 8;
         };
         // residual rows of one block in the wide mapping -> registers (latency hidden behind the current block)
-        auto fetch_res = [&](int g, int blk) {
-            if (!res4 || no_mem || g >= p.total_groups) return;
+        auto fetch_res = [&](int n, int blk) {
+            if (no_mem || n >= n_items) return;
+            const TcItem it = item_decode(items[n]);
+            const float4 *res4 = reinterpret_cast<const float4 *>(Ls[it.layer].res);
+            if (!res4 || blk >= it.mt * jb) return;
             int co0, q_base;
-            const size_t base = block_base_g(g, blk, co0, q_base);
+            const size_t base = block_base(it, blk, co0, q_base);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rr = 4 * i + wr;
                 rres[i] = (q_base + rr < a.Tq) ? __ldg(res4 + base + (size_t)rr * rstep + wc) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        if (half < nblocks) fetch_res(blockIdx.x, half);
-        for (int g = blockIdx.x; g < p.total_groups; g += gridDim.x, ++gi) {
-            int nblk, b, t0;
-            decode(g, nblk, b, t0);
-            const int as = p.n_sets == 2 ? (gi & 1) : 0;
-            auto block_base = [&](int blk, int &co0, int &q_base) -> size_t {
-                const int m = blk / jb, j = blk - m * jb;
-                q_base = t0 + m * kTcM + lane_base;
-                const int cop0 = nblk * p.n_tile + j * 32;          // 32 columns never straddle an upsampler phase
-                int phi = 0;
-                co0 = cop0;
-                if (a.ups_u > 0) { phi = cop0 / a.Cout; co0 = cop0 - phi * a.Cout; }
-                return (((size_t)b * gout + (co0 >> 5)) * a.out_Tp + kPad +
-                        (a.ups_u > 0 ? (size_t)q_base * a.ups_u + phi : (size_t)q_base)) * 8;
-            };
-            mbar_wait_t<ST>(acc_full + as, (p.n_sets == 2 ? (gi >> 1) : gi) & 1, st_w0);
+        fetch_res(0, half);
+        int as = 0, phF = 0;
+        for (int n = 0; n < n_items; ++n) {
+            const TcItem it = item_decode(items[n]);
+            const TcLayer &L = Ls[it.layer];
+            const bool has_res = L.res != nullptr;
+            float4 *out4 = reinterpret_cast<float4 *>(L.out);
+            const float out_scale = L.out_scale;
+            const int accumulate = L.accumulate;
+            const unsigned char *bias_s = smem + p.off_bias + (size_t)L.bias_off * 4;
+            const int nblocks = it.mt * jb;
+            mbar_wait_t<ST>(acc_full + as, phF, st_w0);
             tc_fence_after();
             for (int blk = half; blk < nblocks; blk += 2) {
                 const int m = blk / jb, j = blk - m * jb;
                 int co0, q_base;
-                const size_t base = block_base(blk, co0, q_base);
-                if (res4) {                                          // residual: wide registers -> tile
+                const size_t base = block_base(it, blk, co0, q_base);
+                if (has_res) {                                       // residual: wide registers -> tile
 #pragma unroll
                     for (int i = 0; i < 8; ++i) tile[(4 * i + wr) * 8 + (wc ^ ((4 * i + wr) & 7))] = rres[i];
                     __syncwarp();
                 }
-                // prefetch the residual of this warp's NEXT block: same group, or the first one of its next group
-                if (blk + 2 < nblocks) fetch_res(g, blk + 2);
-                else fetch_res(g + gridDim.x, half);
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * acc_cols + m * p.n_tile + j * 32), v);
-                // own row: accumulator + bias (+ residual) -> tile
+                // prefetch the residual of this warp's NEXT block: same item, or the first one of its next item
+                if (blk + 2 < nblocks) fetch_res(n, blk + 2);
+                else fetch_res(n + 1, half);
+                // own row: accumulator + bias (+ residual) -> tile, 16 columns at a time (register budget: 18 warps x 96)
 #pragma unroll
-                for (int gq = 0; gq < 8; ++gq) {
-                    const float4 bv = *reinterpret_cast<const float4 *>(smem + p.off_bias + (size_t)(co0 + 4 * gq) * 4);
-                    float4 o = make_float4(v[4 * gq] + bv.x, v[4 * gq + 1] + bv.y, v[4 * gq + 2] + bv.z, v[4 * gq + 3] + bv.w);
-                    float4 *slot = tile + lane * 8 + (gq ^ (lane & 7));
-                    if (res4) {
-                        const float4 rv = *slot;
-                        o.x += rv.x, o.y += rv.y, o.z += rv.z, o.w += rv.w;
+                for (int hq = 0; hq < 2; ++hq) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(as * acc_cols + m * p.n_tile + j * 32 + hq * 16), v);
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        const int gq = hq * 4 + g4;
+                        const float4 bv = *reinterpret_cast<const float4 *>(bias_s + (size_t)(co0 + 4 * gq) * 4);
+                        float4 o = make_float4(v[4 * g4] + bv.x, v[4 * g4 + 1] + bv.y, v[4 * g4 + 2] + bv.z, v[4 * g4 + 3] + bv.w);
+                        float4 *slot = tile + lane * 8 + (gq ^ (lane & 7));
+                        if (has_res) {
+                            const float4 rv = *slot;
+                            o.x += rv.x, o.y += rv.y, o.z += rv.z, o.w += rv.w;
+                        }
+                        o.x *= out_scale, o.y *= out_scale, o.z *= out_scale, o.w *= out_scale;
+                        *slot = o;
                     }
-                    o.x *= a.out_scale, o.y *= a.out_scale, o.z *= a.out_scale, o.w *= a.out_scale;
-                    *slot = o;
                 }
                 __syncwarp();
                 // tile -> global, wide mapping (512 contiguous bytes per store instruction)
@@ -468,7 +521,7 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                         if (q_base + rr >= a.Tq) continue;
                         float4 o = tile[rr * 8 + (wc ^ (rr & 7))];
                         float4 *dst = out4 + base + (size_t)rr * rstep + wc;
-                        if (a.accumulate) {
+                        if (accumulate) {                            // same thread wrote *dst in the item before (chain-ordered lists)
                             const float4 old = *dst;
                             o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
                         }
@@ -477,9 +530,11 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
                 }
                 __syncwarp();
             }
+            if (half >= nblocks) fetch_res(n + 1, half);            // idle on this item (one block): still owes the next item's prefetch
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as);             // this accumulator set may be overwritten
+            if (++as == p.n_sets) as = 0, phF ^= 1;
         }
         if (ST && threadIdx.x == 0) {
             long long *o = p.stats + (size_t)blockIdx.x * kTcStatSlots;
@@ -488,7 +543,13 @@ __global__ void __launch_bounds__(kTcThreadsP, 1) conv1d_c4_tc_kernel(TcArgs p) 
     }
     tc_fence_before();
     __syncthreads();
-    if (ST && threadIdx.x == 0) p.stats[(size_t)blockIdx.x * kTcStatSlots + 11] = clock64() - st_t0;
+    if (ST && threadIdx.x == 0) {
+        unsigned long long g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        p.stats[(size_t)blockIdx.x * kTcStatSlots + 11] = clock64() - st_t0;
+        p.stats[(size_t)blockIdx.x * kTcStatSlots + 12] = (long long)st_g0;      // absolute ns: first start / last end over the grid
+        p.stats[(size_t)blockIdx.x * kTcStatSlots + 13] = (long long)g1;
+    }
     if (warp == kWarpMma) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
@@ -668,17 +729,26 @@ static int sm_count() {
     return n[slot];
 }
 
-int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st, int max_ctas) {
-    SVB_CHECK(precision >= SVB_PREC_TF32 && precision <= SVB_PREC_BF16X3, SVB_ERR_INVALID, "tc conv: bad precision %d",
-              precision);
-    TcArgs p;
-    p.a = a, p.w = reinterpret_cast<const unsigned char *>(w.blob[precision]);
-    const int cin_eff = a.cin_blk > 0 ? a.cin_blk : a.Cin;     // input channels one column block contracts over
-    p.n_tile = w.n_tile, p.n_chunks = (cin_eff + kTcCK - 1) / kTcCK;
-    p.blk_chunk_step = a.cin_blk > 0 ? p.n_chunks : 0;
-    const int halo = (a.KS - 1) / 2 * a.dil;
-    const int tiles = (a.Tq + kTcM - 1) / kTcM;              // 128-row tiles per clip
-    p.col_blocks = a.CoutP / p.n_tile;
+// Shape-class plan of one launch: M tiles per item, operand slots, weight ring / residency, TMEM columns and the
+// shared-memory carve-up.  `a[0..n)` are layers of the same shape class (channels, rows, upsampling) that may
+// differ in taps / dilation / pointers; slots are sized for the largest halo.
+static int tc_plan(int n, const TcWeights *const *w, const ConvArgs *a, int precision, TcArgs &p, size_t &smem) {
+    SVB_CHECK(n >= 1 && n <= kTcMaxLayers, SVB_ERR_INVALID, "tc conv: %d layers in one launch", n);
+    const ConvArgs &a0 = a[0];
+    for (int l = 1; l < n; ++l)
+        SVB_CHECK(a[l].B == a0.B && a[l].Cin == a0.Cin && a[l].Cout == a0.Cout && a[l].CoutP == a0.CoutP && a[l].Tq == a0.Tq &&
+                      a[l].in_Tp == a0.in_Tp && a[l].out_Tp == a0.out_Tp && a[l].ups_u == a0.ups_u && a[l].in_slope == a0.in_slope &&
+                      a[l].cin_blk == a0.cin_blk && w[l]->n_tile == w[0]->n_tile,
+                  SVB_ERR_INVALID, "tc conv: layers of one launch must share the shape class");
+    p.a = a0, p.n_layers = n;
+    p.work = nullptr, p.work_off = nullptr;
+    const int cin_eff = a0.cin_blk > 0 ? a0.cin_blk : a0.Cin;     // input channels one column block contracts over
+    p.n_tile = w[0]->n_tile, p.n_chunks = (cin_eff + kTcCK - 1) / kTcCK;
+    p.blk_chunk_step = a0.cin_blk > 0 ? p.n_chunks : 0;
+    int halo = 0, ks_sum = 0;
+    for (int l = 0; l < n; ++l) halo = std::max(halo, (a[l].KS - 1) / 2 * a[l].dil), ks_sum += a[l].KS;
+    const int tiles = (a0.Tq + kTcM - 1) / kTcM;              // 128-row tiles per clip
+    p.col_blocks = a0.CoutP / p.n_tile;
     const int planes = precision == SVB_PREC_TF32X3 ? 2 : 1;
     p.wtile_bytes = (uint32_t)p.n_tile * 128 * planes;
     p.dbg = 0;
@@ -689,75 +759,90 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     if (const char *e = getenv("SVB_TC_PDL")) p.pdl = atoi(e) != 0;
     int force_mt = 0;
     if (const char *e = getenv("SVB_TC_MT")) force_mt = atoi(e);
-    // ---- M tiles per group: each weight tile fetched from L2 feeds MT accumulators.  Two accumulator
+    // ---- M tiles per item: each weight tile fetched from L2 feeds MT accumulators.  Two accumulator
     // sets live in TMEM (2 * MT * N <= 512 columns); slabs and the weight ring must fit shared memory.
-    size_t smem = 0;
-    const size_t bias_bytes = a.Cout <= 1024 ? kBiasBytes : 3 * kBiasBytes;
+    smem = 0;
+    const size_t bias_bytes = (size_t)n * a0.Cout <= 1024 ? kBiasBytes : 3 * kBiasBytes;
+    SVB_CHECK((size_t)n * a0.Cout * 4 <= bias_bytes, SVB_ERR_INVALID, "tc conv: %d layers x %d biases exceed the shared-memory bias area", n, a0.Cout);
     const size_t budget = 226 * 1024 - kStageBytes - bias_bytes;
     int force_sets = 0;
     if (const char *e = getenv("SVB_TC_SETS")) force_sets = atoi(e);
-    const long long tile_units = (long long)tiles * p.col_blocks * a.B;
+    bool planned = false;
     for (int MT : {4, 2, 1}) {
         if (force_mt && MT != force_mt && MT != 1) continue;
-        // Two accumulator sets (epilogue overlapped) need 2*MT*N <= 512 TMEM columns.  Wide layers
-        // (N = 128) that are bound by weight streaming from L2 take MT = 4 with ONE set instead:
-        // every weight tile then feeds 512 rows.  Needs enough groups to keep all SMs busy.
         int sets = 2 * MT * p.n_tile <= 512 ? 2 : 1;
         if (force_sets) sets = force_sets;
         if (sets * MT * p.n_tile > 512) continue;
         if (!force_mt) {
             if (MT == 4) continue;      // measured: MT = 4 (one or two accumulator sets) is slower than MT = 2 on every layer
-            (void)tile_units;
             if (MT == 2 && tiles < 2) continue;
         }
         p.n_sets = sets;
-        if ((tiles + MT - 1) / MT * MT * kTcM > round_up(a.Tq, kTileT) && MT != 1) continue;   // stay inside the allocation
+        if ((tiles + MT - 1) / MT * MT * kTcM > round_up(a0.Tq, kTileT) && MT != 1) continue;   // stay inside the allocation
         p.MT = MT;
-        p.R = MT * kTcM + 2 * halo;
-        p.Rp = round_up(p.R, 8);
-        p.raw_bytes = (uint32_t)p.R * 128;
-        p.op_bytes = (uint32_t)p.Rp * 128 * planes;
+        const int R = MT * kTcM + 2 * halo;
+        p.op_bytes = (uint32_t)round_up(R, 8) * 128 * planes;
         // operand slots double as TMA targets: 3 of them keep two slab copies in flight behind the MMAs
         p.nA = 3;
         if (const char *e = getenv("SVB_TC_NA")) p.nA = std::max(2, std::min(4, atoi(e)));
-        p.off_op = 1024;
+        p.off_op = 1024 + kItemBytes;
+        // narrow layers (one chunk, one column block): every layer's tiles stay resident
+        const size_t res_bytes = (size_t)ks_sum * p.wtile_bytes;
+        const bool can_res = p.n_chunks == 1 && p.col_blocks == 1;
+        p.w_resident = 0;
+        for (int nA : {p.nA, 2}) {
+            if (can_res && p.off_op + (size_t)nA * p.op_bytes + res_bytes <= budget) {
+                p.nA = nA, p.w_resident = 1;
+                break;
+            }
+        }
         p.off_w = p.off_op + (uint32_t)p.nA * p.op_bytes;
-        if (p.off_w + 2 * (size_t)p.wtile_bytes > budget) {
+        if (!p.w_resident && p.off_w + 2 * (size_t)p.wtile_bytes > budget) {
             p.nA = 2;
             p.off_w = p.off_op + (uint32_t)p.nA * p.op_bytes;
         }
-        if (p.off_w + 2 * (size_t)p.wtile_bytes > budget && MT != 1) continue;
-        SVB_CHECK(p.off_w + (size_t)p.wtile_bytes <= budget, SVB_ERR_INVALID, "tc conv: tile does not fit shared memory (N %d)",
-                  p.n_tile);
-        // weight stage = as many taps of one chunk as fit in ~48 KB, fetched by a single bulk copy
+        if (!p.w_resident && p.off_w + 2 * (size_t)p.wtile_bytes > budget && MT != 1) continue;
+        SVB_CHECK(p.w_resident || p.off_w + (size_t)p.wtile_bytes <= budget, SVB_ERR_INVALID,
+                  "tc conv: tile does not fit shared memory (N %d)", p.n_tile);
         const size_t avail = budget - p.off_w;
-        // (measured: one bulk copy per tap beats multi-tap stages -- a single large copy streams slowly)
-        int tps = 1;
-        if (const char *e = getenv("SVB_TC_TPS")) tps = std::max(1, std::min(a.KS, atoi(e)));
-        while (tps > 1 && (size_t)tps * p.wtile_bytes * 2 > avail) --tps;
-        if ((size_t)a.KS * p.wtile_bytes <= avail && p.n_chunks == 1 && p.col_blocks == 1) tps = a.KS;   // whole layer fits
-        p.tps = tps;
-        p.n_st = (a.KS + tps - 1) / tps;
-        p.wstage_bytes = (uint32_t)tps * p.wtile_bytes;
-        p.w_resident = (p.n_chunks * p.n_st == 1 && p.col_blocks == 1) ? 1 : 0;
-        int nW = (int)(avail / p.wstage_bytes);
-        nW = std::max(1, std::min(std::min(nW, kMaxW), p.w_resident ? 1 : 1 << 30));
-        p.nW = nW;
-        p.off_stage = p.off_w + (uint32_t)nW * p.wstage_bytes;
+        size_t w_area;
+        if (p.w_resident) {
+            p.nW = 1, p.w_res_bytes = (uint32_t)res_bytes, w_area = res_bytes;
+        } else {
+            p.nW = std::max(1, std::min((int)(avail / p.wtile_bytes), kMaxW));
+            p.w_res_bytes = 0, w_area = (size_t)p.nW * p.wtile_bytes;
+        }
+        p.off_stage = p.off_w + (uint32_t)round_up((int)w_area, 1024);
         p.off_bias = p.off_stage + kStageBytes;
         smem = (size_t)p.off_bias + bias_bytes;
+        planned = true;
         break;
     }
+    SVB_CHECK(planned && smem <= 227 * 1024, SVB_ERR_INVALID, "tc conv: no tiling fits (N %d, %d layers)", p.n_tile, n);
+    uint32_t res_off = 0;
+    for (int l = 0; l < n; ++l) {
+        TcLayer &L = p.L[l];
+        L.in = a[l].in, L.res = a[l].res, L.out = a[l].out, L.bias = a[l].bias;
+        L.w = reinterpret_cast<const unsigned char *>(w[l]->blob[precision]);
+        L.KS = a[l].KS, L.dil = a[l].dil, L.out_scale = a[l].out_scale, L.accumulate = a[l].accumulate;
+        L.bias_off = l * a0.Cout, L.w_res_off = res_off;
+        res_off += (uint32_t)a[l].KS * p.wtile_bytes;
+    }
+    for (int l = n; l < kTcMaxLayers; ++l) p.L[l] = p.L[0];
     if (getenv("SVB_TC_VERBOSE"))
-        fprintf(stderr, "[tc] Cin %d CoutP %d KS %d dil %d Tq %d | n_tile %d MT %d sets %d R %d nA %d tps %d n_st %d nW %d resident %d smem %zu\n",
-                a.Cin, a.CoutP, a.KS, a.dil, a.Tq, p.n_tile, p.MT, p.n_sets, p.R, p.nA, p.tps, p.n_st, p.nW, p.w_resident, smem);
+        fprintf(stderr, "[tc] %d layer(s) Cin %d CoutP %d KS %d.. halo %d Tq %d | n_tile %d MT %d sets %d nA %d nW %d resident %d smem %zu\n", n,
+                a0.Cin, a0.CoutP, a0.KS, halo, a0.Tq, p.n_tile, p.MT, p.n_sets, p.nA, p.nW, p.w_resident, smem);
     int cols = 32;
     while (cols < p.n_sets * p.MT * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
     p.groups_per_b = (tiles + p.MT - 1) / p.MT;
-    p.total_groups = p.groups_per_b * a.B * p.col_blocks;
-    const int grid = std::min(p.total_groups, max_ctas > 0 ? std::min(max_ctas, sm_count()) : sm_count());
+    p.total_groups = p.groups_per_b * a0.B * p.col_blocks;
     p.stats = nullptr;
+    return SVB_OK;
+}
+
+static int tc_dispatch(TcArgs &p, int precision, int grid, size_t smem, cudaStream_t st) {
+    const ConvArgs &a = p.a;
     const bool want_stats = getenv("SVB_TC_STATS") != nullptr;
     if ((want_stats || p.dbg != 0 || !p.collect) && precision == SVB_PREC_BF16X3) {
         // diagnostics: run the instrumented instantiation, wait for it and print where each role was blocked
@@ -773,10 +858,14 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         long long mx[kTcStatSlots] = {};
         for (int c = 0; c < grid; ++c)
             for (int i = 0; i < kTcStatSlots; ++i) mean[i] += (double)h[(size_t)c * kTcStatSlots + i] / grid, mx[i] = std::max(mx[i], h[(size_t)c * kTcStatSlots + i]);
+        long long g_first = h[12], g_last = h[13];
+        for (int c = 0; c < grid; ++c) g_first = std::min(g_first, h[(size_t)c * kTcStatSlots + 12]), g_last = std::max(g_last, h[(size_t)c * kTcStatSlots + 13]);
+        if (want_stats) fprintf(stderr, "[tc-stats] grid span %.1f us (globaltimer, first CTA start -> last CTA end) = %.2f GHz over the mean CTA\n",
+                                (g_last - g_first) / 1e3, mean[11] / std::max(1.0, (double)(g_last - g_first)));
         if (want_stats) fprintf(stderr,
-                "[tc-stats] C%d>%d k%d d%d Tq %d grid %d groups %d MT %d | kcycles mean (max): total %.0f (%.0f) | producer: a_empty %.0f w_empty %.0f of %.0f | "
+                "[tc-stats] %dx C%d>%d k%d d%d Tq %d grid %d groups %d MT %d | kcycles mean (max): total %.0f (%.0f) | producer: a_empty %.0f w_empty %.0f of %.0f | "
                 "mma: acc_empty %.0f a_ready %.0f w_full %.0f of %.0f | transform: raw_full %.0f of %.0f | epilogue: acc_full %.0f of %.0f\n",
-                a.Cin, a.CoutP, a.KS, a.dil, a.Tq, grid, p.total_groups, p.MT, mean[11] / 1e3, mx[11] / 1e3, mean[0] / 1e3, mean[1] / 1e3, mean[2] / 1e3,
+                p.n_layers, a.Cin, a.CoutP, a.KS, a.dil, a.Tq, grid, p.total_groups, p.MT, mean[11] / 1e3, mx[11] / 1e3, mean[0] / 1e3, mean[1] / 1e3, mean[2] / 1e3,
                 mean[3] / 1e3, mean[4] / 1e3, mean[5] / 1e3, mean[6] / 1e3, mean[7] / 1e3, mean[8] / 1e3, mean[9] / 1e3, mean[10] / 1e3);
         return SVB_OK;
     }
@@ -785,6 +874,120 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
         case SVB_PREC_TF32X3: return launch_mode<SVB_PREC_TF32X3, false>(p, grid, smem, st);
         default: return launch_mode<SVB_PREC_BF16X3, false>(p, grid, smem, st);
     }
+}
+
+int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStream_t st, int max_ctas) {
+    SVB_CHECK(precision >= SVB_PREC_TF32 && precision <= SVB_PREC_BF16X3, SVB_ERR_INVALID, "tc conv: bad precision %d",
+              precision);
+    TcArgs p;
+    size_t smem = 0;
+    const TcWeights *wp = &w;
+    SVB_TRY(tc_plan(1, &wp, &a, precision, p, smem));
+    const int grid = std::min(p.total_groups, max_ctas > 0 ? std::min(max_ctas, sm_count()) : sm_count());
+    if ((p.total_groups + grid - 1) / grid > kMaxItems) {
+        // more items per CTA than the shared-memory list holds: run the batch in slices of clips
+        const int per_b = p.groups_per_b * p.col_blocks;
+        const int nb = std::max(1, kMaxItems * grid / per_b);
+        SVB_CHECK(per_b <= kMaxItems * grid, SVB_ERR_INVALID, "tc conv: one clip alone has %d work items", per_b);
+        for (int b0 = 0; b0 < a.B; b0 += nb) {
+            ConvArgs s = a;
+            s.B = std::min(nb, a.B - b0);
+            s.in = a.in + (size_t)b0 * c4t_groups(a.Cin) * a.in_Tp * 32;
+            s.out = a.out + (size_t)b0 * c4t_groups(a.Cout) * a.out_Tp * 32;
+            if (a.res) s.res = a.res + (size_t)b0 * c4t_groups(a.Cout) * a.out_Tp * 32;
+            SVB_TRY(launch_conv_tc(w, s, precision, st, max_ctas));
+        }
+        return SVB_OK;
+    }
+    return tc_dispatch(p, precision, grid, smem, st);
+}
+
+// ---- merged launches: several layers of one shape class, host-built balanced work list
+void tc_worklist_free(TcWorkList *wl) {
+    if (wl->items) cudaFree(wl->items);
+    if (wl->off) cudaFree(wl->off);
+    *wl = TcWorkList();
+}
+
+int tc_worklist_build(int n, const TcWeights *const *w, const ConvArgs *a, int precision, bool chain_ordered, TcWorkList *out) {
+    TcArgs p;
+    size_t smem = 0;
+    SVB_TRY(tc_plan(n, w, a, precision, p, smem));
+    const int grid = sm_count();
+    const int tiles = (a[0].Tq + kTcM - 1) / kTcM;
+    // cost of an item in "taps of one tile": the MMA work plus a constant for the memory-bound part (slab, epilogue)
+    const double beta = 160.0 / std::max(32, a[0].Cin);
+    struct Unit {
+        double cost;
+        int nblk, b, t0, mt, layer;     // layer < 0: all layers in order (chain-ordered unit)
+    };
+    std::vector<Unit> units;
+    for (int nblk = 0; nblk < p.col_blocks; ++nblk)
+        for (int b = 0; b < a[0].B; ++b)
+            for (int t = 0; t < tiles; t += p.MT) {
+                const int mt = std::min(p.MT, tiles - t);
+                if (chain_ordered) {
+                    double c = 0;
+                    for (int l = 0; l < n; ++l) c += mt * (a[l].KS + beta + (a[l].res ? 1.0 : 0.0) + (a[l].accumulate ? 1.0 : 0.0));
+                    units.push_back({c, nblk, b, t * kTcM, mt, -1});
+                } else {
+                    for (int l = 0; l < n; ++l)
+                        units.push_back({mt * (a[l].KS + beta + (a[l].res ? 1.0 : 0.0)), nblk, b, t * kTcM, mt, l});
+                }
+            }
+    // longest processing time first onto the least-loaded CTA
+    std::stable_sort(units.begin(), units.end(), [](const Unit &x, const Unit &y) { return x.cost > y.cost; });
+    std::vector<double> load(grid, 0.0);
+    std::vector<std::vector<int>> mine(grid);
+    for (size_t u = 0; u < units.size(); ++u) {
+        int best = 0;
+        for (int c = 1; c < grid; ++c)
+            if (load[c] < load[best]) best = c;
+        load[best] += units[u].cost;
+        mine[best].push_back((int)u);
+    }
+    std::vector<int4> items;
+    std::vector<int> off(grid + 1, 0);
+    for (int c = 0; c < grid; ++c) {
+        // neighbours in time next to each other (their halos share L2 lines)
+        std::sort(mine[c].begin(), mine[c].end(), [&](int x, int y) {
+            const Unit &X = units[x], &Y = units[y];
+            if (X.layer != Y.layer) return X.layer < Y.layer;
+            if (X.nblk != Y.nblk) return X.nblk < Y.nblk;
+            if (X.b != Y.b) return X.b < Y.b;
+            return X.t0 < Y.t0;
+        });
+        for (int u : mine[c]) {
+            const Unit &U = units[u];
+            for (int l = (U.layer < 0 ? 0 : U.layer); l < (U.layer < 0 ? n : U.layer + 1); ++l)
+                items.push_back(make_int4(l | (U.nblk << 8) | (U.mt << 24), U.b, U.t0, 0));
+        }
+        off[c + 1] = (int)items.size();
+        SVB_CHECK(off[c + 1] - off[c] <= kMaxItems, SVB_ERR_INVALID, "tc conv: %d work items on one CTA (limit %d)", off[c + 1] - off[c], kMaxItems);
+    }
+    tc_worklist_free(out);
+    SVB_CUDA(cudaMalloc((void **)&out->items, std::max<size_t>(items.size(), 1) * sizeof(int4)));
+    SVB_CUDA(cudaMalloc((void **)&out->off, off.size() * sizeof(int)));
+    SVB_CUDA(cudaMemcpy(out->items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    SVB_CUDA(cudaMemcpy(out->off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    out->grid = grid, out->n_items = (int)items.size(), out->MT = p.MT, out->n_layers = n, out->chain_ordered = chain_ordered;
+    if (getenv("SVB_TC_VERBOSE")) {
+        double mx = 0, sum = 0;
+        for (double v : load) mx = std::max(mx, v), sum += v;
+        fprintf(stderr, "[tc] work list: %d layers, %zu items over %d CTAs, balance %.3f (mean / max load)\n", n, items.size(), grid, sum / grid / mx);
+    }
+    return SVB_OK;
+}
+
+int launch_conv_tc_multi(int n, const TcWeights *const *w, const ConvArgs *a, int precision, cudaStream_t st, const TcWorkList &wl) {
+    SVB_CHECK(precision >= SVB_PREC_TF32 && precision <= SVB_PREC_BF16X3, SVB_ERR_INVALID, "tc conv: bad precision %d", precision);
+    TcArgs p;
+    size_t smem = 0;
+    SVB_TRY(tc_plan(n, w, a, precision, p, smem));
+    SVB_CHECK(wl.items && wl.n_layers == n && wl.MT == p.MT && wl.grid == sm_count(), SVB_ERR_STATE,
+              "tc conv: work list was built for another plan (layers %d / %d, MT %d / %d)", wl.n_layers, n, wl.MT, p.MT);
+    p.work = wl.items, p.work_off = wl.off;
+    return tc_dispatch(p, precision, wl.grid, smem, st);
 }
 
 }  // namespace svb

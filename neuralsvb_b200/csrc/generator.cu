@@ -152,6 +152,38 @@ int run_conv(svb_gen *g, const ConvLayer &L, const float *in, int in_Tp, float *
     return launch_conv_ffma(a, st);
 }
 
+// One merged launch over the nk layers `Ls` (same shape class): layer j reads in[j], writes out[j], adds res[j].
+// chain_ordered: later layers accumulate into the output of earlier ones (the ResBlock sum), see TcWorkList.
+int run_conv_multi(svb_gen *g, int stage, int nk, const ConvLayer *const *Ls, const float *const *in, float *const *out,
+                   const float *const *res, const float *scale, const int *accumulate, bool chain_ordered, int B, int Tq, int Tp,
+                   float in_slope, cudaStream_t st) {
+    ConvArgs a[kTcMaxLayers];
+    const TcWeights *w[kTcMaxLayers];
+    double bytes = 0, flops = 0;
+    for (int j = 0; j < nk; ++j) {
+        const ConvLayer &L = *Ls[j];
+        a[j].in = in[j], a[j].w = L.w, a[j].bias = L.b, a[j].res = res[j], a[j].out = out[j];
+        a[j].B = B, a[j].Cin = L.Cin, a[j].in_Tp = Tp, a[j].Cout = L.Cout, a[j].out_Tp = Tp, a[j].CoutP = L.CoutP, a[j].Tq = Tq;
+        a[j].KS = L.KS, a[j].dil = L.dil, a[j].ups_u = 0, a[j].in_slope = in_slope, a[j].out_scale = scale[j], a[j].accumulate = accumulate[j];
+        w[j] = &L.tc;
+        bytes += 4.0 * ((double)B * Tq * L.Cin + (double)B * Tq * L.Cout * (1 + (res[j] ? 1 : 0) + (accumulate[j] ? 1 : 0)));
+        flops += 2.0 * L.macs_per_row * (double)B * Tq;
+    }
+    g->last_launches += 1;
+    g->last_flops += flops;
+    ProfScope ps(g, st, "conv1d_c4_tc (resblock)", bytes, flops);
+    // the list depends on the plan (MT) of this layer set: try the cached one, rebuild on a plan mismatch
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int key = stage * 4 + (chain_ordered ? 2 : 0) + attempt;
+        TcWorkList &wl = g->worklists[key];
+        if (!wl.items) SVB_TRY(tc_worklist_build(nk, w, a, g->cfg.precision, chain_ordered, &wl));
+        const int rc = launch_conv_tc_multi(nk, w, a, g->cfg.precision, st, wl);
+        if (rc != SVB_ERR_STATE) return rc;
+    }
+    set_error("merged launch: no cached work list matches the plan of stage %d", stage);
+    return SVB_ERR_STATE;
+}
+
 int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float *f0, const float *rand_ini,
                  const float *noise, uint64_t seed, int B, int T, float *wav, cudaStream_t st) {
     SVB_CHECK(g && g->finalized, SVB_ERR_STATE, "generator: forward before finalize");
@@ -168,6 +200,10 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         g->ws = nullptr, g->ws_cap = 0;
         SVB_CUDA(cudaMalloc((void **)&g->ws, need));
         g->ws_cap = need, g->ws_B = 0;
+    }
+    if (g->ws_B != B || g->ws_T != T) {
+        for (auto &kv : g->worklists) tc_worklist_free(&kv.second);
+        g->worklists.clear();
     }
     if (g->ws_B != B || g->ws_T != T || g->ws_training != g->training) {   // new layout: rebuild the zero padding of every buffer
         SVB_CUDA(cudaMemsetAsync(g->ws, 0, need, st));
@@ -240,8 +276,47 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         // into S) are ordered by events.
         const bool par = g->chains > 1 && nk > 1 && nk <= 3 && g->cfg.precision != SVB_PREC_FP32 && !g->profile;
         const int sms = 148;
+        // merged schedule: step m of all nk chains in ONE persistent launch (the chains only share their input)
+        bool merged = g->merge && !par && nk > 1 && nk <= kTcMaxLayers && g->cfg.precision != SVB_PREC_FP32;
+        for (int j = 0; merged && j < nk; ++j)
+            for (int m = 0; m < nd; ++m) {
+                ConvArgs probe;
+                probe.Cin = s.C, probe.Cout = s.C, probe.CoutP = s.C, probe.KS = s.c1[j][m].KS, probe.dil = s.c1[j][m].dil, probe.ups_u = 0;
+                probe.bias = s.c1[j][m].b, probe.cin_blk = 0;
+                merged = merged && tc_supported(s.c1[j][m].tc, probe) && s.c1[j][m].tc.n_tile == s.c1[0][0].tc.n_tile;
+                if (g->cfg.resblock == 1) merged = merged && s.c2[j][m].tc.ok && s.c2[j][m].tc.n_tile == s.c1[0][0].tc.n_tile;
+            }
+        if (merged) {
+            for (int m = 0; m < nd; ++m) {
+                const bool last = m == nd - 1;
+                const ConvLayer *L1[kTcMaxLayers], *L2[kTcMaxLayers];
+                const float *xin[kTcMaxLayers], *ain[kTcMaxLayers], *none[kTcMaxLayers];
+                float *aout[kTcMaxLayers], *dst[kTcMaxLayers];
+                float one[kTcMaxLayers], scl[kTcMaxLayers];
+                int zero[kTcMaxLayers], acc[kTcMaxLayers];
+                for (int j = 0; j < nk; ++j) {
+                    L1[j] = &s.c1[j][m], none[j] = nullptr, one[j] = 1.f, zero[j] = 0;
+                    scl[j] = last ? 1.f / nk : 1.f, acc[j] = (last && j > 0) ? 1 : 0;
+                    if (g->cfg.resblock == 1) {                 // ResBlock1.forward :54-61
+                        L2[j] = &s.c2[j][m];
+                        xin[j] = m == 0 ? X : F(bf.R[i][j][m - 1]);
+                        aout[j] = F(bf.A[i][j][m]), ain[j] = aout[j];
+                        dst[j] = last ? S : F(bf.R[i][j][m]);
+                    } else {                                    // ResBlock2.forward :81-86 (never in place: ping-pong A / R)
+                        xin[j] = m == 0 ? X : (m % 2 ? F(bf.R[i][j][m - 1]) : F(bf.A[i][j][m - 1]));
+                        dst[j] = last ? S : (m % 2 ? F(bf.A[i][j][m]) : F(bf.R[i][j][m]));
+                    }
+                }
+                if (g->cfg.resblock == 1) {
+                    SVB_TRY(run_conv_multi(g, (int)i, nk, L1, xin, aout, none, one, zero, false, B, Ti, Tip, 0.1f, st));
+                    SVB_TRY(run_conv_multi(g, (int)i, nk, L2, ain, dst, xin, scl, acc, last, B, Ti, Tip, 0.1f, st));
+                } else {
+                    SVB_TRY(run_conv_multi(g, (int)i, nk, L1, xin, dst, xin, scl, acc, last, B, Ti, Tip, 0.1f, st));
+                }
+            }
+        }
         if (par) SVB_CUDA(cudaEventRecord(g->ev_fork, st));
-        for (int j = 0; j < nk; ++j) {
+        for (int j = 0; j < nk && !merged; ++j) {
             cudaStream_t cs = par ? g->side[j] : st;
             // SM share of a chain ~ its cost: kernel size plus a constant for the memory-bound part
             int cap = 0;
@@ -253,6 +328,7 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
                     if (jj == j) wj = wv;
                 }
                 cap = std::max(8, (int)(sms * wj / wsum + 0.5));
+                if (g->chains == 2) cap = 0;    // full grids on every stream: the block scheduler interleaves the chains' CTAs
             }
             if (par) SVB_CUDA(cudaStreamWaitEvent(cs, g->ev_fork, 0));
             for (int m = 0; m < nd; ++m) {
@@ -333,6 +409,7 @@ extern "C" int svb_gen_create(const svb_gen_config *cfg, int device, svb_gen_t *
         SVB_CUDA(cudaEventCreateWithFlags(&g->ev_chain[i], cudaEventDisableTiming));
     }
     if (const char *e = getenv("SVB_CHAINS")) g->chains = atoi(e);
+    if (const char *e = getenv("SVB_MERGE")) g->merge = atoi(e) != 0;
     if (const char *e = getenv("SVB_CHAIN_BIAS")) g->chain_bias = atof(e);
     *out = g;
     return SVB_OK;
@@ -342,6 +419,7 @@ extern "C" void svb_gen_destroy(svb_gen_t *g) {
     if (!g) return;
     cudaSetDevice(g->device);
     for (void *p : g->dev_allocs) cudaFree(p);
+    for (auto &kv : g->worklists) tc_worklist_free(&kv.second);
     if (g->ws) cudaFree(g->ws);
     if (g->bws) cudaFree(g->bws);
     for (void *p : g->job_allocs) cudaFree(p);

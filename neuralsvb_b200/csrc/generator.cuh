@@ -138,6 +138,11 @@ struct svb_gen {
     int chains = 1;     // measured on B200: side-by-side chains on SM subsets are SLOWER (7.0 vs 5.7 ms/step); kept for experiments
     double chain_bias = 4.0;
 
+    // merged launches: the ResBlock chains of a stage step together in one persistent launch (conv_tc.cuh: TcWorkList).
+    // Lists depend on the stage, the batch / length and the plan's MT; cached per (stage, chain_ordered, MT).
+    bool merge = true;              // SVB_MERGE=0: one launch per convolution (round-1 schedule)
+    std::map<int, svb::TcWorkList> worklists;
+
     bool profile = false;
     std::vector<LaunchRec> recs;
     std::vector<cudaEvent_t> ev_pool;
