@@ -181,6 +181,54 @@ static int launch_gconv(const GConvArgs &a, cudaStream_t st) {
     return SVB_OK;
 }
 
+// Few output channels over many input channels (the discriminators' conv_post: 1024 -> 1, k 3): gconv_kernel would walk
+// the 1024 input channels serially inside a handful of blocks (0.7 ms per launch, latency bound).  Here a block is 32
+// consecutive outputs of the FLATTENED (t, w) plane x 8 channel slices: the (k, 1) kernel is a dilated 1-D conv over
+// that plane (tap offset (k - pad) * W), so every load is a coalesced 128-byte line; partial sums meet in shared memory.
+template <int CO>
+__global__ void __launch_bounds__(256) conv_fewout_kernel(GConvArgs a) {
+    __shared__ float red[8][CO][32];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int b = blockIdx.y, n_out = a.Tout * a.W;
+    const int e = blockIdx.x * 32 + lane;
+    const int to = e / a.W, wcol = e - to * a.W;
+    float acc[CO];
+#pragma unroll
+    for (int i = 0; i < CO; ++i) acc[i] = 0.f;
+    if (e < n_out) {
+        for (int c = wrp; c < a.Cin; c += 8) {
+            const float *xc = a.x + ((size_t)b * a.Cin + c) * a.Tin * a.W + wcol;
+            for (int k = 0; k < a.K; ++k) {
+                const int t = to - a.pad + k * a.dil;
+                if (t < 0 || t >= a.Tin) continue;
+                const float xv = __ldg(xc + (size_t)t * a.W);
+#pragma unroll
+                for (int i = 0; i < CO; ++i) acc[i] = fmaf(__ldg(a.w + ((size_t)i * a.Cin + c) * a.K + k), xv, acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CO; ++i) red[wrp][i][lane] = acc[i];
+    __syncthreads();
+    if (wrp == 0 && e < n_out) {
+#pragma unroll
+        for (int i = 0; i < CO; ++i) {
+            float v = a.bias ? __ldg(a.bias + i) : 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v += red[q][i][lane];
+            a.y[((size_t)b * a.Cout + i) * n_out + e] = lrelu(v, a.out_slope);
+        }
+    }
+}
+
+template <int CO>
+static int launch_fewout(const GConvArgs &a, cudaStream_t st) {
+    const dim3 grid((a.Tout * a.W + 31) / 32, a.B);
+    conv_fewout_kernel<CO><<<grid, 256, 0, st>>>(a);
+    SVB_CUDA(cudaGetLastError());
+    return SVB_OK;
+}
+
 extern "C" int svb_conv_nct_forward(const float *x_dev, const float *w_dev, const float *bias_dev, float *y_dev, int32_t B,
                                     int32_t Cin, int32_t Cout, int32_t Tin, int32_t W, int32_t K, int32_t stride, int32_t dil,
                                     int32_t pad, int32_t groups, float out_slope, void *stream) {
@@ -194,6 +242,7 @@ extern "C" int svb_conv_nct_forward(const float *x_dev, const float *w_dev, cons
     a.Tout = (Tin + 2 * pad - dil * (K - 1) - 1) / stride + 1;
     SVB_CHECK(a.Tout > 0, SVB_ERR_INVALID, "conv_nct: empty output (Tin %d K %d)", Tin, K);
     const int cout_g = Cout / groups;
+    if (groups == 1 && stride == 1 && Cin >= 64 && Cout <= 2) return Cout == 1 ? launch_fewout<1>(a, as_stream(stream)) : launch_fewout<2>(a, as_stream(stream));
     if (cout_g <= 8) return launch_gconv<2>(a, as_stream(stream));
     if (cout_g <= 16) return launch_gconv<4>(a, as_stream(stream));
     if (cout_g <= 32) return launch_gconv<8>(a, as_stream(stream));

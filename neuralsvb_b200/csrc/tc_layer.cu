@@ -21,71 +21,83 @@ namespace {
 
 // out (G32T: clips = B*W, Ce = C*KE channels, Tq rows, EVERY row of the allocation written so a shared arena needs
 // no memset): out[clip][(c*KE + j)][to] = x[b][c][to*s + j - p][w] * (mask ? lrelu'(mask) : 1)
-__global__ void expand_to_g32t_kernel(const float *__restrict__ x, const float *__restrict__ mask, float slope, int B, int C,
-                                      int T, int W, int KE, int s, int p, int Tq, int Tp, float *__restrict__ out) {
-    const int Ce = C * KE, groups = c4t_groups(Ce);
-    const long long total = (long long)B * W * groups * Tp * 32;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int lane = (int)(i & 31);
-        long long r = i >> 5;
-        const int row = (int)(r % Tp);
-        r /= Tp;
-        const int grp = (int)(r % groups), clip = (int)(r / groups);
-        const int to = row - kPad, cc = grp * 32 + lane;
+// grid (row blocks, channel groups, clips); a warp writes one 128-byte row per step, a thread keeps its (channel, tap):
+// no per-element index division, the gathered input lines are re-read from L1 by the neighbouring rows of the block.
+constexpr int kExpRows = 64;
+__global__ void __launch_bounds__(256) expand_to_g32t_kernel(const float *__restrict__ x, const float *__restrict__ mask, float slope, int C,
+                                                             int T, int W, int KE, int s, int p, int Tq, int Tp, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int grp = blockIdx.y, clip = blockIdx.z, groups = gridDim.y;
+    const int cc = grp * 32 + lane;
+    const int c = cc / KE, j = cc - c * KE;
+    const bool ch_ok = cc < C * KE;
+    const int b = clip / W, w = clip - b * W;
+    const size_t xoff = ((size_t)b * C + (ch_ok ? c : 0)) * T * W + w;
+    const float *xb = x + xoff;
+    const float *mb = mask ? mask + xoff : nullptr;
+    float *ob = out + ((size_t)clip * groups + grp) * Tp * 32 + lane;
+    const int r1 = min(Tp, (int)(blockIdx.x + 1) * kExpRows);
+    for (int row = blockIdx.x * kExpRows + wrp; row < r1; row += 8) {
+        const int to = row - kPad;
         float v = 0.f;
-        if (to >= 0 && to < Tq && cc < Ce) {
-            const int c = cc / KE, j = cc - c * KE;
+        if (ch_ok && to >= 0 && to < Tq) {
             const int t = to * s + j - p;
             if (t >= 0 && t < T) {
-                const int b = clip / W, w = clip - b * W;
-                const size_t xi = (((size_t)b * C + c) * T + t) * W + w;
-                v = __ldg(x + xi);
-                if (mask && !(__ldg(mask + xi) > 0.f)) v *= slope;
+                v = __ldg(xb + (size_t)t * W);
+                if (mb && !(__ldg(mb + (size_t)t * W) > 0.f)) v *= slope;
             }
         }
-        out[i] = v;
+        ob[(size_t)row * 32] = v;
     }
 }
 
-// y[b][c][t][w] = lrelu(g[clip][c][t], slope)
-__global__ void g32t_to_nctw_kernel(const float *__restrict__ g, int B, int C, int T, int W, int Tp, float slope,
-                                    float *__restrict__ y, int row0) {
-    const int groups = c4t_groups(C);
-    const long long total = (long long)B * C * T * W;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(i % W);
-        long long r = i / W;
-        const int t = (int)(r % T);
-        r /= T;
-        const int c = (int)(r % C), b = (int)(r / C);
-        const float v = g[((((size_t)b * W + w) * groups + (c >> 5)) * Tp + kPad + row0 + t) * 32 + (c & 31)];
-        y[i] = v >= 0.f ? v : v * slope;
+// y[b][c][t][w] = lrelu(g[clip][c][row0 + t], slope).  One block = (32 rows, one 32-channel group, one b, ALL w): the rows
+// come in as whole 128-byte lines into a padded smem tile, every channel then leaves as one contiguous run of 32*W floats.
+constexpr int kMaxTileW = 11;       // MPD periods 2..11; wider W fall back to W slices of this size
+__global__ void __launch_bounds__(256) g32t_to_nctw_kernel(const float *__restrict__ g, int C, int T, int W, int Tp, float slope,
+                                                           float *__restrict__ y, int row0, int w0, int wn) {
+    __shared__ float tile[kMaxTileW][32][33];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int t0 = blockIdx.x * 32, grp = blockIdx.y, b = blockIdx.z, groups = gridDim.y;
+    for (int idx = wrp; idx < wn * 32; idx += 8) {          // (w, row) pairs: one coalesced 128-byte line each
+        const int wi = idx >> 5, tr = idx & 31;
+        float v = 0.f;
+        if (t0 + tr < T) v = g[((((size_t)b * W + w0 + wi) * groups + grp) * Tp + kPad + row0 + t0 + tr) * 32 + lane];
+        tile[wi][tr][lane] = v >= 0.f ? v : v * slope;
+    }
+    __syncthreads();
+    const int nt = min(32, T - t0), run = nt * wn;
+    for (int ci = wrp; ci < 32; ci += 8) {
+        const int c = grp * 32 + ci;
+        if (c >= C) break;
+        float *yb = y + (((size_t)b * C + c) * T + t0) * W;
+        for (int e = lane; e < run; e += 32) {
+            const int tr = e / wn, wi = e - tr * wn;
+            yb[(size_t)tr * W + w0 + wi] = tile[wi][tr][ci];
+        }
     }
 }
 
 // dx[b][c][t][w] = sum_j [ (t + p - j) % s == 0 ] g[clip][c*KE + j][(t + p - j) / s]
-__global__ void col2im_to_nctw_kernel(const float *__restrict__ g, int B, int C, int T, int W, int KE, int s, int p, int Tq,
-                                      int Tp, float *__restrict__ dx) {
+// grid (t blocks, C, B): a thread owns consecutive (t, w) of one channel plane; the tap loop visits only taps with
+// (t + p - j) % s == 0.  All index math is 32-bit.
+__global__ void __launch_bounds__(256) col2im_to_nctw_kernel(const float *__restrict__ g, int C, int T, int W, int KE, int s, int p, int Tq,
+                                                             int Tp, float *__restrict__ dx) {
+    const int c = blockIdx.y, b = blockIdx.z;
     const int groups = c4t_groups(C * KE);
-    const long long total = (long long)B * C * T * W;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(i % W);
-        long long r = i / W;
-        const int t = (int)(r % T);
-        r /= T;
-        const int c = (int)(r % C), b = (int)(r / C);
-        const size_t base = ((size_t)b * W + w) * groups;
-        float acc = 0.f;
-        for (int j = 0; j < KE; ++j) {
-            const int num = t + p - j;
-            if (num < 0) break;
-            const int to = num / s;
-            if (to * s != num || to >= Tq) continue;
-            const int cc = c * KE + j;
-            acc += g[((base + (cc >> 5)) * Tp + kPad + to) * 32 + (cc & 31)];
-        }
-        dx[i] = acc;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= T * W) return;
+    const int t = e / W, w = e - t * W;
+    const size_t base = ((size_t)b * W + w) * groups;
+    float acc = 0.f;
+    const int num0 = t + p;
+    for (int j = num0 % s; j < KE && j <= num0; j += s) {
+        const int to = (num0 - j) / s;
+        if (to >= Tq) continue;
+        const int cc = c * KE + j;
+        acc += g[((base + (cc >> 5)) * Tp + kPad + to) * 32 + (cc & 31)];
     }
+    dx[(((size_t)b * C + c) * T) * W + e] = acc;
 }
 
 __global__ void gather_w_kernel(float *__restrict__ dst, const float *__restrict__ nat, const int *__restrict__ idx, size_t n) {
@@ -116,6 +128,21 @@ int arena_get(int device, size_t bytes, char **out) {
 }
 
 int blocks_for(long long total) { return (int)std::min<long long>((total + 255) / 256, 148 * 32); }
+
+void launch_expand(const float *x, const float *mask, float slope, int B, int C, int T, int W, int KE, int s, int p, int Tq, int Tp,
+                   float *out, cudaStream_t st) {
+    const dim3 grid((Tp + kExpRows - 1) / kExpRows, c4t_groups(C * KE), B * W);
+    expand_to_g32t_kernel<<<grid, 256, 0, st>>>(x, mask, slope, C, T, W, KE, s, p, Tq, Tp, out);
+}
+void launch_g32t_to_nctw(const float *g, int B, int C, int T, int W, int Tp, float slope, float *y, int row0, cudaStream_t st) {
+    const dim3 grid((T + 31) / 32, c4t_groups(C), B);
+    for (int w0 = 0; w0 < W; w0 += kMaxTileW)
+        g32t_to_nctw_kernel<<<grid, 256, 0, st>>>(g, C, T, W, Tp, slope, y, row0, w0, std::min(kMaxTileW, W - w0));
+}
+void launch_col2im(const float *g, int B, int C, int T, int W, int KE, int s, int p, int Tq, int Tp, float *dx, cudaStream_t st) {
+    const dim3 grid((T * W + 255) / 256, C, B);
+    col2im_to_nctw_kernel<<<grid, 256, 0, st>>>(g, C, T, W, KE, s, p, Tq, Tp, dx);
+}
 
 }  // namespace
 
@@ -335,9 +362,9 @@ extern "C" int svb_tc_layer_forward(svb_tc_layer_t *L, const float *x_dev, int32
         char *base;
         SVB_TRY(arena_get(L->device, (n_x + n_y) * 4, &base));
         float *xe = reinterpret_cast<float *>(base), *yg = xe + n_x;
-        expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, xe);
+        launch_expand(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, xe, st);
         SVB_TRY(run_tc(L, L->fwd, xe, yg, Tp, clips, Tr, st, L->cin_blk_f));
-        g32t_to_nctw_kernel<<<blocks_for((long long)B * L->Cout * To * W), 256, 0, st>>>(yg, B, L->Cout, To, W, Tp, out_slope, y_dev, L->halo);
+        launch_g32t_to_nctw(yg, B, L->Cout, To, W, Tp, out_slope, y_dev, L->halo, st);
         SVB_CUDA(cudaGetLastError());
         return SVB_OK;
     }
@@ -348,10 +375,10 @@ extern "C" int svb_tc_layer_forward(svb_tc_layer_t *L, const float *x_dev, int32
     char *base;
     SVB_TRY(arena_get(L->device, (n_x + n_y) * 4, &base));
     float *xe = reinterpret_cast<float *>(base), *yg = xe + n_x;
-    expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, gather_pad,
-                                                                         Tq, Tp, xe);
+    launch_expand(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, gather_pad,
+                                                                         Tq, Tp, xe, st);
     SVB_TRY(run_tc(L, L->fwd, xe, yg, Tp, clips, Tq, st));
-    g32t_to_nctw_kernel<<<blocks_for((long long)B * L->Cout * Tq * W), 256, 0, st>>>(yg, B, L->Cout, Tq, W, Tp, out_slope, y_dev, 0);
+    launch_g32t_to_nctw(yg, B, L->Cout, Tq, W, Tp, out_slope, y_dev, 0, st);
     SVB_CUDA(cudaGetLastError());
     return SVB_OK;
 }
@@ -370,11 +397,11 @@ extern "C" int svb_tc_layer_backward(svb_tc_layer_t *L, const float *x_dev, cons
         SVB_TRY(arena_get(L->device, (2 * n_x + n_y) * 4, &base));
         float *xe = reinterpret_cast<float *>(base), *dxe = xe + n_x, *dzg = dxe + n_x;
         // masked output gradient at rows [halo, halo + To) of the T'-row signal, zeros elsewhere
-        expand_to_g32t_kernel<<<blocks_for((long long)n_y), 256, 0, st>>>(dy_dev, out_slope == 1.f ? nullptr : y_dev, out_slope, B, L->Cout,
-                                                                             To, W, 1, 1, L->halo, Tr, Tp, dzg);
+        launch_expand(dy_dev, out_slope == 1.f ? nullptr : y_dev, out_slope, B, L->Cout,
+                                                                             To, W, 1, 1, L->halo, Tr, Tp, dzg, st);
         if (db_dev) SVB_TRY(launch_colsum(dzg, clips, L->Cout, Tr, Tp, db_dev, st));
         if (dw_dev) {
-            expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, xe);
+            launch_expand(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, xe, st);
             WgradArgs a;
             a.A = xe, a.G = dzg, a.out = dw_dev, a.B = clips, a.Tq = Tr, a.Ca = Ce, a.TpA = Tp, a.Cg = L->Cout, a.TpG = Tp, a.K = L->KSp;
             a.sa = 1, a.da = 1, a.pa = L->halo, a.sb = 1, a.db = 0, a.pb = 0, a.slope = 1.f;
@@ -385,7 +412,7 @@ extern "C" int svb_tc_layer_backward(svb_tc_layer_t *L, const float *x_dev, cons
         }
         if (dx_dev) {
             SVB_TRY(run_tc(L, L->bwd, dzg, dxe, Tp, clips, Tr, st, L->cin_blk_b));
-            col2im_to_nctw_kernel<<<blocks_for((long long)B * L->Cin * T * W), 256, 0, st>>>(dxe, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, dx_dev);
+            launch_col2im(dxe, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tr, Tp, dx_dev, st);
         }
         SVB_CUDA(cudaGetLastError());
         return SVB_OK;
@@ -397,12 +424,12 @@ extern "C" int svb_tc_layer_backward(svb_tc_layer_t *L, const float *x_dev, cons
     SVB_TRY(arena_get(L->device, (2 * n_x + n_y) * 4, &base));
     float *xe = reinterpret_cast<float *>(base), *dxe = xe + n_x, *dzg = dxe + n_x;
     // masked output gradient in G32T (KE = 1 gather of dy, leaky-relu derivative from the stored output)
-    expand_to_g32t_kernel<<<blocks_for((long long)n_y), 256, 0, st>>>(dy_dev, out_slope == 1.f ? nullptr : y_dev, out_slope, B, L->Cout,
-                                                                         Tq, W, 1, 1, 0, Tq, Tp, dzg);
+    launch_expand(dy_dev, out_slope == 1.f ? nullptr : y_dev, out_slope, B, L->Cout,
+                                                                         Tq, W, 1, 1, 0, Tq, Tp, dzg, st);
     if (db_dev) SVB_TRY(launch_colsum(dzg, clips, L->Cout, Tq, Tp, db_dev, st));
     if (dw_dev) {
-        expand_to_g32t_kernel<<<blocks_for((long long)n_x), 256, 0, st>>>(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, gather_pad,
-                                                                             Tq, Tp, xe);
+        launch_expand(x_dev, nullptr, 1.f, B, L->Cin, T, W, L->KE, L->stride, gather_pad,
+                                                                             Tq, Tp, xe, st);
         const int KS = L->fwd.KS;
         WgradArgs a;
         a.A = xe, a.G = dzg, a.out = dw_dev, a.B = clips, a.Tq = Tq, a.Ca = Ce, a.TpA = Tp, a.Cg = L->Cout, a.TpG = Tp, a.K = KS;
@@ -414,8 +441,8 @@ extern "C" int svb_tc_layer_backward(svb_tc_layer_t *L, const float *x_dev, cons
     if (dx_dev) {
         SVB_TRY(run_tc(L, L->bwd, dzg, dxe, Tp, clips, Tq, st));
         const long long total = (long long)B * L->Cin * T * W;
-        if (L->stride == 1) g32t_to_nctw_kernel<<<blocks_for(total), 256, 0, st>>>(dxe, B, L->Cin, T, W, Tp, 1.f, dx_dev, 0);
-        else col2im_to_nctw_kernel<<<blocks_for(total), 256, 0, st>>>(dxe, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tq, Tp, dx_dev);
+        if (L->stride == 1) launch_g32t_to_nctw(dxe, B, L->Cin, T, W, Tp, 1.f, dx_dev, 0, st);
+        else launch_col2im(dxe, B, L->Cin, T, W, L->KE, L->stride, L->pad, Tq, Tp, dx_dev, st);
     }
     SVB_CUDA(cudaGetLastError());
     return SVB_OK;
