@@ -328,6 +328,23 @@ int64_t svb_wav2spec_batch_host(const svb_stft_config *cfg, const float *wav_con
                                 int32_t n_clips, const float *mel_basis_host, float *mel_concat_host, int64_t *frames_out,
                                 int device, void *stream);
 
+/* ---- SVB acoustic step, first piece: the WN gated dilated-conv stack of the GlobalFVAE
+ * (modules/fastspeech/fs2_vae.py:19-91; built by modules/voice_conversion/vae_models.py:81-146 with hidden 192,
+ * kernel 5, dilation_rate 1, 4 decoder / 8 encoder layers).  Inference (eval mode: dropout is the identity).
+ * Weights are the FOLDED ones (WN.remove_weight_norm, fs2_vae.py:96-103), set by the reference's state_dict names:
+ *   in_layers.{i}.weight [2H, H, K] / .bias [2H];  res_skip_layers.{i}.weight [2H (H on the last layer), H, 1] / .bias;
+ *   cond_layer.weight [2*H*n_layers, gin, 1] / .bias  (when gin_channels > 0). */
+typedef struct svb_wn svb_wn_t;
+int svb_wn_create(int32_t hidden_channels, int32_t kernel_size, int32_t dilation_rate, int32_t n_layers, int32_t gin_channels,
+                  int32_t precision, int32_t device, svb_wn_t **out);
+void svb_wn_destroy(svb_wn_t *w);
+int svb_wn_set_weight(svb_wn_t *w, const char *name, const float *data_host, const int64_t *shape, int32_t ndim);
+int svb_wn_finalize(svb_wn_t *w);
+/* WN.forward(x, x_mask, g) (fs2_vae.py:62-94) on device tensors in the reference's layout: x [B, H, T], mask [B, T]
+ * (x_mask[:, 0, :], NULL = all ones), g [B, gin, T] (NULL = unconditioned) -> out [B, H, T]. */
+int svb_wn_forward(svb_wn_t *w, const float *x_dev, const float *mask_dev, const float *g_dev, int32_t B, int32_t T, float *out_dev,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,119 @@
+"""WN gated dilated-conv stack of the GlobalFVAE -- first piece of the SVB acoustic step.
+
+Mirror of the reference class ``modules/fastspeech/fs2_vae.py:19-103`` (same constructor, ``state_dict`` names with
+the weight-norm ``weight_g`` / ``weight_v`` pairs, ``remove_weight_norm``, ``forward(x, x_mask, g)``); the module only
+holds parameters, the arithmetic is ``libsvb_vocoder.so`` (``svb_wn_*``, csrc/wn.cu: three tcgen05 convolutions per
+layer plus the gate / residual-skip kernels).  Inference only (eval mode, no autograd): the acoustic model's training
+step is not part of this package yet.
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from neuralsvb_b200 import _native
+
+
+class _WNConv(nn.Module):
+    """Parameter holder with the names ``torch.nn.utils.weight_norm(Conv1d)`` gives: bias, weight_g, weight_v."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(cout))
+        self.weight_g = nn.Parameter(torch.ones(cout, 1, 1))
+        self.weight_v = nn.Parameter(torch.randn(cout, cin, k) * 0.01)
+        self.weight = None                      # set by remove_weight_norm
+
+    def folded(self):
+        if self.weight is not None:
+            return self.weight
+        return torch._weight_norm(self.weight_v, self.weight_g, 0)
+
+    def remove_weight_norm(self):
+        if self.weight is None:
+            w = self.folded().detach()
+            del self.weight_g, self.weight_v
+            self.weight = nn.Parameter(w)
+
+
+class WN(nn.Module):
+    def __init__(self, hidden_channels, kernel_size, dilation_rate, n_layers, gin_channels=0, p_dropout=0,
+                 share_cond_layers=False, is_BTC=False, precision='bf16x3'):
+        super().__init__()
+        assert kernel_size % 2 == 1 and hidden_channels % 2 == 0          # fs2_vae.py:25-26
+        if share_cond_layers:
+            raise NotImplementedError('WN(share_cond_layers=True): the shared cond layer lives outside this module '
+                                      '(glow-style use); the FVAE path of SURVEY 8(f) does not use it')
+        self.is_BTC, self.hidden_channels, self.kernel_size = is_BTC, hidden_channels, kernel_size
+        self.dilation_rate, self.n_layers, self.gin_channels, self.p_dropout = dilation_rate, n_layers, gin_channels, p_dropout
+        self.share_cond_layers, self.precision = share_cond_layers, precision
+        if gin_channels:
+            self.cond_layer = _WNConv(gin_channels, 2 * hidden_channels * n_layers, 1)
+        self.in_layers = nn.ModuleList(_WNConv(hidden_channels, 2 * hidden_channels, kernel_size) for _ in range(n_layers))
+        self.res_skip_layers = nn.ModuleList(
+            _WNConv(hidden_channels, 2 * hidden_channels if i < n_layers - 1 else hidden_channels, 1) for i in range(n_layers))
+        self._handle, self._versions = None, None
+
+    def remove_weight_norm(self):
+        for m in self.modules():
+            if isinstance(m, _WNConv):
+                m.remove_weight_norm()
+
+    def _convs(self):
+        out = [(f'in_layers.{i}', m) for i, m in enumerate(self.in_layers)]
+        out += [(f'res_skip_layers.{i}', m) for i, m in enumerate(self.res_skip_layers)]
+        if self.gin_channels:
+            out.append(('cond_layer', self.cond_layer))
+        return out
+
+    def _native_handle(self, device):
+        versions = tuple(p._version for p in self.parameters()) + (str(device),)
+        if self._handle is not None and versions == self._versions:
+            return self._handle
+        self._free()
+        lib = _native.lib()
+        h = ctypes.c_void_p()
+        _native.check(lib.svb_wn_create(self.hidden_channels, self.kernel_size, self.dilation_rate, self.n_layers, self.gin_channels,
+                                        _native.PREC[self.precision], device.index or 0, ctypes.byref(h)), 'wn_create')
+        for name, m in self._convs():
+            for suffix, t in (('weight', m.folded()), ('bias', m.bias)):
+                t = t.detach().float().cpu().contiguous()
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                _native.check(lib.svb_wn_set_weight(h, f'{name}.{suffix}'.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()),
+                              'wn_set_weight')
+        _native.check(lib.svb_wn_finalize(h), 'wn_finalize')
+        self._handle, self._versions = h, versions
+        return h
+
+    def _free(self):
+        if self._handle is not None:
+            _native.lib().svb_wn_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    def forward(self, x, x_mask=None, g=None, **kwargs):
+        """fs2_vae.py:62-94.  x [B, H, T] ([B, T, H] with is_BTC), x_mask [B, 1, T], g [B, gin, T]."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise RuntimeError('neuralsvb_b200 WN is inference only: call .eval() and run under torch.no_grad()')
+        if not x.is_cuda:
+            raise RuntimeError('neuralsvb_b200 has no CPU path: move the module and its inputs to a CUDA device')
+        if self.is_BTC:
+            x = x.transpose(1, 2)
+            x_mask = x_mask.transpose(1, 2) if x_mask is not None else None
+        x = x.float().contiguous()
+        B, H, T = x.shape
+        assert H == self.hidden_channels, (H, self.hidden_channels)
+        mask = None if x_mask is None else x_mask.float().expand(B, 1, T).reshape(B, T).contiguous()
+        gc = None if g is None else g.float().expand(B, self.gin_channels, T).contiguous()
+        out = torch.empty_like(x)
+        h = self._native_handle(x.device)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _native.check(_native.lib().svb_wn_forward(h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(mask.data_ptr()) if mask is not None else None,
+                                                   ctypes.c_void_p(gc.data_ptr()) if gc is not None else None, B, T,
+                                                   ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st)), 'wn_forward')
+        return out.transpose(1, 2) if self.is_BTC else out

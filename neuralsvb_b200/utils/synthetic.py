@@ -246,3 +246,34 @@ def make_msd_state_dict(seed=1234, use_cond=False, hop=256):
                 g, v = _wn_pair(rs, (cout, cg, k), 1.3 / np.sqrt(cg * k), (1, 2))
                 sd[f'discriminators.{d}.{name}.weight_g'], sd[f'discriminators.{d}.{name}.weight_v'] = g, v
     return OrderedDict((k, torch.from_numpy(np.ascontiguousarray(v))) for k, v in sd.items())
+
+
+def make_wn_state_dict(hidden=192, kernel_size=5, n_layers=4, gin_channels=0, seed=1234):
+    """state_dict of the reference's WN (modules/fastspeech/fs2_vae.py:19-60) with its weight-norm key names:
+    ``in_layers.{i}.{bias,weight_g,weight_v}``, ``res_skip_layers.{i}.*``, ``cond_layer.*``; g != ||v||."""
+    rs = np.random.RandomState(seed)
+    sd = OrderedDict()
+
+    def conv(prefix, cout, cin, k):
+        b = 1.0 / np.sqrt(cin * k)
+        sd[f'{prefix}.bias'] = _uniform(rs, (cout,), b)
+        g, v = _wn_pair(rs, (cout, cin, k), b, (1, 2))
+        sd[f'{prefix}.weight_g'], sd[f'{prefix}.weight_v'] = g, v
+    if gin_channels:
+        conv('cond_layer', 2 * hidden * n_layers, gin_channels, 1)
+    for i in range(n_layers):
+        conv(f'in_layers.{i}', 2 * hidden, hidden, kernel_size)
+        conv(f'res_skip_layers.{i}', 2 * hidden if i < n_layers - 1 else hidden, hidden, 1)
+    return OrderedDict((k, torch.from_numpy(v)) for k, v in sd.items())
+
+
+def make_wn_inputs(B, T, hidden=192, gin_channels=0, seed=1234, ragged=True):
+    """x [B, H, T] ~ N(0, 1), x_mask [B, 1, T] (clip b keeps T - 7 b frames when ``ragged``), g [B, gin, T] or None."""
+    rs = np.random.RandomState(seed + 17)
+    x = torch.from_numpy(_normal(rs, (B, hidden, T), 1.0))
+    mask = torch.ones(B, 1, T)
+    if ragged:
+        for b in range(B):
+            mask[b, :, T - min(7 * b, T - 1):] = 0.0 if b else 1.0
+    g = torch.from_numpy(_normal(rs, (B, gin_channels, T), 1.0)) if gin_channels else None
+    return x * mask, mask, g

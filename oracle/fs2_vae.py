@@ -1,0 +1,40 @@
+"""ORACLE (test infrastructure only; see oracle/__init__.py): torch-CPU restatement of the WN gated dilated-conv
+stack, modules/fastspeech/fs2_vae.py:11-94 of the reference.  Pinned by tests/golden/wn.npz, which
+oracle/gen_golden.py writes from the UNMODIFIED reference class."""
+import torch
+import torch.nn.functional as F
+
+
+def fold_weight_norm(sd):
+    """WN.remove_weight_norm (fs2_vae.py:96-103): weight = g * v / ||v||, norm over every dim except 0."""
+    out = {}
+    for k, v in sd.items():
+        if k.endswith('.weight_g'):
+            continue
+        if k.endswith('.weight_v'):
+            out[k[:-2]] = torch._weight_norm(v, sd[k[:-1] + 'g'], 0)
+        else:
+            out[k] = v
+    return out
+
+
+def wn_forward(w, hidden, kernel_size, dilation_rate, n_layers, x, x_mask=None, g=None):
+    """WN.forward (fs2_vae.py:62-94) on folded weights ``w``; x [B, H, T], x_mask [B, 1, T] or None, g [B, gin, T] or None."""
+    mask = 1 if x_mask is None else x_mask
+    output = torch.zeros_like(x)
+    if g is not None:
+        g = F.conv1d(g, w['cond_layer.weight'], w['cond_layer.bias'])                        # :73-74
+    for i in range(n_layers):
+        d = dilation_rate ** i
+        x_in = F.conv1d(x, w[f'in_layers.{i}.weight'], w[f'in_layers.{i}.bias'], dilation=d,
+                        padding=int((kernel_size * d - d) / 2))                                # :43-46,77
+        if g is not None:
+            x_in = x_in + g[:, i * 2 * hidden:(i + 1) * 2 * hidden]                           # :80-82
+        acts = torch.tanh(x_in[:, :hidden]) * torch.sigmoid(x_in[:, hidden:])                # :11-17
+        rs = F.conv1d(acts, w[f'res_skip_layers.{i}.weight'], w[f'res_skip_layers.{i}.bias'])  # :88
+        if i < n_layers - 1:
+            x = (x + rs[:, :hidden]) * mask                                                   # :90
+            output = output + rs[:, hidden:]                                                  # :91
+        else:
+            output = output + rs                                                              # :93
+    return output * mask                                                                      # :94

@@ -348,6 +348,37 @@ def gen_discriminators_train():
     np.savez_compressed(os.path.join(OUT, 'discriminators_train.npz'), **out)
 
 
+WN_CASES = {
+    # name: (hidden, kernel, dilation_rate, n_layers, gin, B, T)      GlobalFVAE decoder / encoder shapes (vae_models.py:81-146)
+    'fvae_dec': (192, 5, 1, 4, 0, 2, 100),
+    'fvae_enc_cond': (192, 5, 1, 8, 256, 2, 61),
+    'dilated_cond': (64, 3, 2, 3, 32, 1, 300),
+}
+
+
+def gen_wn():
+    """WN outputs of the reference class itself (modules/fastspeech/fs2_vae.py:19-94), weight-normed then folded."""
+    R.install()
+    import contextlib
+    import io
+    from modules.fastspeech.fs2_vae import WN
+    out = {}
+    for name, (H, K, dr, L, gin, B, T) in WN_CASES.items():
+        sd = S.make_wn_state_dict(H, K, L, gin, SEED)
+        x, mask, g = S.make_wn_inputs(B, T, H, gin, SEED)
+        m = WN(H, K, dr, L, gin_channels=gin)
+        m.load_state_dict(sd, strict=True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.remove_weight_norm()
+        m.eval()
+        with torch.no_grad():
+            y = m(x, mask, g)
+        out[f'{name}/y'] = y.numpy().astype(np.float32)
+        out[f'{name}/params'] = np.array([H, K, dr, L, gin, B, T], np.int64)
+    np.savez_compressed(os.path.join(OUT, 'wn.npz'), **out)
+    print('wn.npz', {k: v.shape for k, v in out.items() if k.endswith('/y')})
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
@@ -355,7 +386,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
     which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond', 'generator_extra',
-                             'generator_grads', 'losses_extra', 'discriminators_train']
+                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn']
     for w in which:
         globals()[f'gen_{w}']()
 

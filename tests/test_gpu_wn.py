@@ -1,0 +1,61 @@
+"""WN gated-conv stack (first piece): CUDA path through the C ABI vs the reference-generated fixture
+and the oracle.  Reference: modules/fastspeech/fs2_vae.py:19-94."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from neuralsvb_b200.utils import synthetic as S
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'wn.npz')
+CASES = ['fvae_dec', 'fvae_enc_cond', 'dilated_cond']
+
+
+def _run(name, precision):
+    from neuralsvb_b200.modules.fastspeech.fs2_vae import WN
+    g = np.load(GOLDEN)
+    H, K, dr, L, gin, B, T = [int(v) for v in g[f'{name}/params']]
+    sd = S.make_wn_state_dict(H, K, L, gin, 1234)
+    x, mask, cond = S.make_wn_inputs(B, T, H, gin, 1234)
+    m = WN(H, K, dr, L, gin_channels=gin, precision=precision)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().cuda()
+    with torch.no_grad():
+        y = m(x.cuda(), mask.cuda(), None if cond is None else cond.cuda()).cpu().numpy()
+    return y, g[f'{name}/y']
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_wn_matches_reference_fixture(name, precision):
+    y, ref = _run(name, precision)
+    assert y.shape == ref.shape
+    rel = float(np.abs(y - ref).max() / np.abs(ref).max())
+    # north-star tolerance for spectral features: 1e-3 relative L-inf; the split-bf16 tensor-core path sits at ~1e-5
+    assert rel < 1e-3 and rel < (2e-5 if precision == 'fp32' else 1e-4), rel
+
+
+def test_wn_weight_norm_removed_and_btc_layout():
+    from neuralsvb_b200.modules.fastspeech.fs2_vae import WN
+    g = np.load(GOLDEN)
+    H, K, dr, L, gin, B, T = [int(v) for v in g['fvae_dec/params']]
+    x, mask, _ = S.make_wn_inputs(B, T, H, gin, 1234)
+    m = WN(H, K, dr, L, gin_channels=gin, is_BTC=True)
+    m.load_state_dict(S.make_wn_state_dict(H, K, L, gin, 1234), strict=True)
+    m.remove_weight_norm()
+    assert 'in_layers.0.weight' in m.state_dict() and 'in_layers.0.weight_g' not in m.state_dict()
+    m = m.eval().cuda()
+    with torch.no_grad():
+        y = m(x.transpose(1, 2).cuda(), mask.transpose(1, 2).cuda()).transpose(1, 2).cpu().numpy()
+    assert float(np.abs(y - g['fvae_dec/y']).max() / np.abs(g['fvae_dec/y']).max()) < 1e-4
+
+
+def test_wn_refuses_training_and_cpu():
+    from neuralsvb_b200.modules.fastspeech.fs2_vae import WN
+    m = WN(64, 3, 1, 2)
+    with pytest.raises(RuntimeError):
+        m.eval()(torch.zeros(1, 64, 16))
+    with pytest.raises(RuntimeError):
+        m.train().cuda()(torch.zeros(1, 64, 16).cuda())

@@ -268,3 +268,16 @@ def test_training_mode_discriminators_match_reference(golden_dir, name):
     np.testing.assert_allclose(float(lg), float(g[f'{name}/g_loss']), rtol=2e-5)
     assert abs(float(yh.grad.double().norm()) - float(g[f'{name}/g_dyhat_norm'])) < 2e-4 * float(g[f'{name}/g_dyhat_norm'])
     assert np.abs(yh.grad.numpy()[:, 0, ::5] - g[f'{name}/g_dyhat_sub']).max() < 2e-3 * np.abs(g[f'{name}/g_dyhat_sub']).max()
+
+
+def test_wn_oracle_matches_reference_fixture(golden_dir):
+    """oracle/fs2_vae.py against the reference WN class (tests/golden/wn.npz, written by oracle/gen_golden.py gen_wn)."""
+    from oracle import fs2_vae as OW
+    g = np.load(os.path.join(golden_dir, 'wn.npz'))
+    for name in ('fvae_dec', 'fvae_enc_cond', 'dilated_cond'):
+        H, K, dr, L, gin, B, T = [int(v) for v in g[f'{name}/params']]
+        w = OW.fold_weight_norm(S.make_wn_state_dict(H, K, L, gin, 1234))
+        x, mask, cond = S.make_wn_inputs(B, T, H, gin, 1234)
+        with torch.no_grad():
+            y = OW.wn_forward(w, H, K, dr, L, x, mask, cond).numpy()
+        assert float(np.abs(y - g[f'{name}/y']).max()) <= 1e-5 * float(np.abs(g[f'{name}/y']).max()), name
