@@ -344,6 +344,15 @@ int svb_wn_finalize(svb_wn_t *w);
  * (x_mask[:, 0, :], NULL = all ones), g [B, gin, T] (NULL = unconditioned) -> out [B, H, T]. */
 int svb_wn_forward(svb_wn_t *w, const float *x_dev, const float *mask_dev, const float *g_dev, int32_t B, int32_t T, float *out_dev,
                    void *stream);
+/* FVAEDecoder / GlobalFVAEDecoder (modules/fastspeech/fs2_vae.py:130-152, modules/voice_conversion/vae_models.py:108-128): the mel
+ * decoder whose output `spec2wav` consumes -- pre_net ConvTranspose1d(latent, H, k = stride, stride) -> * mask -> WN(dilation_rate 1)
+ * -> * mask -> out_proj Conv1d(H, out, 1).  Same handle type as WN; additional weights `pre_net.0.weight [latent, H, stride]`,
+ * `pre_net.0.bias`, `out_proj.weight [out, H, 1]`, `out_proj.bias` (svb_wn_set_weight), WN weights under their plain names.
+ * forward: z [B, latent, T / stride], mask [B, T] or NULL, g [B, gin, T] or NULL -> out [B, out_channels, T]. */
+int svb_fvae_decoder_create(int32_t latent_channels, int32_t hidden_channels, int32_t out_channels, int32_t kernel_size, int32_t n_layers,
+                            int32_t gin_channels, int32_t stride, int32_t precision, int32_t device, svb_wn_t **out);
+int svb_fvae_decoder_forward(svb_wn_t *w, const float *z_dev, const float *mask_dev, const float *g_dev, int32_t B, int32_t T,
+                             float *out_dev, void *stream);
 
 #ifdef __cplusplus
 }

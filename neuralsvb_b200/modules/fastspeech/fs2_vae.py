@@ -117,3 +117,83 @@ class WN(nn.Module):
                                                    ctypes.c_void_p(gc.data_ptr()) if gc is not None else None, B, T,
                                                    ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st)), 'wn_forward')
         return out.transpose(1, 2) if self.is_BTC else out
+
+
+class FVAEDecoder(nn.Module):
+    """Mirror of ``modules/fastspeech/fs2_vae.py:130-152``: pre_net ConvTranspose1d(k = s, stride = s) -> * x_mask -> WN -> * x_mask
+    -> out_proj.  One native call (``svb_fvae_decoder_forward``); ``pre_net`` / ``out_proj`` are parameter holders with the
+    reference's ``state_dict`` names.  Inference only."""
+
+    def __init__(self, latent_channels, hidden_channels, out_channels, kernel_size, n_layers, gin_channels=0, p_dropout=0,
+                 strides=[4], precision='bf16x3'):
+        super().__init__()
+        if len(strides) != 1:
+            raise NotImplementedError('FVAEDecoder: one up-sampling stride (the reference configs use strides=[4])')
+        self.strides, self.hidden_size = list(strides), hidden_channels
+        self.latent_channels, self.out_channels, self.precision = latent_channels, out_channels, precision
+        self.pre_net = nn.Sequential(nn.ConvTranspose1d(latent_channels, hidden_channels, kernel_size=strides[0], stride=strides[0]))
+        self.wn = WN(hidden_channels, kernel_size, 1, n_layers, gin_channels, p_dropout, precision=precision)
+        self.out_proj = nn.Conv1d(hidden_channels, out_channels, 1)
+        self._handle, self._versions = None, None
+
+    def _native_handle(self, device):
+        versions = tuple(p._version for p in self.parameters()) + (str(device),)
+        if self._handle is not None and versions == self._versions:
+            return self._handle
+        self._free()
+        lib = _native.lib()
+        h = ctypes.c_void_p()
+        wn = self.wn
+        _native.check(lib.svb_fvae_decoder_create(self.latent_channels, wn.hidden_channels, self.out_channels, wn.kernel_size, wn.n_layers,
+                                                  wn.gin_channels, self.strides[0], _native.PREC[self.precision], device.index or 0,
+                                                  ctypes.byref(h)), 'fvae_decoder_create')
+        tensors = [(f'{name}.{sfx}', t) for name, m in wn._convs() for sfx, t in (('weight', m.folded()), ('bias', m.bias))]
+        tensors += [('pre_net.0.weight', self.pre_net[0].weight), ('pre_net.0.bias', self.pre_net[0].bias),
+                    ('out_proj.weight', self.out_proj.weight), ('out_proj.bias', self.out_proj.bias)]
+        for name, t in tensors:
+            t = t.detach().float().cpu().contiguous()
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            _native.check(lib.svb_wn_set_weight(h, name.encode(), ctypes.c_void_p(t.data_ptr()), shape, t.dim()), 'wn_set_weight')
+        _native.check(lib.svb_wn_finalize(h), 'wn_finalize')
+        self._handle, self._versions = h, versions
+        return h
+
+    def _free(self):
+        if self._handle is not None:
+            _native.lib().svb_wn_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    def forward(self, x, x_mask, g):
+        """x [B, latent, T / s]; x_mask [B, 1, T] (or the scalar 1 the reference passes at inference); g [B, gin, T] or None."""
+        if torch.is_grad_enabled() and self.training:
+            raise RuntimeError('neuralsvb_b200 FVAEDecoder is inference only: call .eval() and run under torch.no_grad()')
+        if not x.is_cuda:
+            raise RuntimeError('neuralsvb_b200 has no CPU path: move the module and its inputs to a CUDA device')
+        x = x.float().contiguous()
+        B, _, Tz = x.shape
+        T = Tz * self.strides[0]
+        mask = None
+        if torch.is_tensor(x_mask):
+            mask = x_mask.float().expand(B, 1, T).reshape(B, T).contiguous()
+        gc = None if g is None else g.float().expand(B, self.wn.gin_channels, T).contiguous()
+        out = torch.empty(B, self.out_channels, T, device=x.device, dtype=torch.float32)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _native.check(_native.lib().svb_fvae_decoder_forward(
+            self._native_handle(x.device), ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(mask.data_ptr()) if mask is not None else None,
+            ctypes.c_void_p(gc.data_ptr()) if gc is not None else None, B, T, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st)),
+            'fvae_decoder_forward')
+        return out
+
+
+class GlobalFVAEDecoder(FVAEDecoder):
+    """``modules/voice_conversion/vae_models.py:108-128``: one latent vector per utterance, repeated over T / 4 frames."""
+
+    def forward(self, x, x_mask, g):
+        x = x.repeat(1, 1, g.shape[-1] // self.strides[0])          # [B, latent, 1] -> [B, latent, T // 4]   :122
+        return super().forward(x, x_mask, g)

@@ -277,3 +277,19 @@ def make_wn_inputs(B, T, hidden=192, gin_channels=0, seed=1234, ragged=True):
             mask[b, :, T - min(7 * b, T - 1):] = 0.0 if b else 1.0
     g = torch.from_numpy(_normal(rs, (B, gin_channels, T), 1.0)) if gin_channels else None
     return x * mask, mask, g
+
+
+def make_fvae_decoder_state_dict(latent=128, hidden=192, out_channels=80, kernel_size=5, n_layers=4, gin_channels=256, stride=4, seed=1234):
+    """state_dict of the reference's FVAEDecoder / GlobalFVAEDecoder (fs2_vae.py:130-146): ``pre_net.0.*`` (ConvTranspose1d),
+    ``wn.*`` (weight-normed), ``out_proj.*``."""
+    rs = np.random.RandomState(seed + 3)
+    sd = OrderedDict()
+    b = 1.0 / np.sqrt(latent)
+    sd['pre_net.0.weight'] = torch.from_numpy(_uniform(rs, (latent, hidden, stride), b))
+    sd['pre_net.0.bias'] = torch.from_numpy(_uniform(rs, (hidden,), b))
+    for k, v in make_wn_state_dict(hidden, kernel_size, n_layers, gin_channels, seed).items():
+        sd[f'wn.{k}'] = v
+    b = 1.0 / np.sqrt(hidden)
+    sd['out_proj.weight'] = torch.from_numpy(_uniform(rs, (out_channels, hidden, 1), b))
+    sd['out_proj.bias'] = torch.from_numpy(_uniform(rs, (out_channels,), b))
+    return sd

@@ -38,3 +38,15 @@ def wn_forward(w, hidden, kernel_size, dilation_rate, n_layers, x, x_mask=None, 
         else:
             output = output + rs                                                              # :93
     return output * mask                                                                      # :94
+
+
+def fvae_decoder_forward(w, hidden, kernel_size, n_layers, stride, x, x_mask, g, global_latent=False):
+    """FVAEDecoder.forward (fs2_vae.py:147-152); with ``global_latent`` GlobalFVAEDecoder.forward (vae_models.py:120-128).
+    ``w``: folded state_dict (pre_net.0.*, wn.*, out_proj.*)."""
+    if global_latent:
+        x = x.repeat(1, 1, g.shape[-1] // stride)
+    x = F.conv_transpose1d(x, w['pre_net.0.weight'], w['pre_net.0.bias'], stride=stride)
+    x = x * x_mask
+    wn_w = {k[3:]: v for k, v in w.items() if k.startswith('wn.')}
+    x = wn_forward(wn_w, hidden, kernel_size, 1, n_layers, x, x_mask if torch.is_tensor(x_mask) else None, g) * x_mask
+    return F.conv1d(x, w['out_proj.weight'], w['out_proj.bias'])

@@ -379,6 +379,39 @@ def gen_wn():
     print('wn.npz', {k: v.shape for k, v in out.items() if k.endswith('/y')})
 
 
+FVAE_DEC_CASES = {
+    # name: (latent, hidden, out, kernel, n_layers, gin, B, T, global latent)   vae_global_mle_eng: hidden 192, latent 128, k 5, dec 4 layers
+    'global_dec': (128, 192, 80, 5, 4, 256, 2, 120, True),
+    'local_dec_nocond_mask1': (16, 64, 80, 3, 2, 0, 1, 52, False),
+}
+
+
+def gen_fvae_decoder():
+    """Mel decoder outputs of the reference classes (FVAEDecoder fs2_vae.py:130-152, GlobalFVAEDecoder vae_models.py:108-128)."""
+    R.install()
+    import contextlib
+    import io
+    from modules.fastspeech.fs2_vae import FVAEDecoder
+    from modules.voice_conversion.vae_models import GlobalFVAEDecoder
+    out = {}
+    for name, (lat, H, oc, K, L, gin, B, T, glob) in FVAE_DEC_CASES.items():
+        sd = S.make_fvae_decoder_state_dict(lat, H, oc, K, L, gin, 4, SEED)
+        _, mask, g = S.make_wn_inputs(B, T, H, gin, SEED)
+        rs = np.random.RandomState(SEED + 5)
+        z = torch.from_numpy(rs.randn(B, lat, 1 if glob else T // 4).astype(np.float32))
+        m = (GlobalFVAEDecoder if glob else FVAEDecoder)(lat, H, oc, K, L, gin, strides=[4])
+        m.load_state_dict(sd, strict=True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.wn.remove_weight_norm()
+        m.eval()
+        with torch.no_grad():
+            y = m(z, mask if glob else 1, g)             # the reference passes x_mask = 1 at inference (fs2_vae.py:213)
+        out[f'{name}/y'] = y.numpy().astype(np.float32)
+        out[f'{name}/params'] = np.array([lat, H, oc, K, L, gin, B, T, int(glob)], np.int64)
+    np.savez_compressed(os.path.join(OUT, 'fvae_decoder.npz'), **out)
+    print('fvae_decoder.npz', {k: v.shape for k, v in out.items() if k.endswith('/y')})
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
@@ -386,7 +419,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
     which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond', 'generator_extra',
-                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn']
+                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder']
     for w in which:
         globals()[f'gen_{w}']()
 

@@ -59,3 +59,23 @@ def test_wn_refuses_training_and_cpu():
         m.eval()(torch.zeros(1, 64, 16))
     with pytest.raises(RuntimeError):
         m.train().cuda()(torch.zeros(1, 64, 16).cuda())
+
+
+@pytest.mark.parametrize('name', ['global_dec', 'local_dec_nocond_mask1'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_fvae_decoder_matches_reference_fixture(name, precision):
+    """FVAEDecoder / GlobalFVAEDecoder (fs2_vae.py:130-152, vae_models.py:108-128): the mel that spec2wav consumes."""
+    from neuralsvb_b200.modules.fastspeech.fs2_vae import FVAEDecoder, GlobalFVAEDecoder
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fvae_decoder.npz'))
+    lat, H, oc, K, L, gin, B, T, glob = [int(v) for v in g[f'{name}/params']]
+    m = (GlobalFVAEDecoder if glob else FVAEDecoder)(lat, H, oc, K, L, gin, strides=[4], precision=precision)
+    m.load_state_dict(S.make_fvae_decoder_state_dict(lat, H, oc, K, L, gin, 4, 1234), strict=True)
+    m = m.eval().cuda()
+    _, mask, cond = S.make_wn_inputs(B, T, H, gin, 1234)
+    z = torch.from_numpy(np.random.RandomState(1234 + 5).randn(B, lat, 1 if glob else T // 4).astype(np.float32))
+    with torch.no_grad():
+        y = m(z.cuda(), mask.cuda() if glob else 1, None if cond is None else cond.cuda()).cpu().numpy()
+    ref = g[f'{name}/y']
+    assert y.shape == ref.shape == (B, oc, T)
+    rel = float(np.abs(y - ref).max() / np.abs(ref).max())
+    assert rel < 1e-3 and rel < (2e-5 if precision == 'fp32' else 1e-4), rel      # north-star: 1e-3 relative L-inf on mel frames

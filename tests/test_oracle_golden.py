@@ -281,3 +281,17 @@ def test_wn_oracle_matches_reference_fixture(golden_dir):
         with torch.no_grad():
             y = OW.wn_forward(w, H, K, dr, L, x, mask, cond).numpy()
         assert float(np.abs(y - g[f'{name}/y']).max()) <= 1e-5 * float(np.abs(g[f'{name}/y']).max()), name
+
+
+def test_fvae_decoder_oracle_matches_reference_fixture(golden_dir):
+    """oracle/fs2_vae.py:fvae_decoder_forward against the reference FVAEDecoder / GlobalFVAEDecoder (tests/golden/fvae_decoder.npz)."""
+    from oracle import fs2_vae as OW
+    g = np.load(os.path.join(golden_dir, 'fvae_decoder.npz'))
+    for name in ('global_dec', 'local_dec_nocond_mask1'):
+        lat, H, oc, K, L, gin, B, T, glob = [int(v) for v in g[f'{name}/params']]
+        w = OW.fold_weight_norm(S.make_fvae_decoder_state_dict(lat, H, oc, K, L, gin, 4, 1234))
+        _, mask, cond = S.make_wn_inputs(B, T, H, gin, 1234)
+        z = torch.from_numpy(np.random.RandomState(1234 + 5).randn(B, lat, 1 if glob else T // 4).astype(np.float32))
+        with torch.no_grad():
+            y = OW.fvae_decoder_forward(w, H, K, L, 4, z, mask if glob else 1, cond, bool(glob)).numpy()
+        assert float(np.abs(y - g[f'{name}/y']).max()) <= 1e-5 * float(np.abs(g[f'{name}/y']).max()), name
