@@ -197,3 +197,51 @@ class GlobalFVAEDecoder(FVAEDecoder):
     def forward(self, x, x_mask, g):
         x = x.repeat(1, 1, g.shape[-1] // self.strides[0])          # [B, latent, 1] -> [B, latent, T // 4]   :122
         return super().forward(x, x_mask, g)
+
+
+class GlobalFVAEEncoder(nn.Module):
+    """``modules/voice_conversion/vae_models.py:81-106`` (FVAEEncoder, fs2_vae.py:106-127, plus the global pooling head):
+    pre_net strided conv -> * mask -> WN (8 layers) -> * mask -> out_proj -> poolings (3 strided convs, ReLU, BatchNorm in eval
+    mode) -> mean over time -> (m, logs) -> z = m + eps * exp(logs).  Every convolution is a native kernel (``svb_conv_nct_forward``
+    for the strided / 1x1 layers, ``svb_wn_forward`` for the stack); the BatchNorm affine and the mean act on [B, 256, T / 32]
+    tensors.  Inference only.  ``forward(..., eps=...)`` injects the posterior noise (parity tests); default: torch.randn_like."""
+
+    def __init__(self, in_channels, hidden_channels, latent_channels, kernel_size, n_layers, gin_channels=0, p_dropout=0, strides=[4],
+                 precision='bf16x3'):
+        super().__init__()
+        if len(strides) != 1:
+            raise NotImplementedError('GlobalFVAEEncoder: one down-sampling stride (the reference configs use strides=[4])')
+        s0 = strides[0]
+        self.strides, self.hidden_size, self.latent_channels = list(strides), hidden_channels, latent_channels
+        self.pre_net = nn.Sequential(nn.Conv1d(in_channels, hidden_channels, kernel_size=s0 * 2, stride=s0, padding=s0 // 2))
+        self.wn = WN(hidden_channels, kernel_size, 1, n_layers, gin_channels, p_dropout, precision=precision)
+        self.out_proj = nn.Conv1d(hidden_channels, latent_channels * 2, 1)
+        c2 = latent_channels * 2
+        self.poolings = nn.Sequential(nn.Conv1d(c2, c2, kernel_size=3, stride=2), nn.ReLU(), nn.BatchNorm1d(c2),
+                                      nn.Conv1d(c2, c2, kernel_size=3, stride=2), nn.ReLU(), nn.BatchNorm1d(c2),
+                                      nn.Conv1d(c2, c2, kernel_size=3, stride=2))
+
+    @staticmethod
+    def _bn_eval(bn, x):
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        return x * scale[None, :, None] + (bn.bias - bn.running_mean * scale)[None, :, None]
+
+    def forward(self, x, x_mask, g, eps=None):
+        from neuralsvb_b200.modules.hifigan.discriminators import conv_nct
+        if torch.is_grad_enabled() and self.training:
+            raise RuntimeError('neuralsvb_b200 GlobalFVAEEncoder is inference only: call .eval() and run under torch.no_grad()')
+        s0 = self.strides[0]
+        c = self.pre_net[0]
+        x = conv_nct(x.float(), c.weight, c.bias, 2 * s0, stride=s0, pad=s0 // 2)                       # vae_models.py:97
+        x_mask = x_mask[:, :, ::s0][:, :, :x.shape[-1]]                                                 # :98
+        x = x * x_mask                                                                                  # :99
+        x = self.wn(x, x_mask, g) * x_mask                                                              # :100
+        x = conv_nct(x, self.out_proj.weight, self.out_proj.bias, 1)                                    # :101
+        p = self.poolings
+        x = self._bn_eval(p[2], conv_nct(x, p[0].weight, p[0].bias, 3, stride=2, slope=0.0))            # conv + ReLU (slope 0), BatchNorm (eval)
+        x = self._bn_eval(p[5], conv_nct(x, p[3].weight, p[3].bias, 3, stride=2, slope=0.0))
+        x = conv_nct(x, p[6].weight, p[6].bias, 3, stride=2)
+        x = torch.mean(x, dim=-1, keepdim=True)                                                         # :102
+        m, logs = torch.split(x, self.latent_channels, dim=1)                                           # :103
+        z = m + (torch.randn_like(m) if eps is None else eps) * torch.exp(logs)                         # :104
+        return z, m, logs, x_mask

@@ -293,3 +293,29 @@ def make_fvae_decoder_state_dict(latent=128, hidden=192, out_channels=80, kernel
     sd['out_proj.weight'] = torch.from_numpy(_uniform(rs, (out_channels, hidden, 1), b))
     sd['out_proj.bias'] = torch.from_numpy(_uniform(rs, (out_channels,), b))
     return sd
+
+
+def make_fvae_encoder_state_dict(in_channels=80, hidden=192, latent=128, kernel_size=5, n_layers=8, gin_channels=256, stride=4, seed=1234):
+    """state_dict of the reference's GlobalFVAEEncoder (vae_models.py:81-95): ``pre_net.0.*``, ``wn.*`` (weight-normed),
+    ``out_proj.*``, ``poolings.{0,3,6}.*`` (convs) and ``poolings.{2,5}.*`` (BatchNorm with non-trivial running statistics)."""
+    rs = np.random.RandomState(seed + 9)
+    sd = OrderedDict()
+
+    def t(a):
+        return torch.from_numpy(a)
+    b = 1.0 / np.sqrt(in_channels * 2 * stride)
+    sd['pre_net.0.weight'], sd['pre_net.0.bias'] = t(_uniform(rs, (hidden, in_channels, 2 * stride), b)), t(_uniform(rs, (hidden,), b))
+    for k, v in make_wn_state_dict(hidden, kernel_size, n_layers, gin_channels, seed).items():
+        sd[f'wn.{k}'] = v
+    b = 1.0 / np.sqrt(hidden)
+    c2 = 2 * latent
+    sd['out_proj.weight'], sd['out_proj.bias'] = t(_uniform(rs, (c2, hidden, 1), b)), t(_uniform(rs, (c2,), b))
+    b = 1.0 / np.sqrt(c2 * 3)
+    for i in (0, 3, 6):
+        sd[f'poolings.{i}.weight'], sd[f'poolings.{i}.bias'] = t(_uniform(rs, (c2, c2, 3), b)), t(_uniform(rs, (c2,), b))
+    for i in (2, 5):
+        sd[f'poolings.{i}.weight'], sd[f'poolings.{i}.bias'] = t(rs.uniform(0.5, 1.5, c2).astype(np.float32)), t(_uniform(rs, (c2,), 0.2))
+        sd[f'poolings.{i}.running_mean'] = t(_uniform(rs, (c2,), 0.1))
+        sd[f'poolings.{i}.running_var'] = t(rs.uniform(0.05, 0.5, c2).astype(np.float32))
+        sd[f'poolings.{i}.num_batches_tracked'] = torch.tensor(100)
+    return sd

@@ -50,3 +50,22 @@ def fvae_decoder_forward(w, hidden, kernel_size, n_layers, stride, x, x_mask, g,
     wn_w = {k[3:]: v for k, v in w.items() if k.startswith('wn.')}
     x = wn_forward(wn_w, hidden, kernel_size, 1, n_layers, x, x_mask if torch.is_tensor(x_mask) else None, g) * x_mask
     return F.conv1d(x, w['out_proj.weight'], w['out_proj.bias'])
+
+
+def global_fvae_encoder_forward(w, hidden, latent, kernel_size, n_layers, stride, x, x_mask, g, eps):
+    """GlobalFVAEEncoder.forward (vae_models.py:96-106) in eval mode on a folded state_dict; ``eps`` replaces randn_like(m)."""
+    x = F.conv1d(x, w['pre_net.0.weight'], w['pre_net.0.bias'], stride=stride, padding=stride // 2)
+    x_mask = x_mask[:, :, ::stride][:, :, :x.shape[-1]]
+    x = x * x_mask
+    wn_w = {k[3:]: v for k, v in w.items() if k.startswith('wn.')}
+    x = wn_forward(wn_w, hidden, kernel_size, 1, n_layers, x, x_mask, g) * x_mask
+    x = F.conv1d(x, w['out_proj.weight'], w['out_proj.bias'])
+    for i in (0, 3):
+        x = torch.relu(F.conv1d(x, w[f'poolings.{i}.weight'], w[f'poolings.{i}.bias'], stride=2))
+        j = i + 2
+        x = F.batch_norm(x, w[f'poolings.{j}.running_mean'], w[f'poolings.{j}.running_var'], w[f'poolings.{j}.weight'], w[f'poolings.{j}.bias'],
+                         training=False, eps=1e-5)
+    x = F.conv1d(x, w['poolings.6.weight'], w['poolings.6.bias'], stride=2)
+    x = torch.mean(x, dim=-1, keepdim=True)
+    m, logs = torch.split(x, latent, dim=1)
+    return m + eps * torch.exp(logs), m, logs, x_mask

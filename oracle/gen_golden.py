@@ -412,6 +412,31 @@ def gen_fvae_decoder():
     print('fvae_decoder.npz', {k: v.shape for k, v in out.items() if k.endswith('/y')})
 
 
+def gen_fvae_encoder():
+    """(m, logs) of the reference GlobalFVAEEncoder in eval mode (vae_models.py:81-106; hidden 192, latent 128, 8 WN layers)."""
+    R.install()
+    import contextlib
+    import io
+    from modules.voice_conversion.vae_models import GlobalFVAEEncoder
+    cin, H, lat, K, L, gin, B, T = 80, 192, 128, 5, 8, 256, 2, 400
+    sd = S.make_fvae_encoder_state_dict(cin, H, lat, K, L, gin, 4, SEED)
+    rs = np.random.RandomState(SEED + 11)
+    x = torch.from_numpy(rs.randn(B, cin, T).astype(np.float32))
+    mask = torch.ones(B, 1, T)
+    mask[1, :, T - 36:] = 0
+    g = torch.from_numpy(rs.randn(B, gin, T // 4).astype(np.float32))
+    m = GlobalFVAEEncoder(cin, H, lat, K, L, gin, strides=[4])
+    m.load_state_dict(sd, strict=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.wn.remove_weight_norm()
+    m.eval()
+    with torch.no_grad():
+        z, mq, logs, xm = m(x * mask, mask, g)
+    out = {'m': mq.numpy(), 'logs': logs.numpy(), 'mask_len': xm.sum(-1).numpy(), 'params': np.array([cin, H, lat, K, L, gin, B, T], np.int64)}
+    np.savez_compressed(os.path.join(OUT, 'fvae_encoder.npz'), **out)
+    print('fvae_encoder.npz', {k: v.shape for k, v in out.items()})
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
@@ -419,7 +444,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
     which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond', 'generator_extra',
-                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder']
+                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder', 'fvae_encoder']
     for w in which:
         globals()[f'gen_{w}']()
 

@@ -79,3 +79,22 @@ def test_fvae_decoder_matches_reference_fixture(name, precision):
     assert y.shape == ref.shape == (B, oc, T)
     rel = float(np.abs(y - ref).max() / np.abs(ref).max())
     assert rel < 1e-3 and rel < (2e-5 if precision == 'fp32' else 1e-4), rel      # north-star: 1e-3 relative L-inf on mel frames
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_global_fvae_encoder_matches_reference_fixture(precision):
+    """GlobalFVAEEncoder (vae_models.py:81-106): posterior mean / log-sigma of an utterance, eval mode."""
+    from neuralsvb_b200.modules.fastspeech.fs2_vae import GlobalFVAEEncoder
+    from tests.test_oracle_golden import _fvae_encoder_inputs
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'fvae_encoder.npz'))
+    (cin, H, lat, K, L, gin, B, T), x, mask, cond = _fvae_encoder_inputs(g)
+    m = GlobalFVAEEncoder(cin, H, lat, K, L, gin, strides=[4], precision=precision)
+    m.load_state_dict(S.make_fvae_encoder_state_dict(cin, H, lat, K, L, gin, 4, 1234), strict=True)
+    m = m.eval().cuda()
+    with torch.no_grad():
+        z, mq, logs, xm = m(x.cuda(), mask.cuda(), cond.cuda(), eps=torch.zeros(B, lat, 1).cuda())
+    for name, t in (('m', mq), ('logs', logs)):
+        ref = g[name]
+        rel = float(np.abs(t.cpu().numpy() - ref).max() / np.abs(ref).max())
+        assert rel < (5e-5 if precision == 'fp32' else 2e-4), (name, rel)
+    assert torch.equal(z, mq) and np.array_equal(xm.sum(-1).cpu().numpy(), g['mask_len'])

@@ -295,3 +295,26 @@ def test_fvae_decoder_oracle_matches_reference_fixture(golden_dir):
         with torch.no_grad():
             y = OW.fvae_decoder_forward(w, H, K, L, 4, z, mask if glob else 1, cond, bool(glob)).numpy()
         assert float(np.abs(y - g[f'{name}/y']).max()) <= 1e-5 * float(np.abs(g[f'{name}/y']).max()), name
+
+
+def _fvae_encoder_inputs(g):
+    cin, H, lat, K, L, gin, B, T = [int(v) for v in g['params']]
+    rs = np.random.RandomState(1234 + 11)
+    x = torch.from_numpy(rs.randn(B, cin, T).astype(np.float32))
+    mask = torch.ones(B, 1, T)
+    mask[1, :, T - 36:] = 0
+    cond = torch.from_numpy(rs.randn(B, gin, T // 4).astype(np.float32))
+    return (cin, H, lat, K, L, gin, B, T), x * mask, mask, cond
+
+
+def test_fvae_encoder_oracle_matches_reference_fixture(golden_dir):
+    """oracle/fs2_vae.py:global_fvae_encoder_forward against the reference GlobalFVAEEncoder (tests/golden/fvae_encoder.npz)."""
+    from oracle import fs2_vae as OW
+    g = np.load(os.path.join(golden_dir, 'fvae_encoder.npz'))
+    (cin, H, lat, K, L, gin, B, T), x, mask, cond = _fvae_encoder_inputs(g)
+    w = OW.fold_weight_norm(S.make_fvae_encoder_state_dict(cin, H, lat, K, L, gin, 4, 1234))
+    with torch.no_grad():
+        z, m, logs, xm = OW.global_fvae_encoder_forward(w, H, lat, K, L, 4, x, mask, cond, torch.zeros(B, lat, 1))
+    for name, t in (('m', m), ('logs', logs)):
+        assert float((t - torch.from_numpy(g[name])).abs().max()) <= 2e-5 * float(np.abs(g[name]).max()), name
+    assert np.array_equal(xm.sum(-1).numpy(), g['mask_len'])
