@@ -902,6 +902,12 @@ int launch_conv_tc(const TcWeights &w, const ConvArgs &a, int precision, cudaStr
     return tc_dispatch(p, precision, grid, smem, st);
 }
 
+// whether `n` layers of this shape class fit one merged launch: the per-CTA item list lives in shared memory
+bool tc_merge_fits(int n, int B, int Tq, int Cout, int n_tile) {
+    const int tiles = (Tq + kTcM - 1) / kTcM, groups = (tiles + 1) / 2 * B * std::max(1, Cout / std::max(1, n_tile));
+    return (long long)groups * n <= (long long)(kMaxItems * 8 / 10) * sm_count();
+}
+
 // ---- merged launches: several layers of one shape class, host-built balanced work list
 void tc_worklist_free(TcWorkList *wl) {
     if (wl->items) cudaFree(wl->items);

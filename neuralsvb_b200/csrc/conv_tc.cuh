@@ -36,6 +36,8 @@ struct TcWorkList {
 };
 int tc_worklist_build(int n, const TcWeights *const *w, const ConvArgs *a, int precision, bool chain_ordered, TcWorkList *out);
 void tc_worklist_free(TcWorkList *wl);
+// the per-CTA item list of a merged launch is bounded (shared memory): very long batches fall back to one launch per layer
+bool tc_merge_fits(int n, int B, int Tq, int Cout, int n_tile);
 // one persistent launch over `n` layers that share channels / rows / upsampling (taps, dilation and pointers may differ)
 int launch_conv_tc_multi(int n, const TcWeights *const *w, const ConvArgs *a, int precision, cudaStream_t st, const TcWorkList &wl);
 // max_ctas > 0 caps the persistent grid (used to run independent ResBlock chains side by side on SM subsets)

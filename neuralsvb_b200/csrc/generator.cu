@@ -277,7 +277,8 @@ int forward_impl(svb_gen *g, const float *mel, bool mel_frame_major, const float
         const bool par = g->chains > 1 && nk > 1 && nk <= 3 && g->cfg.precision != SVB_PREC_FP32 && !g->profile;
         const int sms = 148;
         // merged schedule: step m of all nk chains in ONE persistent launch (the chains only share their input)
-        bool merged = g->merge && !par && nk > 1 && nk <= kTcMaxLayers && g->cfg.precision != SVB_PREC_FP32;
+        bool merged = g->merge && !par && nk > 1 && nk <= kTcMaxLayers && g->cfg.precision != SVB_PREC_FP32 &&
+                      s.c1[0][0].tc.ok && tc_merge_fits(nk, B, Ti, s.C, s.c1[0][0].tc.n_tile);
         for (int j = 0; merged && j < nk; ++j)
             for (int m = 0; m < nd; ++m) {
                 ConvArgs probe;

@@ -82,3 +82,21 @@ def test_errors_surface_as_exceptions_not_fallbacks():
         m(mel.cuda(), f0.cuda())              # f0 given to a non-NSF model: the reference would crash too
     with pytest.raises(RuntimeError, match='CUDA tensors'):
         m(mel)
+
+
+def test_long_batch_falls_back_from_merged_launches(monkeypatch):
+    """8 clips x 689 frames (cfg 5's clip length) has more work items per SM than a merged launch's list holds in the last stage:
+    that stage runs one launch per layer, the others stay merged -- and the result is BIT-IDENTICAL to the all-unmerged schedule
+    (the chain-ordered accumulation adds the three ResBlocks in the same order as three consecutive launches)."""
+    h = S.hifigan_config()
+    B, T = 8, 689
+    mel, f0 = S.make_mel_f0(B, T, U.SEED)
+    ri, nz = S.make_nsf_noise(B, T * 256, U.SEED)
+    args = (mel.cuda(), f0.cuda())
+    kw = dict(rand_ini=ri.cuda(), noise=nz.cuda())
+    with torch.no_grad():
+        y_merged = _model(h)(*args, **kw).clone()
+        monkeypatch.setenv('SVB_MERGE', '0')
+        y_plain = _model(h)(*args, **kw).clone()
+    assert torch.isfinite(y_merged).all()
+    assert torch.equal(y_merged, y_plain)
