@@ -436,6 +436,25 @@ class DiscriminatorP(nn.Module):
         return torch.flatten(x, 1, -1), fmap
 
 
+BATCH_PAIRS = True       # run d(y) and d(y_hat) of a discriminator as ONE pass over [y; y_hat] when no input gradient is needed
+
+
+def _pair_forward(d, y, y_hat, mel, stateful=False):
+    """The reference runs every sub-discriminator twice, on y and on y_hat (hifigan.py:242-248, 314-323).  Convolutions act
+    per sample, so when neither signal needs a gradient (the D step: y_hat is detached; inference) both run as one batch of 2B --
+    half the launches, twice the rows per launch for the short late layers.  Not used when y_hat carries a gradient (the G step
+    would pay the data gradient of the y half too) or for a module whose forward updates state per call (`stateful`: the
+    spectral-norm power iteration of MSD[0] in training mode, hifigan.py:261,294)."""
+    if (BATCH_PAIRS and not stateful and y.shape == y_hat.shape and
+            not (torch.is_grad_enabled() and (y.requires_grad or y_hat.requires_grad))):
+        B = y.shape[0]
+        out, fmap = d(torch.cat([y, y_hat], 0), None if mel is None else torch.cat([mel, mel], 0))
+        return out[:B], [f[:B] for f in fmap], out[B:], [f[B:] for f in fmap]
+    r, fr = d(y, mel)
+    g, fg = d(y_hat, mel)
+    return r, fr, g, fg
+
+
 class MultiPeriodDiscriminator(nn.Module):
     def __init__(self, use_cond=False, c_in=1):
         super().__init__()
@@ -444,8 +463,7 @@ class MultiPeriodDiscriminator(nn.Module):
     def forward(self, y, y_hat, mel=None):
         y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
         for d in self.discriminators:
-            r, fr = d(y, mel)
-            g, fg = d(y_hat, mel)
+            r, fr, g, fg = _pair_forward(d, y, y_hat, mel)
             y_d_rs.append(r), fmap_rs.append(fr), y_d_gs.append(g), fmap_gs.append(fg)
         return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
@@ -498,8 +516,7 @@ class MultiScaleDiscriminator(nn.Module):
         for i, d in enumerate(self.discriminators):
             if i != 0:
                 y, y_hat = avg_pool_4_2_1(y), avg_pool_4_2_1(y_hat)
-            r, fr = d(y, mel)
-            g, fg = d(y_hat, mel)
+            r, fr, g, fg = _pair_forward(d, y, y_hat, mel, stateful=(i == 0 and self.training))
             y_d_rs.append(r), fmap_rs.append(fr), y_d_gs.append(g), fmap_gs.append(fg)
         return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
