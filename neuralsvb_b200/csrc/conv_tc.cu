@@ -993,6 +993,28 @@ int tc_worklist_build(int n, const TcWeights *const *w, const ConvArgs *a, int p
             if (X.b != Y.b) return X.b < Y.b;
             return X.t0 < Y.t0;
         });
+        const char *il = getenv("SVB_TC_INTERLEAVE");
+        if (!chain_ordered && n > 1 && !(il && atoi(il) == 0)) {
+            // alternate the layers inside a CTA (long and short items interleaved) instead of layer after layer: the slab
+            // prefetch of a short-kernel item hides behind the MMAs of a long one (measured: 4.67 -> 4.62 ms per forward)
+            std::vector<std::vector<int>> by(n);
+            for (int u : mine[c]) by[units[u].layer].push_back(u);
+            std::vector<int> order;
+            std::vector<size_t> pos(n, 0);
+            const size_t total = mine[c].size();
+            while (order.size() < total) {
+                // take from the layer that is furthest behind its proportional share
+                int best = -1;
+                double lag = -1e30;
+                for (int l = 0; l < n; ++l) {
+                    if (pos[l] >= by[l].size()) continue;
+                    const double want = (double)(order.size() + 1) * by[l].size() / total - (double)pos[l];
+                    if (want > lag) lag = want, best = l;
+                }
+                order.push_back(by[best][pos[best]++]);
+            }
+            mine[c] = order;
+        }
         for (int u : mine[c]) {
             const Unit &U = units[u];
             for (int l = (U.layer < 0 ? 0 : U.layer); l < (U.layer < 0 ? n : U.layer + 1); ++l)
