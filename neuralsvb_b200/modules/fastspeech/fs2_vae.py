@@ -245,3 +245,40 @@ class GlobalFVAEEncoder(nn.Module):
         m, logs = torch.split(x, self.latent_channels, dim=1)                                           # :103
         z = m + (torch.randn_like(m) if eps is None else eps) * torch.exp(logs)                         # :104
         return z, m, logs, x_mask
+
+
+class GlobalFVAE(nn.Module):
+    """``modules/voice_conversion/vae_models.py:130-146`` (GlobalFVAE over TMPFVAE :11-52, FVAE fs2_vae.py:155-178) without the
+    optional prior flow (``use_prior_glow: false`` in vae_global_mle_eng): ``g_pre_net`` strided conv on the condition, the global
+    posterior encoder and the mel decoder -- every convolution native.  ``forward(x, x_mask, g, infer)`` returns what the reference
+    returns; the KL term is computed in torch on the [B, latent, 1] statistics.  Inference / evaluation only."""
+
+    def __init__(self, in_out_channels, hidden_channels, latent_size, kernel_size, enc_n_layers, dec_n_layers, gin_channels, strides,
+                 use_prior_glow=False, glow_hidden=None, glow_kernel_size=None, glow_n_blocks=None, precision='bf16x3'):
+        super().__init__()
+        if use_prior_glow:
+            raise NotImplementedError('GlobalFVAE(use_prior_glow=True): the prior flow is not part of the SVB configuration')
+        self.strides, self.hidden_size, self.latent_size, self.use_prior_glow = list(strides), hidden_channels, latent_size, False
+        self.g_pre_net = nn.Sequential(*[nn.Conv1d(gin_channels, gin_channels, kernel_size=s * 2, stride=s, padding=s // 2) for s in strides])
+        self.encoder = GlobalFVAEEncoder(in_out_channels, hidden_channels, latent_size, kernel_size, enc_n_layers, gin_channels,
+                                         strides=strides, precision=precision)
+        self.decoder = GlobalFVAEDecoder(latent_size, hidden_channels, in_out_channels, kernel_size, dec_n_layers, gin_channels,
+                                         strides=strides, precision=precision)
+
+    def forward(self, x=None, x_mask=None, g=None, infer=False, eps=None):
+        from neuralsvb_b200.modules.hifigan.discriminators import conv_nct
+        g_sqz = g
+        for c in self.g_pre_net:                                                                        # vae_models.py:20
+            g_sqz = conv_nct(g_sqz.float(), c.weight, c.bias, c.kernel_size[0], stride=c.stride[0], pad=c.padding[0])
+        if infer:                                                                                       # :45-52
+            # the reference samples [B, latent, T / 4] here and its GlobalFVAEDecoder then repeats that T / 4 times (a shape
+            # error: the SVB task never takes this branch, it calls vae_model.decoder directly, svb_vae.py:303); a GLOBAL
+            # latent has one time step
+            z_p = torch.randn(g_sqz.shape[0], self.latent_size, 1, device=g.device) if eps is None else eps
+            return self.decoder(z_p, 1, g), z_p
+        z_q, m_q, logs_q, x_mask_sqz = self.encoder(x, x_mask, g_sqz, eps=eps)                          # :22
+        x_recon = self.decoder(z_q, x_mask, g)                                                          # :23
+        q_dist = torch.distributions.Normal(m_q, logs_q.exp())
+        loss_kl = torch.distributions.kl_divergence(q_dist, torch.distributions.Normal(0, 1))          # :38-39
+        loss_kl = (loss_kl * x_mask_sqz).sum() / x_mask_sqz.sum() / z_q.shape[1]
+        return x_recon, loss_kl, None, m_q, logs_q, x_mask_sqz, z_q

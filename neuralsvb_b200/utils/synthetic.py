@@ -319,3 +319,17 @@ def make_fvae_encoder_state_dict(in_channels=80, hidden=192, latent=128, kernel_
         sd[f'poolings.{i}.running_var'] = t(rs.uniform(0.05, 0.5, c2).astype(np.float32))
         sd[f'poolings.{i}.num_batches_tracked'] = torch.tensor(100)
     return sd
+
+
+def make_global_fvae_state_dict(in_out=80, hidden=192, latent=128, kernel_size=5, enc_layers=8, dec_layers=4, gin=256, stride=4, seed=1234):
+    """state_dict of the reference's GlobalFVAE (vae_models.py:130-146): ``g_pre_net.0.*``, ``encoder.*``, ``decoder.*``."""
+    rs = np.random.RandomState(seed + 21)
+    sd = OrderedDict()
+    b = 1.0 / np.sqrt(gin * 2 * stride)
+    sd['g_pre_net.0.weight'] = torch.from_numpy(_uniform(rs, (gin, gin, 2 * stride), b))
+    sd['g_pre_net.0.bias'] = torch.from_numpy(_uniform(rs, (gin,), b))
+    for k, v in make_fvae_encoder_state_dict(in_out, hidden, latent, kernel_size, enc_layers, gin, stride, seed).items():
+        sd[f'encoder.{k}'] = v
+    for k, v in make_fvae_decoder_state_dict(latent, hidden, in_out, kernel_size, dec_layers, gin, stride, seed).items():
+        sd[f'decoder.{k}'] = v
+    return sd

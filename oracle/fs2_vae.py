@@ -69,3 +69,14 @@ def global_fvae_encoder_forward(w, hidden, latent, kernel_size, n_layers, stride
     x = torch.mean(x, dim=-1, keepdim=True)
     m, logs = torch.split(x, latent, dim=1)
     return m + eps * torch.exp(logs), m, logs, x_mask
+
+
+def global_fvae_forward(w, in_out, hidden, latent, kernel_size, enc_layers, dec_layers, stride, x, x_mask, g, eps):
+    """GlobalFVAE.forward(..., infer=False) (vae_models.py:11-44 via :130-146) in eval mode, ``eps`` in place of randn_like."""
+    g_sqz = F.conv1d(g, w['g_pre_net.0.weight'], w['g_pre_net.0.bias'], stride=stride, padding=stride // 2)
+    enc = {k[8:]: v for k, v in w.items() if k.startswith('encoder.')}
+    dec = {k[8:]: v for k, v in w.items() if k.startswith('decoder.')}
+    z_q, m_q, logs_q, xm = global_fvae_encoder_forward(enc, hidden, latent, kernel_size, enc_layers, stride, x, x_mask, g_sqz, eps)
+    x_recon = fvae_decoder_forward(dec, hidden, kernel_size, dec_layers, stride, z_q, x_mask, g, True)
+    kl = torch.distributions.kl_divergence(torch.distributions.Normal(m_q, logs_q.exp()), torch.distributions.Normal(0, 1))
+    return x_recon, (kl * xm).sum() / xm.sum() / z_q.shape[1], m_q, logs_q

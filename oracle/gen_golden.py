@@ -437,6 +437,38 @@ def gen_fvae_encoder():
     print('fvae_encoder.npz', {k: v.shape for k, v in out.items()})
 
 
+def gen_global_fvae():
+    """x_recon / loss_kl / m_q / logs_q of the reference GlobalFVAE (vae_models.py:130-146, TMPFVAE.forward :11-44) in eval mode with the
+    posterior noise replaced by zeros (z_q = m_q), at the vae_global_mle_eng sizes."""
+    R.install()
+    import contextlib
+    import io
+    from modules.voice_conversion.vae_models import GlobalFVAE
+    io_c, H, lat, K, Le, Ld, gin, B, T = 80, 192, 128, 5, 8, 4, 256, 2, 240
+    sd = S.make_global_fvae_state_dict(io_c, H, lat, K, Le, Ld, gin, 4, SEED)
+    rs = np.random.RandomState(SEED + 23)
+    x = torch.from_numpy(rs.randn(B, io_c, T).astype(np.float32))
+    mask = torch.ones(B, 1, T)
+    mask[1, :, T - 40:] = 0
+    g = torch.from_numpy(rs.randn(B, gin, T).astype(np.float32))
+    m = GlobalFVAE(io_c, H, lat, K, Le, Ld, gin, [4], False)
+    m.load_state_dict(sd, strict=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.encoder.wn.remove_weight_norm(), m.decoder.wn.remove_weight_norm()
+    m.eval()
+    orig = torch.randn_like
+    torch.randn_like = lambda t, **k: torch.zeros_like(t)
+    try:
+        with torch.no_grad():
+            x_recon, loss_kl, _, m_q, logs_q, xm, z_q = m(x * mask, mask, g, infer=False)
+    finally:
+        torch.randn_like = orig
+    out = {'x_recon': x_recon.numpy(), 'loss_kl': np.float64(loss_kl), 'm_q': m_q.numpy(), 'logs_q': logs_q.numpy(),
+           'params': np.array([io_c, H, lat, K, Le, Ld, gin, B, T], np.int64)}
+    np.savez_compressed(os.path.join(OUT, 'global_fvae.npz'), **out)
+    print('global_fvae.npz', {k: np.shape(v) for k, v in out.items()})
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
@@ -444,7 +476,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
     which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond', 'generator_extra',
-                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder', 'fvae_encoder']
+                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder', 'fvae_encoder', 'global_fvae']
     for w in which:
         globals()[f'gen_{w}']()
 

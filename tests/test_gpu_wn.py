@@ -98,3 +98,22 @@ def test_global_fvae_encoder_matches_reference_fixture(precision):
         rel = float(np.abs(t.cpu().numpy() - ref).max() / np.abs(ref).max())
         assert rel < (5e-5 if precision == 'fp32' else 2e-4), (name, rel)
     assert torch.equal(z, mq) and np.array_equal(xm.sum(-1).cpu().numpy(), g['mask_len'])
+
+
+def test_global_fvae_matches_reference_fixture():
+    """The whole GlobalFVAE (vae_models.py:130-146) at the vae_global_mle_eng sizes: reconstruction, KL, posterior statistics."""
+    from neuralsvb_b200.modules.fastspeech.fs2_vae import GlobalFVAE
+    from tests.test_oracle_golden import _global_fvae_inputs
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'global_fvae.npz'))
+    (io_c, H, lat, K, Le, Ld, gin, B, T), x, mask, cond = _global_fvae_inputs(g)
+    m = GlobalFVAE(io_c, H, lat, K, Le, Ld, gin, [4], False)
+    m.load_state_dict(S.make_global_fvae_state_dict(io_c, H, lat, K, Le, Ld, gin, 4, 1234), strict=True)
+    m = m.eval().cuda()
+    with torch.no_grad():
+        xr, kl, _, m_q, logs_q, xm, z_q = m(x.cuda(), mask.cuda(), cond.cuda(), infer=False, eps=torch.zeros(B, lat, 1).cuda())
+        mel, z_p = m(g=cond.cuda(), infer=True)
+    rel = float(np.abs(xr.cpu().numpy() - g['x_recon']).max() / np.abs(g['x_recon']).max())
+    assert rel < 1e-3 and rel < 3e-4, rel                      # north-star: 1e-3 relative L-inf on mel frames
+    assert abs(float(kl) - float(g['loss_kl'])) < 1e-3 * abs(float(g['loss_kl']))
+    assert float(np.abs(m_q.cpu().numpy() - g['m_q']).max() / np.abs(g['m_q']).max()) < 2e-4
+    assert tuple(mel.shape) == (B, io_c, T) and tuple(z_p.shape) == (B, lat, 1) and torch.isfinite(mel).all()

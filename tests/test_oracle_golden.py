@@ -318,3 +318,25 @@ def test_fvae_encoder_oracle_matches_reference_fixture(golden_dir):
     for name, t in (('m', m), ('logs', logs)):
         assert float((t - torch.from_numpy(g[name])).abs().max()) <= 2e-5 * float(np.abs(g[name]).max()), name
     assert np.array_equal(xm.sum(-1).numpy(), g['mask_len'])
+
+
+def _global_fvae_inputs(g):
+    io_c, H, lat, K, Le, Ld, gin, B, T = [int(v) for v in g['params']]
+    rs = np.random.RandomState(1234 + 23)
+    x = torch.from_numpy(rs.randn(B, io_c, T).astype(np.float32))
+    mask = torch.ones(B, 1, T)
+    mask[1, :, T - 40:] = 0
+    cond = torch.from_numpy(rs.randn(B, gin, T).astype(np.float32))
+    return (io_c, H, lat, K, Le, Ld, gin, B, T), x * mask, mask, cond
+
+
+def test_global_fvae_oracle_matches_reference_fixture(golden_dir):
+    """oracle/fs2_vae.py:global_fvae_forward against the reference GlobalFVAE (tests/golden/global_fvae.npz)."""
+    from oracle import fs2_vae as OW
+    g = np.load(os.path.join(golden_dir, 'global_fvae.npz'))
+    (io_c, H, lat, K, Le, Ld, gin, B, T), x, mask, cond = _global_fvae_inputs(g)
+    w = OW.fold_weight_norm(S.make_global_fvae_state_dict(io_c, H, lat, K, Le, Ld, gin, 4, 1234))
+    with torch.no_grad():
+        xr, kl, m, logs = OW.global_fvae_forward(w, io_c, H, lat, K, Le, Ld, 4, x, mask, cond, torch.zeros(B, lat, 1))
+    assert float((xr - torch.from_numpy(g['x_recon'])).abs().max()) <= 2e-5 * float(np.abs(g['x_recon']).max())
+    assert abs(float(kl) - float(g['loss_kl'])) <= 1e-5 * abs(float(g['loss_kl']))
