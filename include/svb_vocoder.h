@@ -354,6 +354,17 @@ int svb_fvae_decoder_create(int32_t latent_channels, int32_t hidden_channels, in
 int svb_fvae_decoder_forward(svb_wn_t *w, const float *z_dev, const float *mask_dev, const float *g_dev, int32_t B, int32_t T,
                              float *out_dev, void *stream);
 
+/* ---- PPG extractor (VCASR, modules/voice_conversion/vc_modules.py:56-80) pieces that are not convolutions, on [B, C, T] tensors.
+ * nn.LayerNorm(C) of EncoderLayer (modules/fastspeech/conformer/layers.py:167-178): statistics over the channel axis per (b, t). */
+int svb_layer_norm_nct(const float *x_dev, const float *gamma_dev, const float *beta_dev, int32_t B, int32_t C, int32_t T, float eps,
+                       float *y_dev, void *stream);
+/* RelPositionMultiHeadedAttention.forward after its linear projections (modules/commons/espnet_transformer_attn.py:147-186, with
+ * rel_shift :127-145 and forward_attention :59-88): q, k, v [B, C, T] (head h = channels [h*dk, (h+1)*dk)), p = linear_pos(pos_emb)
+ * [C, T], pos_bias_u / pos_bias_v [n_head * dk], mask [B, T] (0 = padded key; NULL = none) -> context [B, C, T] (before linear_out). */
+int svb_relpos_attention_nct(const float *q_dev, const float *k_dev, const float *v_dev, const float *p_dev, const float *bias_u_dev,
+                             const float *bias_v_dev, const float *mask_dev, int32_t B, int32_t C, int32_t T, int32_t n_head,
+                             float *out_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -333,3 +333,63 @@ def make_global_fvae_state_dict(in_out=80, hidden=192, latent=128, kernel_size=5
     for k, v in make_fvae_decoder_state_dict(latent, hidden, in_out, kernel_size, dec_layers, gin, stride, seed).items():
         sd[f'decoder.{k}'] = v
     return sd
+
+
+def make_vc_asr_state_dict(seed=1234, hidden=256, n_mel=80, n_layers=2, n_head=4, K=31):
+    """state_dict of the encoder half of the reference's VCASR (vc_modules.py:56-75): ``mel_prenet.*`` (Prenet, pe.py:7-22) and
+    ``content_encoder.*`` (ConformerLayers with asr_last_norm false: the last ``layer_norm`` is a Linear).  BatchNorm layers get
+    non-trivial running statistics, LayerNorms non-trivial affine parameters."""
+    rs = np.random.RandomState(seed + 31)
+    sd = OrderedDict()
+
+    def t(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+    def lin(prefix, cout, cin, k=None, bias=True):
+        shape = (cout, cin) if k is None else (cout, cin, k)
+        b = 1.0 / np.sqrt(cin * (k or 1))
+        sd[prefix + '.weight'] = t(_uniform(rs, shape, b))
+        if bias:
+            sd[prefix + '.bias'] = t(_uniform(rs, (cout,), b))
+
+    def bn(prefix, c):
+        sd[prefix + '.weight'], sd[prefix + '.bias'] = t(rs.uniform(0.5, 1.5, c)), t(_uniform(rs, (c,), 0.2))
+        sd[prefix + '.running_mean'], sd[prefix + '.running_var'] = t(_uniform(rs, (c,), 0.1)), t(rs.uniform(0.2, 1.0, c))
+        sd[prefix + '.num_batches_tracked'] = torch.tensor(100)
+
+    def ln(prefix, c):
+        sd[prefix + '.weight'], sd[prefix + '.bias'] = t(rs.uniform(0.7, 1.3, c)), t(_uniform(rs, (c,), 0.1))
+    cin = n_mel
+    for i in range(3):
+        lin(f'mel_prenet.layers.{i}.0', hidden, cin, 5)
+        bn(f'mel_prenet.layers.{i}.2', hidden)
+        cin = hidden
+    lin('mel_prenet.out_proj', hidden, hidden)
+    for l in range(n_layers):
+        e = f'content_encoder.encoder_layers.{l}'
+        for name in ('linear_q', 'linear_k', 'linear_v', 'linear_out'):
+            lin(f'{e}.self_attn.{name}', hidden, hidden)
+        lin(f'{e}.self_attn.linear_pos', hidden, hidden, bias=False)
+        sd[f'{e}.self_attn.pos_bias_u'] = t(_uniform(rs, (n_head, hidden // n_head), 0.1))
+        sd[f'{e}.self_attn.pos_bias_v'] = t(_uniform(rs, (n_head, hidden // n_head), 0.1))
+        for ff in ('feed_forward', 'feed_forward_macaron'):
+            lin(f'{e}.{ff}.w_1', 4 * hidden, hidden, 1)
+            lin(f'{e}.{ff}.w_2', hidden, 4 * hidden, 1)
+        lin(f'{e}.conv_module.pointwise_conv1', 2 * hidden, hidden, 1)
+        lin(f'{e}.conv_module.depthwise_conv', hidden, 1, K)
+        bn(f'{e}.conv_module.norm', hidden)
+        lin(f'{e}.conv_module.pointwise_conv2', hidden, hidden, 1)
+        for name in ('norm_ff', 'norm_mha', 'norm_ff_macaron', 'norm_conv', 'norm_final'):
+            ln(f'{e}.{name}', hidden)
+    lin('content_encoder.layer_norm', hidden, hidden)
+    return sd
+
+
+def make_vc_asr_mel(B, T, seed=1234, n_mel=80):
+    """mel [B, T, 80] in the log10-mel range; clip b ends 9 b frames early (all-zero frames = padding, pe.py:30)."""
+    rs = np.random.RandomState(seed + 37)
+    mel = torch.from_numpy((rs.randn(B, T, n_mel) * 1.2 - 2.5).clip(-6, 1.5).astype(np.float32))
+    for b in range(B):
+        if b:
+            mel[b, T - 9 * b:] = 0.0
+    return mel

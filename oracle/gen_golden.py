@@ -469,6 +469,28 @@ def gen_global_fvae():
     print('global_fvae.npz', {k: np.shape(v) for k, v in out.items()})
 
 
+def gen_vc_asr():
+    """h_content of the reference VCASR (vc_modules.py:56-80; hidden 256, mel_strides [2, 1, 1], 2 conformer layers, asr_last_norm false)
+    in eval mode on a random-init model whose state_dict is stored seed-reproducibly by neuralsvb_b200/utils/synthetic.py."""
+    R.install()
+    from utils.hparams import hparams
+    hparams.update({'hidden_size': 256, 'asr_enc_layers': 2, 'asr_dec_layers': 2, 'mel_strides': [2, 1, 1], 'asr_enc_type': 'conformer',
+                    'asr_last_norm': False, 'dropout': 0.1, 'enc_ffn_kernel_size': 9, 'num_heads': 2, 'enc_layers': 4, 'dec_layers': 4,
+                    'ffn_hidden_size': 1024, 'ffn_padding': 'SAME', 'ffn_act': 'gelu', 'dec_ffn_kernel_size': 9, 'use_pos_embed': True})
+    from modules.voice_conversion.vc_modules import VCASR
+    m = VCASR(80, 80)
+    sd = S.make_vc_asr_state_dict(SEED)
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all(k.startswith(('asr_decoder', 'token_embed')) for k in missing.missing_keys), missing
+    m.eval()
+    mel = S.make_vc_asr_mel(2, 157, SEED)
+    with torch.no_grad():
+        h = m(mel)['h_content']
+    out = {'h_content': h.numpy(), 'params': np.array([2, 157], np.int64)}
+    np.savez_compressed(os.path.join(OUT, 'vc_asr.npz'), **out)
+    print('vc_asr.npz', h.shape, float(h.abs().max()))
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
@@ -476,7 +498,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
     which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond', 'generator_extra',
-                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder', 'fvae_encoder', 'global_fvae']
+                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder', 'fvae_encoder', 'global_fvae', 'vc_asr']
     for w in which:
         globals()[f'gen_{w}']()
 

@@ -340,3 +340,13 @@ def test_global_fvae_oracle_matches_reference_fixture(golden_dir):
         xr, kl, m, logs = OW.global_fvae_forward(w, io_c, H, lat, K, Le, Ld, 4, x, mask, cond, torch.zeros(B, lat, 1))
     assert float((xr - torch.from_numpy(g['x_recon'])).abs().max()) <= 2e-5 * float(np.abs(g['x_recon']).max())
     assert abs(float(kl) - float(g['loss_kl'])) <= 1e-5 * abs(float(g['loss_kl']))
+
+
+def test_vc_asr_oracle_matches_reference_fixture(golden_dir):
+    """oracle/vc_asr.py against h_content of the reference VCASR (tests/golden/vc_asr.npz): Prenet + 2 conformer layers."""
+    from oracle import vc_asr as OV
+    g = np.load(os.path.join(golden_dir, 'vc_asr.npz'))
+    B, T = [int(v) for v in g['params']]
+    with torch.no_grad():
+        h = OV.vc_asr_h_content(S.make_vc_asr_state_dict(1234), S.make_vc_asr_mel(B, T, 1234))
+    assert float((h - torch.from_numpy(g['h_content'])).abs().max()) <= 1e-5 * float(np.abs(g['h_content']).max())
