@@ -393,3 +393,69 @@ def make_vc_asr_mel(B, T, seed=1234, n_mel=80):
         if b:
             mel[b, T - 9 * b:] = 0.0
     return mel
+
+
+def make_svb_state_dict(seed=1234, hidden=256, latent=128, n_mel=80):
+    """state_dict of the reference's MleSVBVAE (modules/voice_conversion/svb_vae.py:13-56,178-199,251-256) at the
+    vae_global_mle_eng sizes, without the ASR token decoder (``vc_asr.asr_decoder.*``, ``vc_asr.token_embed.*``: training heads)."""
+    rs = np.random.RandomState(seed + 41)
+    sd = OrderedDict()
+
+    def t(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+    def lin(prefix, cout, cin, k=None):
+        shape = (cout, cin) if k is None else (cout, cin, k)
+        b = 1.0 / np.sqrt(cin * (k or 1))
+        sd[prefix + '.weight'], sd[prefix + '.bias'] = t(_uniform(rs, shape, b)), t(_uniform(rs, (cout,), b))
+
+    def bn(prefix, c):
+        sd[prefix + '.weight'], sd[prefix + '.bias'] = t(rs.uniform(0.5, 1.5, c)), t(_uniform(rs, (c,), 0.2))
+        sd[prefix + '.running_mean'], sd[prefix + '.running_var'] = t(_uniform(rs, (c,), 0.1)), t(rs.uniform(0.2, 1.0, c))
+        sd[prefix + '.num_batches_tracked'] = torch.tensor(100)
+    emb = _normal(rs, (300, hidden), hidden ** -0.5)
+    emb[0] = 0
+    sd['pitch_embed.weight'] = t(emb)
+    lin('pitch_encoder.in_proj', hidden, hidden)
+    for i in range(3):
+        lin(f'pitch_encoder.conv.{i}.conv.conv', hidden, hidden, 5)
+        sd[f'pitch_encoder.conv.{i}.norm.weight'], sd[f'pitch_encoder.conv.{i}.norm.bias'] = t(rs.uniform(0.7, 1.3, hidden)), t(_uniform(rs, (hidden,), 0.1))
+    lin('pitch_encoder.out_proj', hidden, hidden)
+    for k, v in make_vc_asr_state_dict(seed, hidden, n_mel).items():
+        sd[f'vc_asr.{k}'] = v
+    lin('upsample_layer.0.1', hidden, hidden, 5)
+    bn('upsample_layer.0.3', hidden)
+    lin('upsample_layer.1', hidden, hidden, 5)
+    lin('spk_embed_proj', hidden, 256)
+    lin('encoded_embed_proj', hidden, 3 * hidden)
+    for k, v in make_global_fvae_state_dict(n_mel, 192, latent, 5, 8, 4, hidden, 4, seed).items():
+        sd[f'vae_model.{k}'] = v
+    for i in (0, 3, 6):
+        lin(f'z_mapping_function.convs.{i}', latent, latent, 1)
+    for i in (1, 4):
+        bn(f'z_mapping_function.convs.{i}', latent)
+    lin('z_mapping_function.spk_proj.0', latent, 256, 1)
+    lin('z_mapping_function.spk_proj.2', latent, latent, 1)
+    return sd
+
+
+def make_svb_batch(B=2, Ta=96, Tp=120, seed=1234, n_mel=80):
+    """A PopBuTFy-shaped batch (SURVEY 8(d) cfg 4 / 5): amateur / professional mels [B, T, 80] (zero frames = padding), coarse pitch
+    ids in [1, 255] (0 = padding), one speaker embedding [B, 256], the a2p alignment [B, Tp] into the amateur frames."""
+    rs = np.random.RandomState(seed + 43)
+
+    def mel(T, short):
+        m = (rs.randn(B, T, n_mel) * 1.2 - 2.5).clip(-6, 1.5).astype(np.float32)
+        m[B - 1, T - short:] = 0.0
+        return torch.from_numpy(m)
+
+    def pitch(T, short):
+        p = rs.randint(1, 256, size=(B, T))
+        p[B - 1, T - short:] = 0
+        return torch.from_numpy(p.astype(np.int64))
+    a_mel, p_mel = mel(Ta, 8), mel(Tp, 12)
+    a_pitch, p_pitch = pitch(Ta, 8), pitch(Tp, 12)
+    spk = torch.from_numpy(_normal(rs, (B, 256), 0.5))
+    align = torch.from_numpy(np.minimum((np.arange(Tp)[None, :] * Ta / Tp).astype(np.int64) + rs.randint(0, 2, size=(B, Tp)), Ta - 1))
+    return dict(amateur_mel=a_mel, prof_mel=p_mel, amateur_pitch=a_pitch, prof_pitch=p_pitch, amateur_spk_id=spk, prof_spk_id=spk,
+                a2p_alignment=align)

@@ -491,6 +491,44 @@ def gen_vc_asr():
     print('vc_asr.npz', h.shape, float(h.abs().max()))
 
 
+SVB_HPARAMS = {'hidden_size': 256, 'audio_num_mel_bins': 80, 'asr_enc_layers': 2, 'asr_dec_layers': 2, 'mel_strides': [2, 1, 1],
+               'asr_enc_type': 'conformer', 'asr_last_norm': False, 'dropout': 0.1, 'enc_ffn_kernel_size': 9, 'num_heads': 2,
+               'enc_layers': 4, 'dec_layers': 4, 'ffn_hidden_size': 1024, 'ffn_padding': 'SAME', 'ffn_act': 'gelu', 'dec_ffn_kernel_size': 9,
+               'use_pos_embed': True, 'latent_size': 128, 'fvae_enc_dec_hidden': 192, 'fvae_kernel_size': 5, 'fvae_enc_n_layers': 8,
+               'fvae_dec_n_layers': 4, 'frames_multiple': 4, 'use_prior_glow': False}
+
+
+def gen_svb_vae():
+    """a2a / p2p / a2p outputs of the reference MleSVBVAE (svb_vae.py:251-312) in eval mode at the vae_global_mle_eng sizes, posterior
+    noise replaced by zeros; also the name / shape listing of its state_dict (the drop-in class must expose the same keys)."""
+    R.install()
+    from utils.hparams import hparams
+    hparams.update(SVB_HPARAMS)
+    from modules.voice_conversion.svb_vae import MleSVBVAE
+    m = MleSVBVAE(80)
+    sd = S.make_svb_state_dict(SEED)
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith(('vc_asr.asr_decoder', 'vc_asr.token_embed')) for k in res.missing_keys), res
+    for wn in (m.vae_model.encoder.wn, m.vae_model.decoder.wn):
+        wn.remove_weight_norm()
+    m.eval()
+    batch = S.make_svb_batch(2, 96, 120, SEED)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, **k: torch.zeros_like(t)
+    try:
+        with torch.no_grad():
+            ret = m(**batch, infer=False, concurrent_ways=['a2a', 'p2p', 'a2p'])
+    finally:
+        torch.randn_like = orig
+    keys = [k for k in MleSVBVAE(80).state_dict().keys() if not k.startswith(('vc_asr.asr_decoder', 'vc_asr.token_embed'))]
+    shapes = MleSVBVAE(80).state_dict()
+    out = {'a2p_mel': ret['a2p']['mel_out'].numpy(), 'a2p_mle': np.float64(ret['a2p']['mle']), 'a2a_mel': ret['a2a']['mel_out'].numpy(),
+           'p2p_m_q': ret['p2p']['m_q'].numpy(), 'a2a_kl': np.float64(ret['a2a']['kl']),
+           'state_keys': np.array(keys), 'state_shapes': np.array([','.join(str(d) for d in shapes[k].shape) for k in keys])}
+    np.savez_compressed(os.path.join(OUT, 'svb_vae.npz'), **out)
+    print('svb_vae.npz', out['a2p_mel'].shape, float(np.abs(out['a2p_mel']).max()), len(keys), 'state keys')
+
+
 def main():
     if not R.available():
         sys.exit('gen_golden needs /root/reference (build container only)')
@@ -498,7 +536,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     warnings.simplefilter('ignore')
     which = sys.argv[1:] or ['frontend', 'generator', 'losses', 'discriminators', 'discriminators_cond', 'generator_extra',
-                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder', 'fvae_encoder', 'global_fvae', 'vc_asr']
+                             'generator_grads', 'losses_extra', 'discriminators_train', 'wn', 'fvae_decoder', 'fvae_encoder', 'global_fvae', 'vc_asr', 'svb_vae']
     for w in which:
         globals()[f'gen_{w}']()
 

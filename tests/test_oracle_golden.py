@@ -350,3 +350,28 @@ def test_vc_asr_oracle_matches_reference_fixture(golden_dir):
     with torch.no_grad():
         h = OV.vc_asr_h_content(S.make_vc_asr_state_dict(1234), S.make_vc_asr_mel(B, T, 1234))
     assert float((h - torch.from_numpy(g['h_content'])).abs().max()) <= 1e-5 * float(np.abs(g['h_content']).max())
+
+
+SVB_HP = {'hidden_size': 256, 'audio_num_mel_bins': 80, 'asr_enc_layers': 2, 'mel_strides': [2, 1, 1], 'asr_last_norm': False, 'latent_size': 128,
+          'fvae_enc_dec_hidden': 192, 'fvae_kernel_size': 5, 'fvae_enc_n_layers': 8, 'fvae_dec_n_layers': 4}
+
+
+def test_svb_vae_oracle_matches_reference_fixture(golden_dir):
+    """oracle/svb_vae.py (conditions + GlobalFVAE + latent map + a2p decode) against the reference MleSVBVAE (tests/golden/svb_vae.npz)."""
+    from oracle import svb_vae as OS
+    g = np.load(os.path.join(golden_dir, 'svb_vae.npz'))
+    with torch.no_grad():
+        r = OS.mle_svb_vae_forward(S.make_svb_state_dict(1234), S.make_svb_batch(2, 96, 120, 1234))
+    for name, t in (('a2p_mel', r['a2p']['mel_out']), ('a2a_mel', r['a2a']['mel_out']), ('p2p_m_q', r['p2p']['m_q'])):
+        assert float((t - torch.from_numpy(g[name])).abs().max()) <= 1e-5 * float(np.abs(g[name]).max()), name
+    assert abs(float(r['a2p']['mle']) - float(g['a2p_mle'])) <= 1e-5 * abs(float(g['a2p_mle']))
+
+
+def test_svb_vae_drop_in_exposes_the_reference_state_dict(golden_dir):
+    """Same parameter / buffer names and shapes as the reference MleSVBVAE (minus the ASR token decoder, a training-time head)."""
+    from neuralsvb_b200.modules.voice_conversion.svb_vae import MleSVBVAE
+    g = np.load(os.path.join(golden_dir, 'svb_vae.npz'))
+    ref = {str(k): str(s) for k, s in zip(g['state_keys'], g['state_shapes'])}
+    mine = {k: ','.join(str(d) for d in v.shape) for k, v in MleSVBVAE(80, hp=SVB_HP).state_dict().items()}
+    assert mine == ref, (sorted(set(mine) ^ set(ref))[:10], [k for k in mine if k in ref and mine[k] != ref[k]][:10])
+    assert MleSVBVAE(80, hp=SVB_HP).load_state_dict(S.make_svb_state_dict(1234), strict=True) is not None
