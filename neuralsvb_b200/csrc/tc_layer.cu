@@ -10,6 +10,7 @@
 // Reference: the Conv2d((5,1),(3,1)) / Conv1d stacks of modules/hifigan/hifigan.py:193-199, :262-271 (layers with
 // groups == 1 and >= 32 channels: 98 % of the discriminators' FLOPs).
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "generator.cuh"
@@ -105,14 +106,20 @@ __global__ void gather_w_kernel(float *__restrict__ dst, const float *__restrict
         dst[i] = idx[i] ? nat[idx[i] - 1] : 0.f;
 }
 
-// one scratch arena per device, shared by every layer handle (calls are stream-ordered)
+// one scratch arena per device, shared by every layer handle.  Contract (include/svb_vocoder.h, "ownership / threading"): the
+// svb_tc_layer_* calls of one device are issued from ONE host thread on ONE stream -- the arena is reused by consecutive calls in
+// stream order and is not guarded against concurrent streams; the mutex below only keeps a (re)allocation from racing with another
+// thread's lookup.
 struct Arena {
     char *p = nullptr;
     size_t cap = 0;
 };
 Arena g_arena[16];
 
+std::mutex g_arena_mu;
+
 int arena_get(int device, size_t bytes, char **out) {
+    std::lock_guard<std::mutex> lock(g_arena_mu);
     Arena &a = g_arena[device & 15];
     if (bytes > a.cap) {
         if (a.p) {
