@@ -44,7 +44,17 @@ def layer_norm_nct(x, ln):
     return y
 
 
+_PE_CACHE = {}
+
+
 def rel_positions(T, H, device, max_len=5000):
+    key = (T, H, str(device), max_len)
+    if key not in _PE_CACHE:
+        _PE_CACHE[key] = _rel_positions(T, H, device, max_len)
+    return _PE_CACHE[key]
+
+
+def _rel_positions(T, H, device, max_len=5000):
     """The reference's RelPositionalEncoding table (espnet_positional_embedding.py:24-46,98-112) is built once for max_len = 5000
     reversed positions and sliced from the front: row n encodes position max_len-1-n.  Returned as [H, T]."""
     assert T <= max_len
@@ -103,8 +113,12 @@ class VCASR(nn.Module):
 
     def _attention(self, a, x, p_emb, key_mask):
         B, H, T = x.shape
-        qkv = _conv(x, torch.cat([a.linear_q.weight, a.linear_k.weight, a.linear_v.weight], 0),
-                    torch.cat([a.linear_q.bias, a.linear_k.bias, a.linear_v.bias], 0))
+        ver = tuple(t._version for t in (a.linear_q.weight, a.linear_k.weight, a.linear_v.weight, a.linear_q.bias)) + (str(x.device),)
+        if getattr(a, '_qkv_ver', None) != ver:                     # one projection for q, k and v: weights concatenated once per update
+            a._qkv_w = torch.cat([a.linear_q.weight, a.linear_k.weight, a.linear_v.weight], 0).detach()[:, :, None].contiguous()
+            a._qkv_b = torch.cat([a.linear_q.bias, a.linear_k.bias, a.linear_v.bias], 0).detach().contiguous()
+            a._qkv_ver = ver
+        qkv = _conv(x, a._qkv_w, a._qkv_b)
         q, k, v = (t.contiguous() for t in qkv.split(H, 1))
         p = _conv(p_emb[None], a.linear_pos.weight, None)[0].contiguous()                        # linear_pos(pos_emb), [H, T]
         ctx = torch.empty_like(q)
