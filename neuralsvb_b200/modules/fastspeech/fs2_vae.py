@@ -278,7 +278,8 @@ class GlobalFVAE(nn.Module):
             return self.decoder(z_p, 1, g), z_p
         z_q, m_q, logs_q, x_mask_sqz = self.encoder(x, x_mask, g_sqz, eps=eps)                          # :22
         x_recon = self.decoder(z_q, x_mask, g)                                                          # :23
-        q_dist = torch.distributions.Normal(m_q, logs_q.exp())
-        loss_kl = torch.distributions.kl_divergence(q_dist, torch.distributions.Normal(0, 1))          # :38-39
+        # validate_args=False: the argument check of torch.distributions is a device -> host synchronisation per call
+        q_dist = torch.distributions.Normal(m_q, logs_q.exp(), validate_args=False)
+        loss_kl = torch.distributions.kl_divergence(q_dist, torch.distributions.Normal(0.0, 1.0, validate_args=False))   # :38-39
         loss_kl = (loss_kl * x_mask_sqz).sum() / x_mask_sqz.sum() / z_q.shape[1]
         return x_recon, loss_kl, None, m_q, logs_q, x_mask_sqz, z_q

@@ -133,7 +133,7 @@ class MleSVBVAE(nn.Module):
         if 'a2p' in ways:
             z = a2a['z_q']
             mapped = z if disable_map else self.z_mapping_function(z, ac['h_style'].transpose(1, 2))
-            prof = torch.distributions.Normal(p2p['m_q'], p2p['logs_q'].exp())
+            prof = torch.distributions.Normal(p2p['m_q'], p2p['logs_q'].exp(), validate_args=False)      # no host sync
             out = {'mle': -prof.log_prob(mapped).sum() / mapped.shape[0] / mapped.shape[1]}
             align = a2p_alignment[:, :, None].repeat(1, 1, self.hidden_size)
             g = self._cond_sum([pc['h_pitch'], torch.gather(ac['h_content'], 1, align),

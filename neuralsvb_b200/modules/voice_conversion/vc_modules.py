@@ -21,12 +21,25 @@ class _Holder(nn.Module):
     """Name-space node: carries sub-modules / parameters under the reference's attribute names, never called."""
 
 
+USE_TC = True        # dense convolutions / linears with >= 32 frames run on the tcgen05 layer kernel (split-bf16, fp32 accumulate)
+
+
 def _conv(x, weight, bias, K=1, stride=1, pad=0, groups=1, relu=False):
-    from neuralsvb_b200.modules.hifigan.discriminators import conv_nct
+    """Conv1d / Linear on [B, C, T] through the C ABI: the tensor-core layer handle (svb_tc_layer_*, one per weight tensor, re-packed
+    only when the weight changes) when the shape qualifies, else the fp32 CUDA-core kernel (svb_conv_nct_forward)."""
+    from neuralsvb_b200.modules.hifigan import discriminators as D
     w = weight if weight.dim() == 3 else weight[:, :, None]
     if bias is None:
-        bias = torch.zeros(w.shape[0], device=x.device)
-    return conv_nct(x, w, bias, K, stride=stride, pad=pad, groups=groups, slope=0.0 if relu else 1.0)
+        bias = getattr(weight, '_svb_zero_bias', None)
+        if bias is None or bias.device != x.device:
+            bias = weight._svb_zero_bias = torch.zeros(w.shape[0], device=x.device)
+    slope = 0.0 if relu else 1.0
+    if USE_TC and groups == 1 and x.shape[2] >= 32 and D.tc_eligible(w.shape[1], w.shape[0], K, stride, 1, pad, 1):
+        layer = getattr(weight, '_svb_tc_layer', None)
+        if layer is None:
+            layer = weight._svb_tc_layer = D.TcLayer()
+        return D.conv_tc(x, w, bias, layer, K, stride, pad, slope, 1)
+    return D.conv_nct(x, w, bias, K, stride=stride, pad=pad, groups=groups, slope=slope)
 
 
 def _bn_affine(bn, x):
