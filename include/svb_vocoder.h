@@ -365,6 +365,15 @@ int svb_relpos_attention_nct(const float *q_dev, const float *k_dev, const float
                              const float *bias_v_dev, const float *mask_dev, int32_t B, int32_t C, int32_t T, int32_t n_head,
                              float *out_dev, void *stream);
 
+/* Host-only view of the schedule of a merged tensor-core launch (csrc/conv_tc.cu: tc_schedule; no CUDA call, usable without a GPU):
+ * `n_layers` convolutions of one shape class (taps KS[l], residual / accumulate flags) over B clips x Tq rows, tiles of 128 rows in
+ * items of up to MT tiles, `col_blocks` column blocks, `grid` CTAs.  items_out receives 5 ints per item (layer, column block, clip,
+ * first row, tiles) in execution order, off_out [grid + 1] the item range of every CTA, balance_out the mean / max estimated load.
+ * Returns the item count or a negative status. */
+int64_t svb_tc_schedule_probe(int32_t n_layers, const int32_t *KS, const int32_t *has_res, const int32_t *accumulate, int32_t Cin, int32_t B,
+                              int32_t Tq, int32_t MT, int32_t col_blocks, int32_t chain_ordered, int32_t grid, int32_t *items_out,
+                              int64_t items_capacity, int32_t *off_out, double *balance_out);
+
 #ifdef __cplusplus
 }
 #endif

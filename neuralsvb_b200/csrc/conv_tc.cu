@@ -915,30 +915,31 @@ void tc_worklist_free(TcWorkList *wl) {
     *wl = TcWorkList();
 }
 
-int tc_worklist_build(int n, const TcWeights *const *w, const ConvArgs *a, int precision, bool chain_ordered, TcWorkList *out) {
-    TcArgs p;
-    size_t smem = 0;
-    SVB_TRY(tc_plan(n, w, a, precision, p, smem));
-    const int grid = sm_count();
-    const int tiles = (a[0].Tq + kTcM - 1) / kTcM;
+// The schedule itself is plain host code (no CUDA call): exposed for the CPU tests through svb_tc_schedule_probe.
+int tc_schedule(int n, const int *KS, const int *has_res, const int *accum, int Cin, int B, int Tq, int MT, int col_blocks, bool chain_ordered,
+                int grid, std::vector<int4> *items_out, std::vector<int> *off_out, double *balance_out) {
+    const int tiles = (Tq + kTcM - 1) / kTcM;
     // cost of an item in "taps of one tile": the MMA work plus a constant for the memory-bound part (slab, epilogue)
-    const double beta = 160.0 / std::max(32, a[0].Cin);
+    const double beta = 160.0 / std::max(32, Cin);
     struct Unit {
         double cost;
         int nblk, b, t0, mt, layer;     // layer < 0: all layers in order (chain-ordered unit)
     };
+    auto unit_cost = [&](int layer, int mt) {
+        if (layer >= 0) return mt * (KS[layer] + beta + (has_res[layer] ? 1.0 : 0.0));
+        double c = 0;
+        for (int l = 0; l < n; ++l) c += mt * (KS[l] + beta + (has_res[l] ? 1.0 : 0.0) + (accum[l] ? 1.0 : 0.0));
+        return c;
+    };
     std::vector<Unit> units;
-    for (int nblk = 0; nblk < p.col_blocks; ++nblk)
-        for (int b = 0; b < a[0].B; ++b)
-            for (int t = 0; t < tiles; t += p.MT) {
-                const int mt = std::min(p.MT, tiles - t);
+    for (int nblk = 0; nblk < col_blocks; ++nblk)
+        for (int b = 0; b < B; ++b)
+            for (int t = 0; t < tiles; t += MT) {
+                const int mt = std::min(MT, tiles - t);
                 if (chain_ordered) {
-                    double c = 0;
-                    for (int l = 0; l < n; ++l) c += mt * (a[l].KS + beta + (a[l].res ? 1.0 : 0.0) + (a[l].accumulate ? 1.0 : 0.0));
-                    units.push_back({c, nblk, b, t * kTcM, mt, -1});
+                    units.push_back({unit_cost(-1, mt), nblk, b, t * kTcM, mt, -1});
                 } else {
-                    for (int l = 0; l < n; ++l)
-                        units.push_back({mt * (a[l].KS + beta + (a[l].res ? 1.0 : 0.0)), nblk, b, t * kTcM, mt, l});
+                    for (int l = 0; l < n; ++l) units.push_back({unit_cost(l, mt), nblk, b, t * kTcM, mt, l});
                 }
             }
     // longest processing time first onto the least-loaded CTA.  Experiment kept behind SVB_TC_SPLIT=1: when the units are
@@ -947,12 +948,6 @@ int tc_worklist_build(int n, const TcWeights *const *w, const ConvArgs *a, int p
     // a one-tile item streams every weight tile for half the rows.
     std::vector<double> load;
     std::vector<std::vector<int>> mine;
-    auto unit_cost = [&](int layer, int mt) {
-        if (layer >= 0) return mt * (a[layer].KS + beta + (a[layer].res ? 1.0 : 0.0));
-        double c = 0;
-        for (int l = 0; l < n; ++l) c += mt * (a[l].KS + beta + (a[l].res ? 1.0 : 0.0) + (a[l].accumulate ? 1.0 : 0.0));
-        return c;
-    };
     double balance = 0;
     for (int round = 0; round < 4; ++round) {
         std::stable_sort(units.begin(), units.end(), [](const Unit &x, const Unit &y) { return x.cost > y.cost; });
@@ -982,8 +977,10 @@ int tc_worklist_build(int n, const TcWeights *const *w, const ConvArgs *a, int p
         }
         if (!split) break;
     }
-    std::vector<int4> items;
-    std::vector<int> off(grid + 1, 0);
+    std::vector<int4> &items = *items_out;
+    std::vector<int> &off = *off_out;
+    items.clear();
+    off.assign(grid + 1, 0);
     for (int c = 0; c < grid; ++c) {
         // neighbours in time next to each other (their halos share L2 lines)
         std::sort(mine[c].begin(), mine[c].end(), [&](int x, int y) {
@@ -1023,6 +1020,21 @@ int tc_worklist_build(int n, const TcWeights *const *w, const ConvArgs *a, int p
         off[c + 1] = (int)items.size();
         SVB_CHECK(off[c + 1] - off[c] <= kMaxItems, SVB_ERR_INVALID, "tc conv: %d work items on one CTA (limit %d)", off[c + 1] - off[c], kMaxItems);
     }
+    *balance_out = balance;
+    return SVB_OK;
+}
+
+int tc_worklist_build(int n, const TcWeights *const *w, const ConvArgs *a, int precision, bool chain_ordered, TcWorkList *out) {
+    TcArgs p;
+    size_t smem = 0;
+    SVB_TRY(tc_plan(n, w, a, precision, p, smem));
+    const int grid = sm_count();
+    int KS[kTcMaxLayers], has_res[kTcMaxLayers], accum[kTcMaxLayers];
+    for (int l = 0; l < n; ++l) KS[l] = a[l].KS, has_res[l] = a[l].res != nullptr, accum[l] = a[l].accumulate;
+    std::vector<int4> items;
+    std::vector<int> off;
+    double balance = 0;
+    SVB_TRY(tc_schedule(n, KS, has_res, accum, a[0].Cin, a[0].B, a[0].Tq, p.MT, p.col_blocks, chain_ordered, grid, &items, &off, &balance));
     tc_worklist_free(out);
     SVB_CUDA(cudaMalloc((void **)&out->items, std::max<size_t>(items.size(), 1) * sizeof(int4)));
     SVB_CUDA(cudaMalloc((void **)&out->off, off.size() * sizeof(int)));
@@ -1046,3 +1058,26 @@ int launch_conv_tc_multi(int n, const TcWeights *const *w, const ConvArgs *a, in
 }
 
 }  // namespace svb
+
+// Host-only view of the merged-launch schedule (no CUDA call): used by the CPU tests to check that every (layer, tile) is
+// scheduled exactly once, that chain-ordered lists keep the layers of a tile together and in order, and the LPT balance.
+extern "C" int64_t svb_tc_schedule_probe(int32_t n_layers, const int32_t *KS, const int32_t *has_res, const int32_t *accumulate, int32_t Cin,
+                                         int32_t B, int32_t Tq, int32_t MT, int32_t col_blocks, int32_t chain_ordered, int32_t grid,
+                                         int32_t *items_out, int64_t items_capacity, int32_t *off_out, double *balance_out) {
+    SVB_CHECK(n_layers >= 1 && n_layers <= svb::kTcMaxLayers && KS && has_res && accumulate && B > 0 && Tq > 0 && (MT == 1 || MT == 2) &&
+                  col_blocks >= 1 && grid >= 1 && items_out && off_out && balance_out,
+              SVB_ERR_INVALID, "tc_schedule_probe: bad argument");
+    std::vector<int4> items;
+    std::vector<int> off;
+    int ks[svb::kTcMaxLayers], hr[svb::kTcMaxLayers], ac[svb::kTcMaxLayers];
+    for (int l = 0; l < n_layers; ++l) ks[l] = KS[l], hr[l] = has_res[l], ac[l] = accumulate[l];
+    SVB_TRY(svb::tc_schedule(n_layers, ks, hr, ac, Cin, B, Tq, MT, col_blocks, chain_ordered != 0, grid, &items, &off, balance_out));
+    SVB_CHECK((int64_t)items.size() <= items_capacity, SVB_ERR_INVALID, "tc_schedule_probe: %zu items, capacity %lld", items.size(),
+              (long long)items_capacity);
+    for (size_t i = 0; i < items.size(); ++i) {
+        int32_t *o = items_out + 5 * i;                             // layer, column block, clip, first row, tiles
+        o[0] = items[i].x & 0xff, o[1] = (items[i].x >> 8) & 0xffff, o[2] = items[i].y, o[3] = items[i].z, o[4] = items[i].x >> 24;
+    }
+    for (int c = 0; c <= grid; ++c) off_out[c] = off[c];
+    return (int64_t)items.size();
+}

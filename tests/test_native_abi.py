@@ -94,3 +94,57 @@ def test_training_entry_points_validate_arguments_without_gpu(built):
     assert l.svb_denoise(ctypes.byref(c), None, 1, 4096, f(0.1), None, None) < 0
     c.n_fft = 1000
     assert l.svb_stft_backward(ctypes.byref(c), None, 1, 4096, None, None, None, None) < 0 and b'power of two' in l.svb_last_error()
+
+
+def _schedule(KS, has_res, accum, B, Tq, MT, col_blocks, chain_ordered, grid=148, Cin=128):
+    import ctypes
+
+    import numpy as np
+    from neuralsvb_b200 import _native
+    n = len(KS)
+    arr = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+    ks, hr, ac = arr(KS), arr(has_res), arr(accum)
+    cap = 200000
+    items, off, bal = np.zeros((cap, 5), np.int32), np.zeros(grid + 1, np.int32), ctypes.c_double()
+    cnt = _native.check(_native.lib().svb_tc_schedule_probe(n, ks.ctypes.data, hr.ctypes.data, ac.ctypes.data, Cin, B, Tq, MT, col_blocks,
+                                                            int(chain_ordered), grid, items.ctypes.data, cap, off.ctypes.data, ctypes.byref(bal)),
+                        'tc_schedule_probe')
+    return items[:cnt], off, bal.value
+
+
+def test_merged_launch_schedule_covers_every_tile_once():
+    """Host logic of the merged ResBlock-chain launches (csrc/conv_tc.cu:tc_schedule), no GPU needed: the three chains of stage 1 of
+    config 2 (C = 128: k 3 / 7 / 11, 16 clips x 8192 rows)."""
+    import numpy as np
+    items, off, bal = _schedule([3, 7, 11], [0, 0, 0], [0, 0, 0], 16, 8192, 2, 1, False)
+    assert len(items) == 3 * 16 * 32 and off[0] == 0 and off[-1] == len(items)
+    seen = set(map(tuple, items[:, :4]))
+    assert len(seen) == len(items)                                           # no (layer, block, clip, row) twice
+    for l in range(3):
+        rows = items[items[:, 0] == l]
+        assert sorted(map(tuple, rows[:, 2:4])) == [(b, t) for b in range(16) for t in range(0, 8192, 256)]
+    assert (items[:, 4] == 2).all() and bal > 0.95
+    assert (np.diff(off) <= 120).all()
+    # a CTA alternates its layers instead of running them one after the other
+    first = items[off[0]:off[1], 0]
+    assert len(set(first[:3].tolist())) > 1
+
+
+def test_chain_ordered_schedule_keeps_the_layers_of_a_tile_together():
+    """The step that accumulates the three ResBlocks into the stage output: every CTA runs layers 0, 1, 2 of a tile back to back."""
+    items, off, bal = _schedule([3, 7, 11], [1, 1, 1], [0, 1, 1], 16, 1024, 2, 2, True, Cin=256)
+    assert len(items) == 3 * 16 * 4 * 2
+    for c in range(len(off) - 1):
+        mine = items[off[c]:off[c + 1]]
+        assert len(mine) % 3 == 0
+        for i in range(0, len(mine), 3):
+            assert mine[i:i + 3, 0].tolist() == [0, 1, 2]
+            assert (mine[i:i + 3, 1:] == mine[i, 1:]).all()                    # same column block, clip, row, tiles
+    assert 0.8 < bal <= 1.0
+
+
+def test_schedule_handles_an_odd_tile_count():
+    items, off, bal = _schedule([3, 11], [0, 0], [0, 0], 3, 5 * 128 - 7, 2, 1, False, grid=8)
+    tiles = items[:, 4]
+    assert set(tiles.tolist()) == {1, 2}                                      # the last item of a clip has one tile
+    assert int(tiles.sum()) == 2 * 3 * 5
