@@ -170,3 +170,57 @@ def test_indexed_dataset_format_and_vocoder_loader(tmp_path):
     r0 = {n for r, names in seen if r == 0 for n in names}
     r1 = {n for r, names in seen if r == 1 for n in names}
     assert not (r0 & r1) and len(r0) == len(r1) == 4                           # disjoint shards of the same global batches
+
+
+# ---- SVB acoustic model drop-ins: host-side contracts that need no GPU
+def test_acoustic_modules_refuse_cpu_tensors_and_training_mode():
+    """No CPU / PyTorch fallback in the product: the drop-in classes raise instead of silently computing elsewhere."""
+    import pytest
+    import torch
+    from neuralsvb_b200.modules.fastspeech.fs2_vae import WN, FVAEDecoder
+    from neuralsvb_b200.modules.voice_conversion.vc_modules import VCASR
+    wn = WN(64, 3, 1, 2).eval()
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        with torch.no_grad():
+            wn(torch.zeros(1, 64, 16))
+    dec = FVAEDecoder(16, 64, 80, 3, 2).eval()
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        with torch.no_grad():
+            dec(torch.zeros(1, 16, 4), 1, None)
+    asr = VCASR(80, 80, hidden_size=64, asr_enc_layers=1, mel_strides=[2, 1, 1], asr_last_norm=False)
+    with pytest.raises(RuntimeError, match='inference only'):
+        asr.train()(torch.zeros(1, 8, 80))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        with torch.no_grad():
+            asr.eval()(torch.zeros(1, 8, 80))
+    with pytest.raises(NotImplementedError):
+        WN(64, 3, 1, 2, share_cond_layers=True)
+
+
+def test_vc_asr_ignores_the_token_decoder_of_a_reference_checkpoint():
+    """vc_modules.py:69-74 of the reference also owns an ASR token decoder (training head); its checkpoint keys must not break loading."""
+    import torch
+    from neuralsvb_b200.modules.voice_conversion.vc_modules import VCASR
+    from neuralsvb_b200.utils import synthetic as S
+    sd = S.make_vc_asr_state_dict(1234)
+    sd['asr_decoder.layers.0.self_attn.in_proj_weight'] = torch.zeros(3)
+    sd['token_embed.weight'] = torch.zeros(80, 256)
+    m = VCASR(80, 80, hidden_size=256, asr_enc_layers=2, mel_strides=[2, 1, 1], asr_last_norm=False)
+    m.load_state_dict(sd, strict=True)
+    assert torch.equal(m.content_encoder.encoder_layers[1].self_attn.pos_bias_u, sd['content_encoder.encoder_layers.1.self_attn.pos_bias_u'])
+    assert isinstance(m.content_encoder.layer_norm, torch.nn.Linear)          # asr_last_norm false (vc_ppg.yaml:16)
+    assert isinstance(VCASR(80, 80, hidden_size=64, asr_enc_layers=1, mel_strides=[2, 1, 1], asr_last_norm=True).content_encoder.layer_norm,
+                      torch.nn.LayerNorm)
+
+
+def test_wn_state_dict_names_before_and_after_weight_norm_removal():
+    from neuralsvb_b200.modules.fastspeech.fs2_vae import WN
+    from neuralsvb_b200.utils import synthetic as S
+    m = WN(64, 3, 2, 3, gin_channels=32)
+    sd = S.make_wn_state_dict(64, 3, 3, 32, 1234)
+    assert set(m.state_dict()) == set(sd)
+    m.load_state_dict(sd, strict=True)
+    m.remove_weight_norm()
+    names = set(m.state_dict())
+    assert 'cond_layer.weight' in names and 'in_layers.2.weight' in names and not any(k.endswith(('weight_g', 'weight_v')) for k in names)
+    assert tuple(m.state_dict()['res_skip_layers.2.weight'].shape) == (64, 64, 1)      # the last layer has no skip half (fs2_vae.py:52-55)
